@@ -1,0 +1,1128 @@
+// fslr_b200 — B200 (sm_100a) implementation of the read-clustering step of kcleal/fslr.
+//
+// Replaces, behind the C ABI of include/fslr_b200.h, the reference calls of
+// /root/reference/fslr/main.py:233-257,334-342 into /root/reference/fslr/cluster.py:
+//   keep_fillings (cluster.py:14-31)           -> k_first_last, k_keep, k_compact_rows
+//   prepare_data + mask_sequences2 (:89-121)    -> k_item_keys, radix sort by start, k_mask_flags, k_build_items
+//   query_intervals dict order (:189-191)       -> k_first_dp, k_is_first, scan, sort by query rank
+//   build_interval_trees / IntervalMap (:124-130, third-party superintervals)
+//                                               -> sort by (chrom, start, end desc, data order), k_ub, prefix-max of ends
+//   query_interval_trees (:187-227)             -> k_pair (order-free relation + capped degree) and k_replay
+//                                                  (reads that can reach edge_threshold, in query order)
+//   different_lengths_or_alignments (:178-183), overall_jaccard_similarity (:140-170),
+//   calculate_overlap (:133-136), cutoff lookup (:218-219)
+//                                               -> integer thresholds T/Lq/Ln/umax (k_read_info, k_records, host umax)
+//   get_subgraphs / networkx (:230-234)         -> k_union_entries, k_union_edges, k_flatten (lock-free union-find,
+//                                                  root = smallest query rank = the component's first-inserted node)
+//   cluster / n_reads columns (main.py:251-257,334-342) -> k_roots, k_number
+//
+// Why the sequential reference loop parallelises exactly: a filling's scan of
+// search_values() results covers a contiguous run of sorted positions [stop, ub] walked downwards, so the
+// loop state that later queries can observe is one integer per filling.  Reads whose number of passing
+// candidates is below edge_threshold can never break: their stop is the chromosome start and their edges follow
+// from the order-free relation.  The remaining reads are replayed in query order by a persistent ticket kernel in
+// which a warp only ever waits for reads holding smaller tickets.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "fslr_b200.h"
+
+#define FSLRC_VERSION 1
+#define LMAX FSLRC_MAX_FILLINGS
+
+enum { EF_RANGE = 1, EF_ZERO = 2, EF_TOOMANY = 4, EF_NALN = 8, EF_OVERFLOW = 16 };
+
+// ---------------------------------------------------------------- context
+struct fslrc_ctx {
+    int device;
+    char err[512];
+    cudaStream_t stream;
+    std::vector<void *> allocs;
+    int64_t *h_pin;          // pinned scratch for read-backs (64 x int64)
+    cudaEvent_t ev[FSLRC_N_STAGES + 1];
+    // pipeline state (kept between the fslrc_mg_* stages)
+    struct Pipe *pipe;
+};
+
+static const char *STAGE_NAMES[FSLRC_N_STAGES] = {
+    "h2d", "keep_fillings", "data_order_mask", "query_rank_read_lists", "chrom_sort", "records_bands",
+    "pair_kernel", "saturating_set", "replay", "union_find", "numbering", "d2h"};
+
+static int fail(fslrc_ctx *c, int code, const char *fmt, const char *a = "") {
+    snprintf(c->err, sizeof(c->err), fmt, a);
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return FSLRC_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+template <typename T>
+static int dalloc(fslrc_ctx *ctx, T **p, int64_t n) {
+    void *q = nullptr;
+    size_t bytes = (size_t)(n > 0 ? n : 1) * sizeof(T);
+    CK(cudaMallocAsync(&q, bytes, ctx->stream));
+    ctx->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+static void free_all(fslrc_ctx *ctx) {
+    for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
+    ctx->allocs.clear();
+}
+#define DA(ptr, n)                                  \
+    do {                                            \
+        int r__ = dalloc(ctx, &(ptr), (int64_t)(n)); \
+        if (r__) return r__;                        \
+    } while (0)
+
+static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
+
+// ---------------------------------------------------------------- small utility kernels
+template <typename T>
+__global__ void k_fill(T *p, int64_t n, T v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_iota(int *p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+__global__ void k_total(const int *scan, const int *flag, int n, int64_t *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = n > 0 ? (int64_t)scan[n - 1] + flag[n - 1] : 0;
+}
+
+// exact threshold in the reference's double arithmetic: min{o >= 0 : fl(o/a) >= p}  (cluster.py:133-136,179,181)
+__device__ __forceinline__ int thr_f64(int a, double p) {
+    if (!(p > 0.0)) return 0;
+    double da = (double)a;
+    double x = ceil(__dmul_rn(p, da));
+    if (x >= 2147483000.0) return 2147483647;
+    long long o = (long long)x;
+    while (o > 0 && __ddiv_rn((double)(o - 1), da) >= p) --o;
+    while (__ddiv_rn((double)o, da) < p) ++o;
+    return (int)o;
+}
+
+// ---------------------------------------------------------------- stage 1: keep_fillings (cluster.py:14-31)
+__global__ void k_first_last(int A, int R, const int *__restrict__ rid, int *first, int *last, int *err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    int r = rid[i];
+    if ((unsigned)r >= (unsigned)R) { atomicOr(err, EF_RANGE); return; }
+    atomicMin(&first[r], i);
+    atomicMax(&last[r], i);
+}
+__global__ void k_keep(int A, int R, const int *__restrict__ rid, const int *__restrict__ first, const int *__restrict__ last,
+                       const int *__restrict__ qstart, const int *__restrict__ qend, int *flag, int *qmin, int *qmax) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    int r = rid[i];
+    int keep = 0;
+    if ((unsigned)r < (unsigned)R) {
+        keep = (i != first[r] && i != last[r]);
+        if (keep) { atomicMax(&qmax[r], qend[i]); atomicMin(&qmin[r], qstart[i]); }
+    }
+    flag[i] = keep;
+}
+__global__ void k_compact_rows(int A, const int *__restrict__ flag, const int *__restrict__ pos, int *frow) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A && flag[i]) frow[pos[i]] = i;
+}
+
+// ---------------------------------------------------------------- stage 2: prepare_data + mask (cluster.py:109-121, 89-106)
+__global__ void k_start_keys(int F, const int *__restrict__ frow, const int *__restrict__ rstart, const int *__restrict__ rend, int *key) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < F) { int r = frow[k]; key[k] = min(rstart[r], rend[r]); }
+}
+__global__ void k_check_order(int F, const int *__restrict__ order, int *err) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < F && (unsigned)order[k] >= (unsigned)F) atomicOr(err, EF_RANGE);
+}
+__global__ void k_mask_flags(int F, const int *__restrict__ dk, const int *__restrict__ frow, const int *__restrict__ chrom,
+                             const int *__restrict__ rstart, const int *__restrict__ rend, int n_chrom,
+                             const long long *__restrict__ clen, const unsigned char *__restrict__ cmasked, int sub_on,
+                             long long subtel, int *flag, int *err) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    int row = frow[dk[k]];
+    int c = chrom[row];
+    if ((unsigned)c >= (unsigned)n_chrom) { atomicOr(err, EF_RANGE); flag[k] = 0; return; }
+    int s = min(rstart[row], rend[row]), e = max(rstart[row], rend[row]);
+    if (s < 0) atomicOr(err, EF_RANGE);
+    bool masked = cmasked[c] != 0;                                          // cluster.py:96
+    long long cl = clen[c];
+    if (sub_on && cl > 1000000 && ((long long)s < subtel || cl - (long long)e < subtel)) masked = true;   // :94,98-100
+    flag[k] = masked ? 0 : 1;
+}
+// data items in data order (SoA)
+__global__ void k_build_items(int F, const int *__restrict__ dk, const int *__restrict__ frow, const int *__restrict__ flag,
+                              const int *__restrict__ dpos, const int *__restrict__ rid, const int *__restrict__ chrom,
+                              const int *__restrict__ rstart, const int *__restrict__ rend, const int *__restrict__ aln,
+                              const int *__restrict__ naln, int *it_rid, int *it_chrom, int *it_start, int *it_end, int *it_aln,
+                              int *it_naln, int *firstdp, int *err) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F || !flag[k]) return;
+    int row = frow[dk[k]], d = dpos[k];
+    int r = rid[row];
+    it_rid[d] = r; it_chrom[d] = chrom[row];
+    it_start[d] = min(rstart[row], rend[row]); it_end[d] = max(rstart[row], rend[row]);
+    int a = aln[row], n = naln[row];
+    it_aln[d] = a; it_naln[d] = n;
+    if (a <= 0 || n <= 0) atomicOr(err, EF_ZERO);
+    if (n >= 65535) atomicOr(err, EF_RANGE);
+    atomicMin(&firstdp[r], d);
+}
+
+// ---------------------------------------------------------------- stage 3: query rank (cluster.py:189-191) + per-read lists
+__global__ void k_is_first(int D, const int *__restrict__ it_rid, const int *__restrict__ firstdp, int *flag) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) flag[d] = (firstdp[it_rid[d]] == d);
+}
+__global__ void k_rank_reads(int R, const int *__restrict__ firstdp, const int *__restrict__ rank_at, int *q_of_rid, int *rid_of_q) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int f = firstdp[r];
+    int q = -1;
+    if (f != 0x7fffffff) { q = rank_at[f]; rid_of_q[q] = r; }
+    q_of_rid[r] = q;
+}
+__global__ void k_item_q(int D, const int *__restrict__ it_rid, const int *__restrict__ q_of_rid, int *it_q) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) it_q[d] = q_of_rid[it_rid[d]];
+}
+// rm order: items grouped by query rank, data order inside a read
+__global__ void k_read_bounds(int D, const int *__restrict__ qs /*sorted q*/, const int *__restrict__ rm_dp, int *rmidx, int *off, int *len_end) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= D) return;
+    int q = qs[m];
+    rmidx[rm_dp[m]] = m;
+    if (m == 0 || qs[m - 1] != q) off[q] = m;
+    if (m == D - 1 || qs[m + 1] != q) len_end[q] = m + 1;
+}
+// per read: qlen2, n_alignments and their ratio thresholds (cluster.py:26-29,178-183)
+__global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *__restrict__ off, const int *__restrict__ len_end,
+                            const int *__restrict__ rm_dp, const int *__restrict__ it_naln, const int *__restrict__ qmin,
+                            const int *__restrict__ qmax, double qlen_c, double naln_c, int4 *RD, int4 *RI, int *err) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int r = rid_of_q[q], o = off[q], L = len_end[q] - o;
+    if (L > LMAX) atomicOr(err, EF_TOOMANY);
+    long long ql = (long long)qmax[r] - (long long)qmin[r];
+    int na = it_naln[rm_dp[o]];
+    if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
+    if (ql > 0x7fffffffLL) { atomicOr(err, EF_RANGE); ql = 1; }
+    int Ln = thr_f64(na, naln_c);
+    if (Ln > 65535) Ln = 65535;
+    RD[q] = make_int4(o, L, r, 0);
+    RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), 0);
+}
+__global__ void k_check_naln(int D, const int *__restrict__ it_q, const int *__restrict__ it_naln, const int4 *__restrict__ RI, int *err) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D && (RI[it_q[d]].z & 0xffff) != it_naln[d]) atomicOr(err, EF_NALN);
+}
+
+// ---------------------------------------------------------------- stage 4/5: IntervalMap order + records + bands
+__global__ void k_end_keys(int D, const int *__restrict__ it_end, unsigned *key) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) key[d] = ~(unsigned)it_end[d];                       // ascending ~end == end descending
+}
+__global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const int *__restrict__ it_chrom, const int *__restrict__ it_start,
+                                   unsigned long long *key) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < D) { int d = dp_in[k]; key[k] = ((unsigned long long)(unsigned)it_chrom[d] << 32) | (unsigned)it_start[d]; }
+}
+// SR0[p] = {start, end, T, q}; SR1[p] = {qlen2, Lq, naln | Ln<<16, m}; RM0[m] = {chrom, start, end, T}; RM1[m] = {pos, ub}
+__global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
+                          const int *__restrict__ it_chrom, const int *__restrict__ it_start, const int *__restrict__ it_end,
+                          const int *__restrict__ it_aln, const int4 *__restrict__ RI, double overlap, int4 *SR0, int4 *SR1,
+                          int4 *RM0, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    int d = s_dp[p], m = rmidx[d], q = it_q[d], c = it_chrom[d];
+    int s = it_start[d], e = it_end[d];
+    int T = thr_f64(max(it_aln[d], 1), overlap);
+    int4 ri = RI[q];
+    SR0[p] = make_int4(s, e, T, q);
+    SR1[p] = make_int4(ri.x, ri.y, ri.z, m);
+    RM0[m] = make_int4(c, s, e, T);
+    s_chrom[p] = c; s_end[p] = e;
+    int cprev = p > 0 ? it_chrom[s_dp[p - 1]] : -1;
+    int cnext = p < D - 1 ? it_chrom[s_dp[p + 1]] : -1;
+    if (cprev != c) chrom_lo[c] = p;
+    if (cnext != c) chrom_hi[c] = p + 1;
+}
+// ub(p): last sorted position on the chromosome with start <= end_p  (IntervalMap upper bound)
+__global__ void k_ub(int D, const int4 *__restrict__ SR0, const int4 *__restrict__ SR1, const int *__restrict__ s_chrom,
+                     const int *__restrict__ chrom_hi, int *ubS, int2 *RM1, unsigned long long *band_pairs) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    long long mine = 0;
+    if (p < D) {
+        int e = SR0[p].y;
+        int lo = p, hi = chrom_hi[s_chrom[p]];                    // invariant: start[lo] <= e, answer in [lo, hi)
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (SR0[mid].x <= e) lo = mid; else hi = mid; }
+        ubS[p] = lo;
+        RM1[SR1[p].w] = make_int2(p, lo);
+        mine = lo - p;
+    }
+    typedef cub::BlockReduce<long long, 256> BR;
+    __shared__ typename BR::TempStorage tmp;
+    long long s = BR(tmp).Sum(mine);
+    if (threadIdx.x == 0 && s) atomicAdd(band_pairs, (unsigned long long)s);
+}
+struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
+
+// ---------------------------------------------------------------- pair-level pieces
+struct Tab {                 // kernel-side view of the tables
+    const int4 *SR0, *SR1, *RM0, *RD;
+    const int2 *RM1;
+    const int *ubS, *pmaxS, *s_chrom, *chrom_lo;
+    int D, Q, Tedge;
+};
+__constant__ int c_umax[LMAX + 1];
+
+// a (query, its fillings A[0..La) in shared memory) against b's fillings in RM0[offb..offb+Lb):
+// greedy first-fit count of cluster.py:152-161 plus the lexicographically first matching filling pair
+__device__ __forceinline__ int greedy_ab(const int4 *A, int La, const int4 *__restrict__ B, int Lb, int *first_fa, int *first_fb) {
+    unsigned long long used = 0;
+    int n = 0, ffa = -1, ffb = -1;
+    for (int fa = 0; fa < La; fa++) {
+        int4 a = A[fa];
+        for (int fb = 0; fb < Lb; fb++) {
+            int4 b = __ldg(&B[fb]);
+            int ov = min(a.z, b.z) - max(a.y, b.y);
+            bool m = (a.x == b.x) && (max(ov, 0) >= max(a.w, b.w));
+            if (m) {
+                if (ffa < 0) { ffa = fa; ffb = fb; }
+                if (!((used >> fb) & 1ull)) { used |= 1ull << fb; n++; break; }
+            }
+        }
+    }
+    *first_fa = ffa; *first_fb = ffb;
+    return n;
+}
+__device__ __forceinline__ bool difflen_ok(int qa, int Lqa, int nla, int qb, int Lqb, int nlb) {
+    bool q_ok = min(qa, qb) >= max(Lqa, Lqb);
+    bool n_ok = min(nla & 0xffff, nlb & 0xffff) >= max((nla >> 16) & 0xffff, (nlb >> 16) & 0xffff);
+    return q_ok || n_ok;                                           // cluster.py:178-183 (skip only if both fail)
+}
+
+// ---------------------------------------------------------------- stage 6: pair kernel (order-free relation)
+// One warp per sorted interval i (read a): scans a's closed band in chunks of 32 sorted positions, keeps lanes whose
+// interval reciprocally overlaps i (the only way a read pair can ever match), and for the canonical (first matching)
+// filling pair evaluates pass(a -> b).  Per read it counts passing candidates (capped: once the count reaches
+// edge_threshold the read is "saturating" and is replayed later, so its scan stops) and records (a, b).
+#define PAIR_WARPS 8
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(Tab t, int shard, int nshard, int *degub, int2 *entries,
+                                                           unsigned long long *n_entries, unsigned long long cap_entries,
+                                                           unsigned long long *n_tests, int *err) {
+    __shared__ int4 As[PAIR_WARPS][LMAX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gw = blockIdx.x * PAIR_WARPS + w, nw = gridDim.x * PAIR_WARPS;
+    unsigned long long tests = 0;
+    for (int i = gw; i < t.D; i += nw) {
+        if (nshard > 1 && ((i >> 6) % nshard) != shard) continue;
+        const int4 s0 = t.SR0[i], s1 = t.SR1[i];
+        const int a = s0.w;
+        const int4 rda = __ldg(&t.RD[a]);
+        const int La = rda.y, fia = s1.w - rda.x;
+        __syncwarp();
+        for (int k = lane; k < La; k += 32) As[w][k] = __ldg(&t.RM0[rda.x + k]);
+        __syncwarp();
+        const int lo = t.chrom_lo[t.s_chrom[i]];
+        for (int base = t.ubS[i]; base >= lo; base -= 32) {
+            if (t.pmaxS[base] < s0.x) break;                                       // nothing further down reaches start_i
+            int deg = *(volatile int *)&degub[a];
+            if (deg >= t.Tedge) break;                                             // saturating: replayed in query order
+            const int p = base - lane;
+            bool v = (p >= lo) && (p != i);
+            int4 c0 = make_int4(0, 0, 0, 0);
+            if (v) c0 = __ldg(&t.SR0[p]);
+            const int b = c0.w;
+            int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
+            v = v && (b != a) && (max(ov, 0) >= max(s0.z, c0.z));                   // this interval pair matches (cluster.py:157)
+            bool pass = false;
+            if (v) {
+                const int4 c1 = __ldg(&t.SR1[p]);
+                if (difflen_ok(s1.x, s1.y, s1.z, c1.x, c1.y, c1.z)) {
+                    const int4 rdb = __ldg(&t.RD[b]);
+                    int ffa, ffb;
+                    int n = greedy_ab(As[w], La, t.RM0 + rdb.x, rdb.y, &ffa, &ffb);
+                    if (ffa == fia && ffb == c1.w - rdb.x) {                         // canonical filling pair of (a, b)
+                        tests++;
+                        pass = n > 0 && (La + rdb.y - n) <= c_umax[n];               // cluster.py:165-170,218-219
+                    }
+                }
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, pass);
+            if (pm) {
+                int old = 0;
+                if (lane == 0) old = atomicAdd(&degub[a], __popc(pm));
+                old = __shfl_sync(0xffffffffu, old, 0);
+                const bool rec = pass && (old + __popc(pm & ((1u << lane) - 1u)) < t.Tedge);
+                const unsigned rm = __ballot_sync(0xffffffffu, rec);
+                if (rm) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(n_entries, (unsigned long long)__popc(rm));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (rec) {
+                        unsigned long long k = at + __popc(rm & ((1u << lane) - 1u));
+                        if (k < cap_entries) entries[k] = make_int2(a, b); else atomicOr(err, EF_OVERFLOW);
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
+    if (lane == 0 && tests) atomicAdd(n_tests, tests);
+}
+
+// ---------------------------------------------------------------- stage 7: saturating set
+__global__ void k_satur_flags(int Q, const int *__restrict__ degub, int Tedge, int *isP) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) isP[q] = degub[q] >= Tedge;
+}
+__global__ void k_compact_flagged(int n, const int *__restrict__ flag, const int *__restrict__ pos, int *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = i;
+}
+
+// did read b's own query scan reach one of a's intervals?  (stops of b must be final)
+__device__ __forceinline__ bool visited_ba(const int4 *__restrict__ RM0, const int2 *__restrict__ RM1, const int *stop, int offb, int Lb,
+                                           const int4 *A0, const int2 *A1, int La) {
+    for (int f = 0; f < Lb; f++) {
+        const int4 bf = __ldg(&RM0[offb + f]);
+        const int ubf = __ldg(&RM1[offb + f]).y;
+        const int sf = __ldcg(&stop[offb + f]);
+        for (int g = 0; g < La; g++) {
+            const int4 ag = A0[g];
+            const int pg = A1[g].x;
+            if (ag.x == bf.x && sf <= pg && pg <= ubf && ag.z >= bf.y) return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- stage 8: replay of saturating reads in query order
+// Persistent ticket kernel: plist holds the saturating reads in ascending query rank; a warp takes the next ticket,
+// re-runs that read's query exactly as cluster.py:197-224 would (descending sorted positions per filling, seen
+// pairs skipped, edges counted, break), and publishes the read's stops.  Whether an earlier-ranked saturating read b
+// "saw" the pair first is a function of b's stops, so a lane waits (spin on final[b]) only for smaller tickets.
+#define REPLAY_WARPS 4
+__global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, const int *__restrict__ isP,
+                                                               int *stop, int *final_, unsigned *ticket, int2 *pedges,
+                                                               unsigned long long *n_pedges, unsigned long long cap_pedges,
+                                                               unsigned long long *n_tests, int *err) {
+    __shared__ int4 A0[REPLAY_WARPS][LMAX];
+    __shared__ int2 A1[REPLAY_WARPS][LMAX];
+    __shared__ int Astop[REPLAY_WARPS][LMAX];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long tests = 0;
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(ticket, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= (unsigned)nP) break;
+        const int a = plist[tk];
+        const int4 rda = __ldg(&t.RD[a]);
+        const int offa = rda.x, La = rda.y;
+        __syncwarp();
+        for (int k = lane; k < La; k += 32) { A0[w][k] = __ldg(&t.RM0[offa + k]); A1[w][k] = __ldg(&t.RM1[offa + k]); }
+        __syncwarp();
+        const int4 ria = __ldg(&t.SR1[A1[w][0].x]);                               // {qlen2, Lq, naln|Ln, m} of a
+        int edges = 0;
+        for (int fi = 0; fi < La; fi++) {
+            const int4 f = A0[w][fi];
+            const int top = A1[w][fi].y;
+            const int lo = t.chrom_lo[f.x];
+            int stopf = lo;
+            for (int base = top; base >= lo; base -= 32) {
+                if (t.pmaxS[base] < f.y) break;
+                const int p = base - lane;
+                bool reach = false, edge = false;
+                int b = -1;
+                if (p >= lo) {
+                    const int4 c0 = __ldg(&t.SR0[p]);
+                    b = c0.w;
+                    if (b != a && c0.y >= f.y) {                // closed overlap (start_p <= end_f by p <= ub)
+                        const int4 c1 = __ldg(&t.SR1[p]);
+                        if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
+                            const int4 rdb = __ldg(&t.RD[b]);
+                            const int offb = rdb.x, Lb = rdb.y;
+                            bool met = false;                                          // pair already seen earlier in this very query?
+                            for (int g = 0; g < Lb && !met; g++) {
+                                const int4 bg = __ldg(&t.RM0[offb + g]);
+                                const int pg = __ldg(&t.RM1[offb + g]).x;
+                                for (int f2 = 0; f2 < fi; f2++) {
+                                    const int4 af = A0[w][f2];
+                                    if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
+                                }
+                                if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
+                            }
+                            if (!met) {
+                                int ffa, ffb;
+                                const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
+                                tests++;
+                                if (n > 0) {
+                                    reach = true;
+                                    if (b < a) {                                       // b queried first: did it get here?
+                                        if (!__ldg(&isP[b])) reach = false;            // never breaks -> it saw the pair
+                                        else {
+                                            while (*(volatile int *)&final_[b] == 0) __nanosleep(100);
+                                            __threadfence();
+                                            if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
+                                        }
+                                    }
+                                    edge = reach && (La + Lb - n) <= c_umax[n];
+                                }
+                            }
+                        }
+                    }
+                }
+                const unsigned M = __ballot_sync(0xffffffffu, reach), E = __ballot_sync(0xffffffffu, edge);
+                int brk = -1;
+                for (unsigned mm = M; mm; mm &= mm - 1) {                              // cluster.py:219-224 in scan order
+                    const int l = __ffs(mm) - 1;
+                    if (edges + __popc(E & ((2u << l) - 1u)) >= t.Tedge) { brk = l; break; }
+                }
+                const unsigned Euse = brk >= 0 ? (E & ((2u << brk) - 1u)) : E;
+                if (Euse) {
+                    unsigned long long at = 0;
+                    if (lane == 0) at = atomicAdd(n_pedges, (unsigned long long)__popc(Euse));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if ((Euse >> lane) & 1u) {
+                        unsigned long long k = at + __popc(Euse & ((1u << lane) - 1u));
+                        if (k < cap_pedges) pedges[k] = make_int2(a, b); else atomicOr(err, EF_OVERFLOW);
+                    }
+                }
+                edges += __popc(Euse);
+                if (brk >= 0) { stopf = base - brk; break; }
+            }
+            if (lane == 0) Astop[w][fi] = stopf;
+            __syncwarp();
+        }
+        for (int k = lane; k < La; k += 32) stop[offa + k] = Astop[w][k];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) { *(volatile int *)&final_[a] = 1; }
+    }
+    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
+    if (lane == 0 && tests) atomicAdd(n_tests, tests);
+}
+
+// ---------------------------------------------------------------- stage 9: union-find (root = smallest query rank)
+__device__ __forceinline__ int uf_find(int *parent, int x) {
+    for (;;) {
+        int p = *(volatile int *)&parent[x];
+        if (p == x) return x;
+        int gp = *(volatile int *)&parent[p];
+        if (gp != p) atomicMin(&parent[x], gp);                                      // path halving, keeps parent <= index
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int tmp = a; a = b; b = tmp; }                                  // hook the larger root under the smaller
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+// entries (a, b) recorded by k_pair: a not saturating; b > a -> a tested it (edge); b < a -> edge only if b is
+// saturating and its scan stopped before reaching a (then a's query tested the pair, direction a -> b)
+__global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP, Tab t,
+                                const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    bool e = false;
+    if (k < n) {
+        const int2 ab = entries[k];
+        const int a = ab.x, b = ab.y;
+        if (!isP[a]) {
+            if (b > a) e = true;
+            else if (isP[b]) {
+                const int4 rda = t.RD[a], rdb = t.RD[b];
+                e = true;
+                for (int f = 0; f < rdb.y && e; f++) {
+                    const int4 bf = t.RM0[rdb.x + f];
+                    const int ubf = t.RM1[rdb.x + f].y, sf = stop[rdb.x + f];
+                    for (int g = 0; g < rda.y; g++) {
+                        const int4 ag = t.RM0[rda.x + g];
+                        const int pg = t.RM1[rda.x + g].x;
+                        if (ag.x == bf.x && sf <= pg && pg <= ubf && ag.z >= bf.y) { e = false; break; }
+                    }
+                }
+            }
+        }
+        if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_edges, (unsigned long long)__popc(m));
+}
+__global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int2 ab = edges[k];
+    ing[ab.x] = 1; ing[ab.y] = 1;
+    uf_union(parent, ab.x, ab.y);
+}
+__global__ void k_flatten(int Q, int *parent, const int *__restrict__ ing, int *isroot, int *csize) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int r = uf_find(parent, q);
+    parent[q] = r;                                                                  // safe: r is a root and stays one
+    isroot[q] = (ing[q] && r == q);
+    if (ing[q]) atomicAdd(&csize[r], 1);
+}
+// spanning forest of the local components (multi-GPU exchange)
+__global__ void k_forest(int Q, const int *__restrict__ parent, const int *__restrict__ ing, int2 *forest, unsigned long long *n) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    bool e = q < Q && ing[q] && parent[q] != q;
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    unsigned long long at = 0;
+    if ((threadIdx.x & 31) == 0 && m) at = atomicAdd(n, (unsigned long long)__popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (e) forest[at + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = make_int2(q, parent[q]);
+}
+
+// ---------------------------------------------------------------- stage 10: cluster / n_reads (main.py:251-257,334-342)
+__global__ void k_single_flags(int R, const int *__restrict__ q_of_rid, const int *__restrict__ ing, int *flag) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int q = q_of_rid[r];
+    flag[r] = !(q >= 0 && ing[q]);
+}
+__global__ void k_number(int R, const int *__restrict__ q_of_rid, const int *__restrict__ ing, const int *__restrict__ root,
+                         const int *__restrict__ cidx, const int *__restrict__ csize, const int *__restrict__ spos,
+                         const int64_t *__restrict__ ncl, int *out_cluster, int *out_n) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int q = q_of_rid[r];
+    if (q >= 0 && ing[q]) { int rt = root[q]; out_cluster[r] = cidx[rt]; out_n[r] = csize[rt]; }
+    else { out_cluster[r] = (int)(*ncl) + spos[r]; out_n[r] = 1; }                   // singletons after the clusters, bed order
+}
+
+// ---------------------------------------------------------------- integer-issue microbenchmark (roofline denominator)
+__global__ void k_int_peak(int iters, int *out) {
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 5, a5 = a0 + 7, a6 = a0 + 11, a7 = a0 + 13;
+    const int k = blockIdx.x | 1;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {                                               // 8 independent chains x 2 ops: min/max + add/xor
+            a0 = max(a0 + k, a1) ^ j; a1 = min(a1 - k, a2) ^ j; a2 = max(a2 + k, a3) ^ j; a3 = min(a3 - k, a4) ^ j;
+            a4 = max(a4 + k, a5) ^ j; a5 = min(a5 - k, a6) ^ j; a6 = max(a6 + k, a7) ^ j; a7 = min(a7 - k, a0) ^ j;
+        }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678) out[0] = a0;
+}
+
+// ================================================================ host pipeline
+struct Pipe {
+    // inputs (device)
+    fslrc_table tb;
+    fslrc_params pr;
+    int A, R, F, D, Q, nP, Tedge;
+    int *err;
+    int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entries,6 nP,7 pedges,8 edges,9 ncl,10 forest, 11 clustered
+    int *q_of_rid, *rid_of_q;
+    int4 *SR0, *SR1, *RM0, *RD, *RI;
+    int2 *RM1;
+    int *ubS, *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
+    int *degub, *isP, *plist, *stop, *final_;
+    int2 *entries, *pedges;
+    unsigned long long cap_entries, cap_pedges;
+    int *parent, *ing;
+    unsigned *ticket;
+    void *cub_tmp; size_t cub_bytes;
+    int stage;               // next event index
+    Tab tab;
+};
+
+static int mark(fslrc_ctx *ctx, int stage_end) {   // record the event closing `stage_end`
+    CK(cudaEventRecord(ctx->ev[stage_end + 1], ctx->stream));
+    return 0;
+}
+static int cub_tmp(fslrc_ctx *ctx, Pipe *P, size_t bytes) {
+    if (bytes > P->cub_bytes) {
+        void *q; size_t nb = bytes + (bytes >> 2) + 256;
+        CK(cudaMallocAsync(&q, nb, ctx->stream));
+        ctx->allocs.push_back(q);
+        P->cub_tmp = q; P->cub_bytes = nb;
+    }
+    return 0;
+}
+static int xscan(fslrc_ctx *ctx, Pipe *P, const int *in, int *out, int n) {
+    if (n <= 0) return 0;
+    size_t b = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, b, in, out, n, ctx->stream));
+    int r = cub_tmp(ctx, P, b); if (r) return r;
+    b = P->cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(P->cub_tmp, b, in, out, n, ctx->stream));
+    return 0;
+}
+template <typename K>
+static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const K *kin, K *kout, const int *vin, int *vout, int n, int b0, int b1) {
+    if (n <= 0) return 0;
+    size_t b = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, b, kin, kout, vin, vout, n, b0, b1, ctx->stream));
+    int r = cub_tmp(ctx, P, b); if (r) return r;
+    b = P->cub_bytes;
+    CK(cub::DeviceRadixSort::SortPairs(P->cub_tmp, b, kin, kout, vin, vout, n, b0, b1, ctx->stream));
+    return 0;
+}
+static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
+    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 16, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+static int err_code(fslrc_ctx *ctx) {
+    int e = (int)(ctx->h_pin[16] & 0xffffffff);
+    if (!e) return 0;
+    if (e & EF_RANGE) return fail(ctx, FSLRC_ERR_RANGE, "a table value is out of range (read_id/chrom id, negative coordinate, n_alignments >= 65535 or a bad `order`)");
+    if (e & EF_ZERO) return fail(ctx, FSLRC_ERR_ZERO_DIVISOR, "aln_size, qlen2 or n_alignments <= 0 on a filling (the reference raises ZeroDivisionError)");
+    if (e & EF_TOOMANY) return fail(ctx, FSLRC_ERR_TOO_MANY_FILLINGS, "a read has more than 64 fillings");
+    if (e & EF_NALN) return fail(ctx, FSLRC_ERR_NALN_NOT_CONSTANT, "n_alignments is not constant over the rows of a read");
+    return fail(ctx, FSLRC_ERR_OVERFLOW, "internal edge buffer overflow");
+}
+static int bits_for(int64_t n) { int b = 1; while ((1ll << b) < n && b < 32) b++; return b; }
+
+// ---- stages 1-5: ingestion, orders, records (replicated on every rank)
+static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
+    const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
+    cudaStream_t st = ctx->stream;
+    const int A = P->A, R = P->R, TB = 256;
+    DA(P->err, 1); DA(P->cnt, 16);
+    CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(P->cnt, 0, 16 * sizeof(int64_t), st));
+    CK(cudaMemcpyToSymbolAsync(c_umax, pr.umax, sizeof(int) * (LMAX + 1), 0, cudaMemcpyHostToDevice, st));
+    long long *d_clen; unsigned char *d_cmask;
+    DA(d_clen, pr.n_chrom); DA(d_cmask, pr.n_chrom);
+    if (pr.n_chrom > 0) {
+        CK(cudaMemcpyAsync(d_clen, pr.chrom_len, sizeof(int64_t) * pr.n_chrom, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_cmask, pr.chrom_masked, pr.n_chrom, cudaMemcpyHostToDevice, st));
+    }
+    // ---- stage 1: keep_fillings
+    int *first, *last, *qmin, *qmax, *flagA, *posA, *frow;
+    DA(first, R); DA(last, R); DA(qmin, R); DA(qmax, R); DA(flagA, A); DA(posA, A);
+    DA(P->q_of_rid, R);
+    if (R > 0) {
+        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(first, R, 0x7fffffff);
+        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(last, R, -1);
+        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(qmin, R, 0x7fffffff);
+        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(qmax, R, (int)0x80000000);
+        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(P->q_of_rid, R, -1);
+    }
+    if (A > 0) {
+        k_first_last<<<nblk(A, TB), TB, 0, st>>>(A, R, tb.read_id, first, last, P->err);
+        k_keep<<<nblk(A, TB), TB, 0, st>>>(A, R, tb.read_id, first, last, tb.qstart, tb.qend, flagA, qmin, qmax);
+        int r = xscan(ctx, P, flagA, posA, A); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(posA, flagA, A, P->cnt + 0);
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    const int F = P->F = (int)ctx->h_pin[0];
+    if (tb.order && tb.n_order != F) return fail(ctx, FSLRC_ERR_ARG, "order has the wrong length (must equal the number of fillings)");
+    DA(frow, F);
+    if (A > 0) k_compact_rows<<<nblk(A, TB), TB, 0, st>>>(A, flagA, posA, frow);
+    { int r = mark(ctx, 1); if (r) return r; }
+    // ---- stage 2: data order (cluster.py:114) + mask
+    int *dk = nullptr, *flagF, *posF;
+    DA(flagF, F); DA(posF, F);
+    if (tb.order) {
+        dk = (int *)tb.order;
+        if (F > 0) k_check_order<<<nblk(F, TB), TB, 0, st>>>(F, tb.order, P->err);
+    } else {
+        int *key, *key2, *v; DA(key, F); DA(key2, F); DA(v, F); DA(dk, F);
+        if (F > 0) {
+            k_start_keys<<<nblk(F, TB), TB, 0, st>>>(F, frow, tb.rstart, tb.rend, key);
+            k_iota<<<nblk(F, TB), TB, 0, st>>>(v, F);
+            int r = sort_pairs<int>(ctx, P, key, key2, v, dk, F, 0, 32); if (r) return r;     // stable: ties keep bed order
+        }
+    }
+    if (F > 0) {
+        k_mask_flags<<<nblk(F, TB), TB, 0, st>>>(F, dk, frow, tb.chrom, tb.rstart, tb.rend, pr.n_chrom, d_clen, d_cmask,
+                                                   pr.mask_subtelomere, (long long)pr.subtel, flagF, P->err);
+        int r = xscan(ctx, P, flagF, posF, F); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(posF, flagF, F, P->cnt + 1);
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    const int D = P->D = (int)ctx->h_pin[1];
+    int *it_rid, *it_chrom, *it_start, *it_end, *it_aln, *it_naln, *firstdp;
+    DA(it_rid, D); DA(it_chrom, D); DA(it_start, D); DA(it_end, D); DA(it_aln, D); DA(it_naln, D); DA(firstdp, R);
+    if (R > 0) k_fill<int><<<nblk(R, TB), TB, 0, st>>>(firstdp, R, 0x7fffffff);
+    if (F > 0) k_build_items<<<nblk(F, TB), TB, 0, st>>>(F, dk, frow, flagF, posF, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size,
+                                                          tb.n_alignments, it_rid, it_chrom, it_start, it_end, it_aln, it_naln, firstdp, P->err);
+    { int r = mark(ctx, 2); if (r) return r; }
+    // ---- stage 3: query rank + per-read lists
+    int *flagD, *posD, *it_q;
+    DA(flagD, D); DA(posD, D); DA(it_q, D);
+    if (D > 0) {
+        k_is_first<<<nblk(D, TB), TB, 0, st>>>(D, it_rid, firstdp, flagD);
+        int r = xscan(ctx, P, flagD, posD, D); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(posD, flagD, D, P->cnt + 2);
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    const int Q = P->Q = (int)ctx->h_pin[2];
+    DA(P->rid_of_q, Q);
+    int *qs, *rm_dp, *iotaD, *rmidx, *off, *len_end;
+    DA(qs, D); DA(rm_dp, D); DA(iotaD, D); DA(rmidx, D); DA(off, Q); DA(len_end, Q);
+    DA(P->RD, Q); DA(P->RI, Q);
+    if (R > 0) k_rank_reads<<<nblk(R, TB), TB, 0, st>>>(R, firstdp, posD, P->q_of_rid, P->rid_of_q);
+    if (D > 0) {
+        k_item_q<<<nblk(D, TB), TB, 0, st>>>(D, it_rid, P->q_of_rid, it_q);
+        k_iota<<<nblk(D, TB), TB, 0, st>>>(iotaD, D);
+        int r = sort_pairs<int>(ctx, P, it_q, qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
+        k_read_bounds<<<nblk(D, TB), TB, 0, st>>>(D, qs, rm_dp, rmidx, off, len_end);
+        k_read_info<<<nblk(Q, TB), TB, 0, st>>>(Q, P->rid_of_q, off, len_end, rm_dp, it_naln, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
+        k_check_naln<<<nblk(D, TB), TB, 0, st>>>(D, it_q, it_naln, P->RI, P->err);
+    }
+    { int r = mark(ctx, 3); if (r) return r; }
+    // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
+    unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1, *s_dp;
+    DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D); DA(s_dp, D);
+    if (D > 0) {
+        k_end_keys<<<nblk(D, TB), TB, 0, st>>>(D, it_end, ek);
+        int r = sort_pairs<unsigned>(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
+        k_chrom_start_keys<<<nblk(D, TB), TB, 0, st>>>(D, v1, it_chrom, it_start, ck);
+        r = sort_pairs<unsigned long long>(ctx, P, ck, ck2, v1, s_dp, D, 0, 32 + bits_for(pr.n_chrom)); if (r) return r;
+    }
+    { int r = mark(ctx, 4); if (r) return r; }
+    // ---- stage 5: records, thresholds, bands
+    int *s_end;
+    DA(P->SR0, D); DA(P->SR1, D); DA(P->RM0, D); DA(P->RM1, D); DA(P->s_chrom, D); DA(s_end, D);
+    DA(P->ubS, D); DA(P->pmaxS, D); DA(P->chrom_lo, pr.n_chrom); DA(P->chrom_hi, pr.n_chrom);
+    if (pr.n_chrom > 0) { CK(cudaMemsetAsync(P->chrom_lo, 0, sizeof(int) * pr.n_chrom, st)); CK(cudaMemsetAsync(P->chrom_hi, 0, sizeof(int) * pr.n_chrom, st)); }
+    if (D > 0) {
+        k_records<<<nblk(D, TB), TB, 0, st>>>(D, s_dp, rmidx, it_q, it_chrom, it_start, it_end, it_aln, P->RI, pr.overlap, P->SR0, P->SR1,
+                                               P->RM0, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
+        k_ub<<<nblk(D, 256), 256, 0, st>>>(D, P->SR0, P->SR1, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
+        size_t b = 0;
+        CK(cub::DeviceScan::InclusiveScanByKey(nullptr, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
+        int r = cub_tmp(ctx, P, b); if (r) return r;
+        b = P->cub_bytes;
+        CK(cub::DeviceScan::InclusiveScanByKey(P->cub_tmp, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    long long T = pr.edge_threshold;
+    P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
+    Tab &t = P->tab;
+    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RM1 = P->RM1; t.ubS = P->ubS; t.pmaxS = P->pmaxS;
+    t.s_chrom = P->s_chrom; t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
+    // relation entries: every read records fewer than edge_threshold passing candidates, and never more than exist
+    const unsigned long long band = (unsigned long long)ctx->h_pin[3];
+    unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * (unsigned long long)P->Tedge : 0ull;
+    P->cap_entries = std::min<unsigned long long>(capT, 2ull * band) + 64;
+    DA(P->entries, P->cap_entries);
+    DA(P->degub, Q); DA(P->isP, Q); DA(P->stop, D); DA(P->final_, Q); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
+    if (Q > 0) CK(cudaMemsetAsync(P->degub, 0, sizeof(int) * Q, st));
+    return mark(ctx, 5);
+}
+
+static int n_sms(fslrc_ctx *ctx) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
+    return n;
+}
+
+// ---- stage 6: pair kernel on one shard
+static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
+    cudaStream_t st = ctx->stream;
+    if (P->D > 0) {
+        int blocks = std::min(nblk(P->D, PAIR_WARPS), n_sms(ctx) * 8);
+        k_pair<<<blocks, PAIR_WARPS * 32, 0, st>>>(P->tab, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
+                                                   P->cap_entries, (unsigned long long *)(P->cnt + 4), P->err);
+    }
+    return mark(ctx, 6);
+}
+
+// ---- stages 7-9 (after degub is complete): saturating set, replay, union-find
+static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
+    cudaStream_t st = ctx->stream;
+    const int Q = P->Q, D = P->D, TB = 256;
+    int *posQ;
+    DA(posQ, Q);
+    if (Q > 0) {
+        k_satur_flags<<<nblk(Q, TB), TB, 0, st>>>(Q, P->degub, P->Tedge, P->isP);
+        int r = xscan(ctx, P, P->isP, posQ, Q); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(posQ, P->isP, Q, P->cnt + 6);
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    const int nP = P->nP = (int)ctx->h_pin[6];
+    DA(P->plist, nP);
+    if (Q > 0) k_compact_flagged<<<nblk(Q, TB), TB, 0, st>>>(Q, P->isP, posQ, P->plist);
+    // stops: a read that never breaks walks every filling's scan to the chromosome start; final = not saturating
+    if (D > 0) CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st));
+    if (Q > 0) CK(cudaMemsetAsync(P->final_, 0, sizeof(int) * Q, st));
+    CK(cudaMemsetAsync(P->ticket, 0, sizeof(unsigned), st));
+    { int r = mark(ctx, 7); if (r) return r; }
+    // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
+    unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
+    unsigned long long alt = 2ull * (unsigned long long)ctx->h_pin[3] + 64;
+    P->cap_pedges = std::min(capp, alt);
+    DA(P->pedges, P->cap_pedges);
+    if (nP > 0) {
+        int blocks = std::min(nblk(nP, REPLAY_WARPS), n_sms(ctx) * 8);
+        k_replay<<<blocks, REPLAY_WARPS * 32, 0, st>>>(P->tab, nP, P->plist, P->isP, P->stop, P->final_, P->ticket, P->pedges,
+                                                       (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err);
+    }
+    { int r = mark(ctx, 8); if (r) return r; }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
+    const unsigned long long nped = (unsigned long long)ctx->h_pin[7];
+    if (Q > 0) {
+        k_iota<<<nblk(Q, TB), TB, 0, st>>>(P->parent, Q);
+        CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
+    }
+    if (nent > 0) k_union_entries<<<nblk((int64_t)nent, TB), TB, 0, st>>>(nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
+                                                                           (unsigned long long *)(P->cnt + 8));
+    // replayed edges are identical on every rank; rank `shard` contributes them once
+    if (nped > 0 && shard == 0) k_union_edges<<<nblk((int64_t)nped, TB), TB, 0, st>>>(nped, P->pedges, P->parent, P->ing);
+    (void)nshard;
+    return mark(ctx, 9);
+}
+
+// ---- stage 10: numbering
+static int pipe_number(fslrc_ctx *ctx, Pipe *P, int *out_cluster, int *out_n) {
+    cudaStream_t st = ctx->stream;
+    const int Q = P->Q, R = P->R, TB = 256;
+    int *isroot, *cidx, *csize, *sflag, *spos;
+    DA(isroot, Q); DA(cidx, Q); DA(csize, Q); DA(sflag, R); DA(spos, R);
+    if (Q > 0) {
+        CK(cudaMemsetAsync(csize, 0, sizeof(int) * Q, st));
+        k_flatten<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, isroot, csize);
+        int r = xscan(ctx, P, isroot, cidx, Q); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(cidx, isroot, Q, P->cnt + 9);
+    }
+    if (R > 0) {
+        k_single_flags<<<nblk(R, TB), TB, 0, st>>>(R, P->q_of_rid, P->ing, sflag);
+        int r = xscan(ctx, P, sflag, spos, R); if (r) return r;
+        k_total<<<1, 1, 0, st>>>(spos, sflag, R, P->cnt + 11);
+        k_number<<<nblk(R, TB), TB, 0, st>>>(R, P->q_of_rid, P->ing, P->parent, cidx, csize, spos, P->cnt + 9, out_cluster, out_n);
+    }
+    return mark(ctx, 10);
+}
+
+static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
+    if (!s) return;
+    const int64_t *h = ctx->h_pin;
+    memset(s, 0, sizeof(*s));
+    s->n_fillings = P->F; s->n_intervals = P->D; s->n_query_reads = P->Q;
+    s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[5]; s->saturating_reads = P->nP;
+    s->edges = h[8] + h[7]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
+    s->no_clusters = h[9] == 0;
+    for (int i = 0; i < FSLRC_N_STAGES; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
+        s->stage_ms[i] = ms;
+    }
+}
+
+static int check_args(fslrc_ctx *ctx, const fslrc_table *tb, const fslrc_params *pr, const void *oc, const void *on) {
+    if (!ctx) return FSLRC_ERR_ARG;
+    if (!tb || !pr || !oc || !on) return fail(ctx, FSLRC_ERR_ARG, "null argument");
+    if (tb->n_rows < 0 || tb->n_reads < 0 || tb->n_rows > 0x7ffffff0LL || tb->n_reads > 0x7ffffff0LL) return fail(ctx, FSLRC_ERR_ARG, "table size out of range");
+    if (tb->n_rows > 0 && (!tb->read_id || !tb->chrom || !tb->rstart || !tb->rend || !tb->aln_size || !tb->qstart || !tb->qend || !tb->n_alignments))
+        return fail(ctx, FSLRC_ERR_ARG, "null column");
+    if (pr->n_chrom < 0 || pr->n_chrom > (1 << 20) || (pr->n_chrom > 0 && (!pr->chrom_len || !pr->chrom_masked))) return fail(ctx, FSLRC_ERR_ARG, "bad chromosome tables");
+    if (pr->overlap != pr->overlap || pr->qlen_c != pr->qlen_c || pr->naln_c != pr->naln_c) return fail(ctx, FSLRC_ERR_ARG, "NaN option");
+    return 0;
+}
+
+static int run_device(fslrc_ctx *ctx, Pipe *P, int32_t *oc, int32_t *on, fslrc_stats *stats) {
+    int r = pipe_prepare(ctx, P); if (r) return r;
+    r = pipe_pair(ctx, P, 0, 1); if (r) return r;
+    r = pipe_replay_union(ctx, P, 0, 1); if (r) return r;
+    r = pipe_number(ctx, P, oc, on); if (r) return r;
+    return 0;
+}
+
+extern "C" {
+
+int fslrc_version(void) { return FSLRC_VERSION; }
+const char *fslrc_stage_name(int s) { return (s >= 0 && s < FSLRC_N_STAGES) ? STAGE_NAMES[s] : ""; }
+const char *fslrc_last_error(const fslrc_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int fslrc_create(int device, fslrc_ctx **out) {
+    if (!out) return FSLRC_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FSLRC_ERR_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) return FSLRC_ERR_CUDA;
+    fslrc_ctx *ctx = new fslrc_ctx();
+    ctx->device = device; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->h_pin = nullptr;
+    if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
+    for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaMemPool_t pool;                                   // keep freed scratch cached between calls
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return 0;
+}
+
+void fslrc_destroy(fslrc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    free_all(ctx);
+    cudaDeviceSynchronize();
+    for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    delete ctx->pipe;
+    delete ctx;
+}
+
+int fslrc_cluster_device(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params, int32_t *out_cluster,
+                         int32_t *out_n_reads, fslrc_stats *stats, void *stream) {
+    int r = check_args(ctx, table, params, out_cluster, out_n_reads); if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    Pipe P; memset(&P, 0, sizeof(P));
+    P.tb = *table; P.pr = *params; P.A = (int)table->n_rows; P.R = (int)table->n_reads;
+    for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+    r = run_device(ctx, &P, out_cluster, out_n_reads, stats);
+    if (!r) { r = mark(ctx, 11); }
+    if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
+    if (!r) fill_stats(ctx, &P, stats);
+    free_all(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    return r;
+}
+
+int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params, int32_t *out_cluster,
+                       int32_t *out_n_reads, fslrc_stats *stats, void *stream) {
+    int r = check_args(ctx, table, params, out_cluster, out_n_reads); if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    cudaStream_t st = ctx->stream;
+    const int64_t A = table->n_rows, R = table->n_reads;
+    for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], st);
+    fslrc_table d = *table;
+    int32_t *cols[8]; const int32_t *src[8] = {table->read_id, table->chrom, table->rstart, table->rend, table->aln_size,
+                                               table->qstart, table->qend, table->n_alignments};
+    for (int c = 0; c < 8; c++) {
+        DA(cols[c], A);
+        if (A > 0) CK(cudaMemcpyAsync(cols[c], src[c], sizeof(int32_t) * A, cudaMemcpyHostToDevice, st));
+    }
+    d.read_id = cols[0]; d.chrom = cols[1]; d.rstart = cols[2]; d.rend = cols[3]; d.aln_size = cols[4]; d.qstart = cols[5];
+    d.qend = cols[6]; d.n_alignments = cols[7];
+    int32_t *d_order = nullptr;
+    if (table->order) {
+        DA(d_order, table->n_order);
+        if (table->n_order > 0) CK(cudaMemcpyAsync(d_order, table->order, sizeof(int32_t) * table->n_order, cudaMemcpyHostToDevice, st));
+        d.order = d_order;
+    }
+    int32_t *d_oc, *d_on;
+    DA(d_oc, R); DA(d_on, R);
+    CK(cudaEventRecord(ctx->ev[1], st));                                   // closes stage 0 (h2d)
+    Pipe P; memset(&P, 0, sizeof(P));
+    P.tb = d; P.pr = *params; P.A = (int)A; P.R = (int)R;
+    r = run_device(ctx, &P, d_oc, d_on, stats);
+    if (!r && R > 0) {
+        CK(cudaMemcpyAsync(out_cluster, d_oc, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_n_reads, d_on, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
+    }
+    if (!r) r = mark(ctx, 11);
+    if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
+    if (!r) fill_stats(ctx, &P, stats);
+    free_all(ctx);
+    cudaStreamSynchronize(st);
+    return r;
+}
+
+// ---------------------------------------------------------------- multi-GPU staging
+int fslrc_mg_prepare(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params, void *stream) {
+    int dummy = 0;
+    int r = check_args(ctx, table, params, &dummy, &dummy); if (r) return r;
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    free_all(ctx);
+    delete ctx->pipe;
+    Pipe *P = ctx->pipe = new Pipe(); memset(P, 0, sizeof(*P));
+    P->tb = *table; P->pr = *params; P->A = (int)table->n_rows; P->R = (int)table->n_reads;
+    for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
+    r = pipe_prepare(ctx, P);
+    if (r) { free_all(ctx); cudaStreamSynchronize(ctx->stream); }
+    return r;
+}
+int fslrc_mg_pair(fslrc_ctx *ctx, int rank, int world, int32_t **counts, int64_t *n_counts) {
+    if (!ctx || !ctx->pipe || !counts || !n_counts || world < 1 || rank < 0 || rank >= world) return FSLRC_ERR_ARG;
+    Pipe *P = ctx->pipe;
+    CK(cudaSetDevice(ctx->device));
+    int r = pipe_pair(ctx, P, rank, world); if (r) return r;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *counts = P->degub; *n_counts = P->Q;
+    return 0;
+}
+int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64_t *n_forest_edges) {
+    if (!ctx || !ctx->pipe || !forest || !n_forest_edges) return FSLRC_ERR_ARG;
+    Pipe *P = ctx->pipe;
+    CK(cudaSetDevice(ctx->device));
+    int r = pipe_replay_union(ctx, P, rank, world); if (r) return r;
+    cudaStream_t st = ctx->stream;
+    const int Q = P->Q, TB = 256;
+    int *isroot, *csize; int2 *fo;
+    DA(isroot, Q); DA(csize, Q); DA(fo, Q);
+    if (Q > 0) {
+        CK(cudaMemsetAsync(csize, 0, sizeof(int) * Q, st));
+        k_flatten<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, isroot, csize);
+        k_forest<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, fo, (unsigned long long *)(P->cnt + 10));
+    }
+    r = read_counts(ctx, P); if (r) return r;
+    r = err_code(ctx); if (r) return r;
+    *forest = (int32_t *)fo; *n_forest_edges = ctx->h_pin[10];
+    return 0;
+}
+int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, int32_t *out_cluster, int32_t *out_n_reads,
+                    fslrc_stats *stats) {
+    if (!ctx || !ctx->pipe || !out_cluster || !out_n_reads || n_edges < 0 || (n_edges > 0 && !all_forest)) return FSLRC_ERR_ARG;
+    Pipe *P = ctx->pipe;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int Q = P->Q, TB = 256;
+    if (Q > 0) {
+        k_iota<<<nblk(Q, TB), TB, 0, st>>>(P->parent, Q);
+        CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
+    }
+    if (n_edges > 0) k_union_edges<<<nblk(n_edges, TB), TB, 0, st>>>((unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing);
+    int r = pipe_number(ctx, P, out_cluster, out_n_reads);
+    if (!r) r = mark(ctx, 11);
+    if (!r) { r = read_counts(ctx, P); if (!r) r = err_code(ctx); }
+    if (!r) fill_stats(ctx, P, stats);
+    free_all(ctx);
+    cudaStreamSynchronize(st);
+    delete ctx->pipe; ctx->pipe = nullptr;
+    return r;
+}
+
+int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s) {
+    if (!ctx || !lane_ops_per_s) return FSLRC_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int *d; CK(cudaMalloc(&d, 4));
+    const int iters = 4096, blocks = n_sms(ctx) * 8, threads = 256;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_int_peak<<<blocks, threads>>>(64, d);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0);
+        k_int_peak<<<blocks, threads>>>(iters, d);
+        cudaEventRecord(e1);
+        CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0 * 3.0;     // add + min/max + xor per chain step
+        best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *lane_ops_per_s = best;
+    return 0;
+}
+
+}  // extern "C"

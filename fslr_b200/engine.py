@@ -1,0 +1,185 @@
+"""Host side of the B200 clustering step: owns buffers through PyTorch, calls the C ABI.
+
+`Engine.cluster(table, params)` is the fused entry the benchmark and the drop-in functions of
+fslr_b200.cluster use (SURVEY.md §8b `cluster_table`).  Threshold tables that depend on floating point
+(`umax`, `1 - qlen_diff`, `1 - n_alignment_diff`) are computed here with Python floats — the reference's own
+arithmetic (cluster.py:170,179,181,218-219) — so the device only ever compares integers.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native
+from .table import ClusterParams, ColumnarTable
+
+_COLS = ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments")
+
+
+def umax_table(cutoffs, n_max=_native.MAX_FILLINGS):
+    """umax[n] = largest union u >= n with n/u >= cutoff(n) in float64; n-1 when none (cluster.py:165-170,218-219)."""
+    out = [0]
+    for n in range(1, n_max + 1):
+        t = cutoffs[n - 1] if n - 1 < len(cutoffs) else cutoffs[-1]
+        if t <= 0:
+            out.append(2**31 - 1)
+            continue
+        u = min(int(n / t) + 2, 2**31 - 1)
+        while u >= n and not (n / u >= t):
+            u -= 1
+        out.append(u if u >= n else n - 1)
+    return out
+
+
+@dataclass
+class ClusterResult:
+    cluster: np.ndarray        # int32 per read id: the `cluster` value main.py:334-342 writes for that read's rows
+    n_reads: np.ndarray        # int32 per read id
+    no_clusters: bool          # main.py:247-249 early return ("No clusters were found.")
+    stats: dict
+
+
+class DeviceTable:
+    """The table's columns resident in HBM (torch tensors own the memory)."""
+
+    def __init__(self, table: ColumnarTable, device, order=None):
+        self.n_rows, self.n_reads = table.n_rows, table.n_reads
+        self.cols = {k: torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32)).to(device) for k in _COLS}
+        self.order = None
+        if order is not None:
+            self.order = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int32)).to(device)
+        self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=device)
+        self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=device)
+
+
+class PinnedTable:
+    """The table's columns in pinned host memory (the e2e path copies them in every call)."""
+
+    def __init__(self, table: ColumnarTable, order=None):
+        self.n_rows, self.n_reads = table.n_rows, table.n_reads
+        self.cols = {}
+        for k in _COLS:
+            t = torch.empty(max(self.n_rows, 1), dtype=torch.int32).pin_memory()
+            t[:self.n_rows] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
+            self.cols[k] = t
+        self.order = None
+        if order is not None:
+            self.order = torch.from_numpy(np.ascontiguousarray(order, dtype=np.int32)).pin_memory()
+        self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32).pin_memory()
+        self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32).pin_memory()
+
+    @property
+    def h2d_bytes(self):
+        return 4 * self.n_rows * len(_COLS) + (4 * int(self.order.numel()) if self.order is not None else 0)
+
+    @property
+    def d2h_bytes(self):
+        return 8 * self.n_reads
+
+
+class Engine:
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fslr_b200: no CUDA device — this package has no CPU fallback")
+        self.lib = _native.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)            # make sure the primary context exists
+        self.ctx = C.c_void_p()
+        rc = self.lib.fslrc_create(device, C.byref(self.ctx))
+        if rc != 0:
+            raise _native.FslrError(rc, "fslrc_create failed")
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.fslrc_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- argument marshalling
+    def _params(self, table, params: ClusterParams):
+        p = _native.Params()
+        p.overlap = float(params.overlap)
+        p.qlen_c = 1 - params.qlen_diff                 # cluster.py:179
+        p.naln_c = 1 - params.n_alignment_diff          # cluster.py:181
+        um = umax_table(list(params.jaccard_cutoffs))
+        for i, v in enumerate(um):
+            p.umax[i] = int(v)
+        p.edge_threshold = int(max(min(params.edge_threshold, 2**62), -2**62))
+        self._clen = np.ascontiguousarray(table_chrom_len(table), dtype=np.int64)
+        m = params.chrom_masked if params.chrom_masked is not None else np.zeros(len(self._clen), np.uint8)
+        self._cmask = np.ascontiguousarray(m, dtype=np.uint8)
+        p.n_chrom = len(self._clen)
+        p.chrom_len = self._clen.ctypes.data if len(self._clen) else None
+        p.chrom_masked = self._cmask.ctypes.data if len(self._cmask) else None
+        p.mask_subtelomere = int(bool(params.mask_subtelomere))
+        p.subtel = int(params.subtel)
+        return p
+
+    @staticmethod
+    def _table(buf):
+        t = _native.Table()
+        t.n_rows, t.n_reads = buf.n_rows, buf.n_reads
+        for k in _COLS:
+            setattr(t, k, buf.cols[k].data_ptr())
+        if buf.order is not None:
+            t.order, t.n_order = buf.order.data_ptr(), int(buf.order.numel())
+        else:
+            t.order, t.n_order = None, 0
+        return t
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _native.FslrError(rc, self.lib.fslrc_last_error(self.ctx).decode())
+
+    # ---- compute entry points
+    def run_resident(self, dtab: DeviceTable, chrom_table, params: ClusterParams):
+        """Inputs already in HBM; outputs stay in HBM (dtab.out_cluster / out_n_reads).  Returns stats dict."""
+        p = self._params(chrom_table, params)
+        t = self._table(dtab)
+        st = _native.Stats()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.fslrc_cluster_device(self.ctx, C.byref(t), C.byref(p), dtab.out_cluster.data_ptr(),
+                                                  dtab.out_n_reads.data_ptr(), C.byref(st), C.c_void_p(stream)))
+        return st.as_dict(self.lib)
+
+    def run_host(self, ptab: PinnedTable, chrom_table, params: ClusterParams):
+        """Host buffers in, host buffers out (H2D + D2H inside the call).  Returns stats dict."""
+        p = self._params(chrom_table, params)
+        t = self._table(ptab)
+        st = _native.Stats()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.fslrc_cluster_host(self.ctx, C.byref(t), C.byref(p), ptab.out_cluster.data_ptr(),
+                                                ptab.out_n_reads.data_ptr(), C.byref(st), C.c_void_p(stream)))
+        return st.as_dict(self.lib)
+
+    def cluster(self, table: ColumnarTable, params: ClusterParams, order=None) -> ClusterResult:
+        ptab = PinnedTable(table, order)
+        stats = self.run_host(ptab, table, params)
+        n = table.n_reads
+        return ClusterResult(ptab.out_cluster[:n].numpy().copy(), ptab.out_n_reads[:n].numpy().copy(),
+                             bool(stats["no_clusters"]), stats)
+
+    def int_peak(self):
+        v = C.c_double()
+        self._check(self.lib.fslrc_int_peak(self.ctx, C.byref(v)))
+        return v.value
+
+
+def table_chrom_len(table):
+    return table.chrom_len
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -51,6 +51,8 @@ class MappingsTable:
     chrom_names: list = field(default_factory=lambda: list(CHROM_NAMES))
     chr_lengths: dict = field(default_factory=lambda: {n: int(l) for n, l in GENOME})
     name: str = ""
+    read_id: np.ndarray = None  # int32 dense read ids in order of first appearance (== pandas.factorize(qname))
+    n_reads: int = 0
 
     @property
     def n_rows(self):
@@ -58,11 +60,7 @@ class MappingsTable:
 
     def read_ids(self):
         """Dense read ids in order of first appearance (what pandas.factorize(qname) yields)."""
-        uniq, first, inv = np.unique(self.read_key, return_index=True, return_inverse=True)
-        order = np.argsort(first, kind="stable")
-        rank = np.empty_like(order)
-        rank[order] = np.arange(order.shape[0])
-        return rank[inv].astype(np.int32), int(uniq.shape[0])
+        return self.read_id, self.n_reads
 
     def qnames(self):
         pn = np.array(self.primers)[self.primer]
@@ -179,9 +177,14 @@ def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_f
 
     # ---- qname keys: random permutation so name order is unrelated to family membership
     key = rng.permutation(R).astype(np.int64)
+    # table order of collect_mapping_info.py:174: n_alignments desc, qname asc, qstart asc.  Rows of a read are
+    # generated in qstart order and keys are unique, so ordering the READS and expanding is the same permutation.
+    ro = np.argsort(((6 - read_naln).astype(np.int64) << 40) | key)
+    na_s = read_naln[ro]
+    new_first = np.cumsum(na_s) - na_s
+    order = np.repeat(r_first[ro] - new_first, na_s) + np.arange(A)
+    read_id = np.repeat(np.arange(R, dtype=np.int32), na_s)          # dense ids in order of first appearance
     row_key = key[row_read]
-    # table order of collect_mapping_info.py:174: n_alignments desc, qname asc, qstart asc
-    order = np.lexsort((qstart, row_key, -read_naln[row_read]))
     return MappingsTable(
         chrom=t_chrom[row_t][order].astype(np.int32),
         rstart=rstart[order].astype(np.int32), rend=rend[order].astype(np.int32),
@@ -193,7 +196,7 @@ def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_f
         qlen=qlen[order].astype(np.int32),
         alignment_score=(aln[order] * 9 // 5).astype(np.int32),
         primer=fam_primer[read_fam[row_read]][order].astype(np.int8),
-        primers=primers, name=name)
+        primers=primers, name=name, read_id=read_id, n_reads=R)
 
 
 # name -> (generator kwargs, clustering parameters handed to main.py's options)

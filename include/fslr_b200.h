@@ -1,0 +1,134 @@
+/* fslr_b200 — C ABI of the B200-native read-clustering step of kcleal/fslr.
+ *
+ * The reference has no FFI: the boundary it offers is the set of in-process Python calls that
+ * /root/reference/fslr/main.py:227-244 makes into /root/reference/fslr/cluster.py.  This header is
+ * what a ctypes binding of that step binds instead (INTEGRATION.md shows the stub); each entry
+ * point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; return 0 on success, a negative
+ * FSLRC_ERR_* otherwise (fslrc_last_error() gives the text); no exception crosses the ABI.  The
+ * caller owns every input/output buffer and keeps it alive until the call returns (calls are
+ * synchronous with respect to the host: they end with a stream synchronise).  A context belongs to
+ * one device and is not re-entrant; separate contexts are independent.  There is NO CPU fallback:
+ * every entry point fails with FSLRC_ERR_CUDA when no device is usable.
+ */
+#ifndef FSLR_B200_H
+#define FSLR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSLRC_MAX_FILLINGS 64      /* fillings per read after keep_fillings/masking (n_alignments - 2) */
+#define FSLRC_N_STAGES 12
+
+enum {
+    FSLRC_OK = 0,
+    FSLRC_ERR_CUDA = -1,            /* CUDA runtime error, or no device */
+    FSLRC_ERR_ARG = -2,             /* null/inconsistent argument */
+    FSLRC_ERR_ZERO_DIVISOR = -3,    /* aln_size / qlen2 / n_alignments <= 0 on a filling: the reference raises
+                                       ZeroDivisionError at cluster.py:135,179,181 */
+    FSLRC_ERR_TOO_MANY_FILLINGS = -4, /* a read has more than FSLRC_MAX_FILLINGS fillings */
+    FSLRC_ERR_NALN_NOT_CONSTANT = -5, /* n_alignments differs between rows of one read (the producer,
+                                         collect_mapping_info.py:80,122,141, never emits that) */
+    FSLRC_ERR_OVERFLOW = -6,        /* internal edge buffer overflow (cannot happen within the stated bounds) */
+    FSLRC_ERR_RANGE = -7            /* a value does not fit the packed device records (n_alignments >= 65536, id out of range) */
+};
+
+typedef struct fslrc_ctx fslrc_ctx;
+
+/* `<name>.mappings.bed` in columnar form, one entry per alignment row in table order
+ * (replaces the DataFrame main.py:209 reads; columns as written by collect_mapping_info.py:176-181).
+ * read_id is the dense id of `qname` in order of first appearance, chrom the integer id
+ * cluster.rename_chromosomes assigns (cluster.py:34-43; only equality is used). */
+typedef struct {
+    int64_t n_rows;
+    int64_t n_reads;
+    const int32_t *read_id;        /* [n_rows] 0..n_reads-1 */
+    const int32_t *chrom;          /* [n_rows] 0..n_chrom-1 */
+    const int32_t *rstart;         /* [n_rows] */
+    const int32_t *rend;           /* [n_rows] */
+    const int32_t *aln_size;       /* [n_rows] */
+    const int32_t *qstart;         /* [n_rows] */
+    const int32_t *qend;           /* [n_rows] */
+    const int32_t *n_alignments;   /* [n_rows] */
+    /* optional: the permutation cluster.py:114 (`sort_values('start')`, an UNSTABLE sort) applies to the
+     * frame keep_fillings returns, as indices into that frame in bed order; NULL = stable sort on the GPU
+     * (ties keep bed order).  n_order must equal the number of fillings when given. */
+    const int32_t *order;
+    int64_t n_order;
+} fslrc_table;
+
+/* The options of main.py:33-37,219-223,237 in numeric form.  The three `*_c`/umax fields are computed by the
+ * host in the reference's own double arithmetic (Python floats) so no rounding decision is re-made here. */
+typedef struct {
+    double overlap;                /* --overlap            (main.py:34,220; cluster.py:157) */
+    double qlen_c;                 /* 1 - qlen_diff        (cluster.py:179) */
+    double naln_c;                 /* 1 - n_alignment_diff (cluster.py:181) */
+    int32_t umax[FSLRC_MAX_FILLINGS + 1]; /* umax[n] = largest union with n/union >= cutoff(n), n-1 if none
+                                       (cluster.py:165-170,218-219); umax[0] unused */
+    int64_t edge_threshold;        /* main.py:221 */
+    int32_t n_chrom;
+    const int64_t *chrom_len;      /* [n_chrom] host pointer; 0 = chromosome not in the BAM header (cluster.py:99) */
+    const uint8_t *chrom_masked;   /* [n_chrom] host pointer; 1 = named in --cluster-mask (cluster.py:96) */
+    int32_t mask_subtelomere;      /* 'subtelomere' in mask (cluster.py:98) */
+    int64_t subtel;                /* 500000 (main.py:237) */
+} fslrc_params;
+
+typedef struct {
+    int64_t n_fillings;            /* rows left by keep_fillings (cluster.py:14-31) */
+    int64_t n_intervals;           /* after mask_sequences2 (cluster.py:89-106) */
+    int64_t n_query_reads;         /* reads with >= 1 interval (cluster.py:189-191) */
+    int64_t band_pairs;            /* interval-level candidate pairs {i<j<=ub(i)} (what search_values can return) */
+    int64_t pair_tests;            /* full read-pair tests evaluated on the GPU (a10+a11+a13 of SURVEY §8a) */
+    int64_t relation_entries;      /* passing (query, other) pairs recorded by the pair kernel */
+    int64_t saturating_reads;      /* reads that can reach edge_threshold (replayed in query order) */
+    int64_t edges;                 /* edges handed to union-find */
+    int64_t components;            /* clusters with >= 2 reads */
+    int64_t clustered_reads;       /* reads in those clusters */
+    int32_t no_clusters;           /* main.py:247-249: the reference prints "No clusters were found." and returns */
+    int32_t reserved;
+    float stage_ms[FSLRC_N_STAGES];/* CUDA-event time per stage, see fslrc_stage_name() */
+} fslrc_stats;
+
+int fslrc_create(int device, fslrc_ctx **out);
+void fslrc_destroy(fslrc_ctx *ctx);
+const char *fslrc_last_error(const fslrc_ctx *ctx);
+const char *fslrc_stage_name(int stage);
+int fslrc_version(void);
+
+/* The whole step, main.py:233-257,334-342 (keep_fillings -> prepare_data -> build_interval_trees ->
+ * query_interval_trees -> get_subgraphs -> cluster / n_reads columns), on DEVICE-resident columns.
+ * out_cluster / out_n_reads: device int32 [n_reads] indexed by read_id: the `cluster` and `n_reads`
+ * values the reference writes for that read's rows (as integers; the reference stores them as floats).
+ * `stream` is a cudaStream_t (NULL = default stream). */
+int fslrc_cluster_device(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params,
+                         int32_t *out_cluster, int32_t *out_n_reads, fslrc_stats *stats, void *stream);
+
+/* Same with HOST buffers (pinned recommended): copies the columns in, runs, copies both outputs back. */
+int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params,
+                       int32_t *out_cluster, int32_t *out_n_reads, fslrc_stats *stats, void *stream);
+
+/* ---- multi-GPU staging: the interval table is replicated, the pair space is sharded ----
+ * fslrc_mg_prepare     : ingestion + sort/band on this device (identical on every rank)
+ * fslrc_mg_pair        : pair kernel on shard `rank` of `world`; leaves the per-read passing-candidate counts
+ *                        in a device int32 [n_query_reads] buffer (*counts) that the caller sum-all-reduces
+ * fslrc_mg_replay      : after the all-reduce: replay of saturating reads (replicated, it is sequential) and
+ *                        union-find over this rank's edges; leaves a spanning forest (int32 pairs) in *forest
+ * fslrc_mg_finish      : takes the all-gathered forests, final union-find + numbering
+ */
+int fslrc_mg_prepare(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params, void *stream);
+int fslrc_mg_pair(fslrc_ctx *ctx, int rank, int world, int32_t **counts, int64_t *n_counts);
+int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64_t *n_forest_edges);
+int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges,
+                    int32_t *out_cluster, int32_t *out_n_reads, fslrc_stats *stats);
+
+/* Integer-issue microbenchmark used as the pair-kernel roofline denominator: returns the measured
+ * dependent-free IADD3/LOP3/VIMNMX lane-ops per second on this device. */
+int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,90 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden fixtures produced by the unmodified
+cluster.py, and the oracle on seeded inputs.  Bit-exact: integer cluster ids and sizes."""
+import numpy as np
+import pytest
+
+from tests import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from fslr_b200.engine import get_engine
+    return get_engine(0)
+
+
+def _check_case(engine, case):
+    res = engine.cluster(case.table, case.params, order=case.order)
+    assert res.no_clusters == case.no_clusters, case.name
+    if not case.no_clusters:
+        ecl, enr = case.expected
+        bad = np.nonzero(res.cluster != ecl)[0]
+        assert bad.size == 0, "%s: %d reads differ, first %s" % (case.name, bad.size, bad[:5])
+        assert np.array_equal(res.n_reads, enr), case.name
+
+
+def test_golden_small_cases(engine):
+    cases = golden_io.load("small_cases.npz")
+    failed = []
+    for c in cases:
+        try:
+            _check_case(engine, c)
+        except AssertionError as e:
+            failed.append(str(e))
+    assert not failed, "%d/%d cases differ: %s" % (len(failed), len(cases), failed[:5])
+
+
+@pytest.mark.parametrize("idx", range(8))
+def test_golden_config_cases(engine, idx):
+    cases = golden_io.load("config_cases.npz")
+    _check_case(engine, cases[idx])
+
+
+@pytest.mark.parametrize("name,scale,T", [("C1", 1.0, 10), ("C2", 1.0, 10), ("C2", 0.2, 1), ("C2", 0.2, 3), ("C3", 0.1, 10),
+                                          ("C5", 0.02, 10), ("C5", 0.02, 2), ("C4", 0.02, 10)])
+def test_oracle_stable_order(engine, name, scale, T):
+    """Production mode (GPU stable sort) against the oracle with the same tie rule."""
+    from fslr_b200 import synth
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    from oracle import oracle as orc
+    t = ColumnarTable.from_synth(synth.make_config(name, scale))
+    p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK[name], edge_threshold=T)
+    res = engine.cluster(t, p)
+    ocl, onr, ost = orc.oracle_cluster(t, p)
+    assert np.array_equal(res.cluster, ocl)
+    assert np.array_equal(res.n_reads, onr)
+    assert res.stats["components"] == ost["components"]
+    assert res.stats["n_intervals"] == ost["n_data"] and res.stats["n_fillings"] == ost["n_fillings"]
+
+
+def test_resident_path_matches_host_path(engine):
+    from fslr_b200 import synth
+    from fslr_b200.engine import DeviceTable
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C1"))
+    p = ClusterParams.from_options(t)
+    a = engine.cluster(t, p)
+    d = DeviceTable(t, engine.device)
+    engine.run_resident(d, t, p)
+    assert np.array_equal(d.out_cluster[:t.n_reads].cpu().numpy(), a.cluster)
+    assert np.array_equal(d.out_n_reads[:t.n_reads].cpu().numpy(), a.n_reads)
+
+
+def test_errors(engine):
+    from fslr_b200 import synth
+    from fslr_b200._native import FslrError
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C1", 0.1))
+    p = ClusterParams.from_options(t)
+    bad = ColumnarTable(**{**t.__dict__})
+    bad.aln_size = t.aln_size.copy(); bad.aln_size[:] = 0
+    with pytest.raises(FslrError) as e:
+        engine.cluster(bad, p)
+    assert e.value.code == -3
+    empty = ColumnarTable(**{**t.__dict__})
+    for k in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments"):
+        setattr(empty, k, np.zeros(0, np.int32))
+    empty.n_reads = 0
+    r = engine.cluster(empty, p)
+    assert r.no_clusters and r.cluster.shape[0] == 0
