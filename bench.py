@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Benchmark of the read-clustering step (BASELINE.json metric: reads clustered/s + pair tests/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C4] [--impl reference]
+
+A "step" is one pass of the whole clustering step (keep_fillings -> ... -> cluster / n_reads columns) over one
+synthetic mappings table.  `value` is measured with the table already resident in HBM; `e2e` goes through the host
+buffer C-ABI call (pinned host columns -> H2D -> step -> D2H of both result columns) every step.  For N > 1 the
+10M-read table is replicated and the pair space sharded (strong scaling); launch under torchrun.
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/, kind "port": the reference itself
+is pure Python and /root/reference does not exist on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from fslr_b200 import synth                                      # noqa: E402
+from fslr_b200.table import ClusterParams, ColumnarTable         # noqa: E402
+
+METRIC, UNIT = "reads_clustered_per_s", "reads/s"
+CPU_SAMPLE_READS = 1_000_000
+
+
+def env_int(k, d):
+    return int(os.environ.get(k, d))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_workload(config, scale=1.0):
+    t = synth.make_config(config, scale)
+    ct = ColumnarTable.from_synth(t)
+    params = ClusterParams.from_options(ct, cluster_mask=synth.CONFIG_MASK[config])
+    return ct, params
+
+
+def cpu_port_run(config, n_reads):
+    """One pass of the CPU restatement over `n_reads` reads of the config's distribution.  Returns (seconds, stats)."""
+    from oracle import oracle as orc
+    kw = dict(synth.CONFIGS[config])
+    frac = n_reads / kw["n_reads"]
+    ct, params = make_workload(config, min(1.0, frac))
+    t0 = time.perf_counter()
+    _, _, st = orc.oracle_cluster(ct, params)
+    return time.perf_counter() - t0, st, ct.n_reads
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.strip().lower() == "active":
+                        reasons.add(name)
+            except Exception:
+                pass
+        if sm:
+            hi = sorted(sm)[len(sm) // 2:]                       # samples under load: the upper half
+            out = {"sm_mhz": float(np.median(hi)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = min(args.cpu_sample_reads, synth.CONFIGS[args.config]["n_reads"])
+    for _ in range(args.warmup and 1):
+        cpu_port_run(args.config, n)
+    t_tot, reads, tests = 0.0, 0, 0
+    for _ in range(args.steps):
+        s, st, nr = cpu_port_run(args.config, n)
+        t_tot += s; reads += nr; tests += st["pair_tests"]
+    v = reads / t_tot
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.config, WORKLOADS[args.config]), "sample": "%d reads of the same distribution per step" % n},
+            "pair_tests_per_s": tests / t_tot,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d-read table of the %s distribution, whole clustering step, oracle/fslr_oracle.c "
+                                       "(the reference step is single-threaded: main.py:190-352 never reads --procs)" % (n, args.config)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+WORKLOADS = {
+    "C1": "5k reads, primer 21q1, default cutoffs",
+    "C2": "100k reads, 2-6 alignments/read, primers 21q1,17p6",
+    "C3": "1M reads, --cluster-mask subtelomere,L1_TALEN",
+    "C4": "10M reads, 2-6 alignments/read, primers 21q1,17p6 (40M table rows, 20M fillings)",
+    "C5": "2M reads with a 500k-read breakpoint hotspot",
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="C4")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cpu-sample-reads", type=int, default=CPU_SAMPLE_READS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fslr_b200.engine import DeviceTable, Engine, PinnedTable
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    ct, params = make_workload(args.config, args.scale)
+    R, A = ct.n_reads, ct.n_rows
+    dtab = DeviceTable(ct, eng.device)
+    ptab = PinnedTable(ct)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if world > 1:
+            return eng.run_sharded(dtab, ct, params, rank, world)
+        return eng.run_resident(dtab, ct, params)
+
+    def step_e2e():
+        if world > 1:
+            for k, t in ptab.cols.items():
+                dtab.cols[k].copy_(t[:A], non_blocking=True)
+            st = eng.run_sharded(dtab, ct, params, rank, world)
+            ptab.out_cluster[:R].copy_(dtab.out_cluster[:R], non_blocking=True)
+            ptab.out_n_reads[:R].copy_(dtab.out_n_reads[:R], non_blocking=True)
+            torch.cuda.synchronize()
+            return st
+        return eng.run_host(ptab, ct, params)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count()
+        e0.record()
+        sts = [fn() for _ in range(steps)]
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=eng.device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), sts, eng.launch_count() - l0
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, sts, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else {}
+    step_e2e()
+    ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
+
+    # correctness guard inside the bench: both paths agree with each other
+    res_a = dtab.out_cluster[:R].cpu().numpy()
+    if world == 1:
+        assert np.array_equal(res_a, ptab.out_cluster[:R].numpy()), "resident and host paths disagree"
+
+    st = sts[-1]
+    stage_ms = {k: float(np.mean([s["stage_ms"][k] for s in sts])) for k in st["stage_ms"]}
+    value = R * args.steps / (ms * 1e-3)
+    e2e = R * args.steps / (ms_e2e * 1e-3)
+    peak, peak_kind = load_peaks()
+    F, D, Q = st["n_fillings"], st["n_intervals"], st["n_query_reads"]
+    # algorithmic HBM bytes per stage: what one pass over the stage's data must move at least once
+    alg_bytes = {
+        "keep_fillings": 12 * A + 8 * ct.n_reads + 4 * F,
+        "data_order_mask": 2 * 8 * F + 16 * F + 24 * D,
+        "query_rank_read_lists": 2 * 8 * D + 8 * D + 32 * Q,
+        "chrom_sort": 2 * 8 * D + 2 * 12 * D,
+        "records_bands": 28 * D + 80 * D,
+        "pair_kernel": 32 * D + 16 * D + 8 * st["relation_entries"],
+        "replay": 64 * st["saturating_reads"],
+        "union_find": 8 * st["relation_entries"] + 8 * Q,
+        "numbering": 12 * Q + 16 * ct.n_reads,
+    }
+    top = max((k for k in alg_bytes), key=lambda k: stage_ms[k])
+    ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+    roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes[top],
+                "ms_per_launch": stage_ms[top]}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.config, WORKLOADS[args.config]) + ("" if args.scale == 1.0 else " x%g" % args.scale),
+                       "reads": R, "table_rows": A, "fillings": F, "intervals": D,
+                       "l2": "inputs larger than L2 (%.2f GB of columns re-read every step)" % (32 * A / 1e9),
+                       "parallelism": "1 GPU" if world == 1 else "table replicated, pair space sharded over %d GPUs, all-reduce + all-gather" % world},
+            "pair_tests_per_s": st["pair_tests"] / (stage_ms["pair_kernel"] + stage_ms["replay"]) * 1e3 if stage_ms["pair_kernel"] > 0 else None,
+            "pair_tests": st["pair_tests"], "band_pairs": st["band_pairs"], "edges": st["edges"], "clusters": st["components"],
+            "saturating_reads": st["saturating_reads"],
+            "stage_ms": stage_ms, "roofline": roofline, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": ptab.h2d_bytes,
+                    "d2h_bytes_per_step": ptab.d2h_bytes},
+            "gpu_launches": launches}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            n = min(args.cpu_sample_reads, R)
+            s, ost, nr = cpu_port_run(args.config, n)
+            line["cpu_baseline"] = {"value": nr / s, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "pair_tests_per_s": ost["pair_tests"] / s,
+                                    "sample": "%d-read table of the %s distribution, whole clustering step once (%.1f s), "
+                                              "oracle/fslr_oracle.c; the reference step is single-threaded" % (nr, args.config, s)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

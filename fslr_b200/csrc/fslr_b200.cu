@@ -46,6 +46,7 @@ struct fslrc_ctx {
     cudaEvent_t ev[FSLRC_N_STAGES + 1];
     // pipeline state (kept between the fslrc_mg_* stages)
     struct Pipe *pipe;
+    long long launches;      // kernels of this library launched since fslrc_create
 };
 
 static const char *STAGE_NAMES[FSLRC_N_STAGES] = {
@@ -82,6 +83,13 @@ static void free_all(fslrc_ctx *ctx) {
     do {                                            \
         int r__ = dalloc(ctx, &(ptr), (int64_t)(n)); \
         if (r__) return r__;                        \
+    } while (0)
+
+// every launch of one of OUR kernels goes through KL so that the count can be reported (bench.py "gpu_launches")
+#define KL(kernel, grid, block, ...)                         \
+    do {                                                     \
+        ctx->launches++;                                     \
+        kernel<<<(grid), (block), 0, st>>>(__VA_ARGS__);     \
     } while (0)
 
 static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
@@ -240,19 +248,22 @@ __global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const i
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < D) { int d = dp_in[k]; key[k] = ((unsigned long long)(unsigned)it_chrom[d] << 32) | (unsigned)it_start[d]; }
 }
-// SR0[p] = {start, end, T, q}; SR1[p] = {qlen2, Lq, naln | Ln<<16, m}; RM0[m] = {chrom, start, end, T}; RM1[m] = {pos, ub}
+// SR0[p] = {start, end, T, q}; SR1[p] = {qlen2, Lq, naln | Ln<<16, off<<6 | (L-1)} (off, L: the read's run in RM);
+// RM0[m] = {chrom, start, end, T}; RM1[m] = {pos, ub}
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
                           const int *__restrict__ it_chrom, const int *__restrict__ it_start, const int *__restrict__ it_end,
-                          const int *__restrict__ it_aln, const int4 *__restrict__ RI, double overlap, int4 *SR0, int4 *SR1,
-                          int4 *RM0, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
+                          const int *__restrict__ it_aln, const int4 *__restrict__ RI, const int4 *__restrict__ RD, double overlap,
+                          int4 *SR0, int4 *SR1, int4 *RM0, int *s_m, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
     int d = s_dp[p], m = rmidx[d], q = it_q[d], c = it_chrom[d];
     int s = it_start[d], e = it_end[d];
     int T = thr_f64(max(it_aln[d], 1), overlap);
     int4 ri = RI[q];
+    int4 rd = RD[q];
     SR0[p] = make_int4(s, e, T, q);
-    SR1[p] = make_int4(ri.x, ri.y, ri.z, m);
+    SR1[p] = make_int4(ri.x, ri.y, ri.z, (rd.x << 6) | ((rd.y - 1) & 63));
+    s_m[p] = m;
     RM0[m] = make_int4(c, s, e, T);
     s_chrom[p] = c; s_end[p] = e;
     int cprev = p > 0 ? it_chrom[s_dp[p - 1]] : -1;
@@ -261,7 +272,7 @@ __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__rest
     if (cnext != c) chrom_hi[c] = p + 1;
 }
 // ub(p): last sorted position on the chromosome with start <= end_p  (IntervalMap upper bound)
-__global__ void k_ub(int D, const int4 *__restrict__ SR0, const int4 *__restrict__ SR1, const int *__restrict__ s_chrom,
+__global__ void k_ub(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
                      const int *__restrict__ chrom_hi, int *ubS, int2 *RM1, unsigned long long *band_pairs) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     long long mine = 0;
@@ -270,7 +281,7 @@ __global__ void k_ub(int D, const int4 *__restrict__ SR0, const int4 *__restrict
         int lo = p, hi = chrom_hi[s_chrom[p]];                    // invariant: start[lo] <= e, answer in [lo, hi)
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (SR0[mid].x <= e) lo = mid; else hi = mid; }
         ubS[p] = lo;
-        RM1[SR1[p].w] = make_int2(p, lo);
+        RM1[s_m[p]] = make_int2(p, lo);
         mine = lo - p;
     }
     typedef cub::BlockReduce<long long, 256> BR;
@@ -282,7 +293,7 @@ struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { r
 
 // ---------------------------------------------------------------- pair-level pieces
 struct Tab {                 // kernel-side view of the tables
-    const int4 *SR0, *SR1, *RM0, *RD;
+    const int4 *SR0, *SR1, *RM0, *RD, *RI;
     const int2 *RM1;
     const int *ubS, *pmaxS, *s_chrom, *chrom_lo;
     int D, Q, Tedge;
@@ -316,10 +327,12 @@ __device__ __forceinline__ bool difflen_ok(int qa, int Lqa, int nla, int qb, int
 }
 
 // ---------------------------------------------------------------- stage 6: pair kernel (order-free relation)
-// One warp per sorted interval i (read a): scans a's closed band in chunks of 32 sorted positions, keeps lanes whose
-// interval reciprocally overlaps i (the only way a read pair can ever match), and for the canonical (first matching)
-// filling pair evaluates pass(a -> b).  Per read it counts passing candidates (capped: once the count reaches
-// edge_threshold the read is "saturating" and is replayed later, so its scan stops) and records (a, b).
+// One warp per sorted interval i (read a, filling fia): scans a's closed band in chunks of 32 sorted positions, keeps
+// lanes whose interval reciprocally overlaps i (the only way a read pair can ever match) and evaluates pass(a -> b).
+// The pair is recorded, and counted in degub[a], by the warp that owns its lexicographically first matching filling
+// pair.  Capping: once a read has edge_threshold passing candidates it is "saturating" (replayed later in query order)
+// and its scans stop; a warp also stops when its OWN filling has edge_threshold distinct passing candidates, so a
+// filling that is never canonical (a hotspot shared by 500k reads) cannot walk its whole band.
 #define PAIR_WARPS 8
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(Tab t, int shard, int nshard, int *degub, int2 *entries,
                                                            unsigned long long *n_entries, unsigned long long cap_entries,
@@ -330,39 +343,55 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(Tab t, int shard, int 
     unsigned long long tests = 0;
     for (int i = gw; i < t.D; i += nw) {
         if (nshard > 1 && ((i >> 6) % nshard) != shard) continue;
-        const int4 s0 = t.SR0[i], s1 = t.SR1[i];
+        const int4 s0 = __ldg(&t.SR0[i]), s1 = __ldg(&t.SR1[i]);
         const int a = s0.w;
-        const int4 rda = __ldg(&t.RD[a]);
-        const int La = rda.y, fia = s1.w - rda.x;
-        __syncwarp();
-        for (int k = lane; k < La; k += 32) As[w][k] = __ldg(&t.RM0[rda.x + k]);
-        __syncwarp();
+        const int offa = s1.w >> 6, La = (s1.w & 63) + 1;
+        const int top = t.ubS[i];
         const int lo = t.chrom_lo[t.s_chrom[i]];
-        for (int base = t.ubS[i]; base >= lo; base -= 32) {
+        __syncwarp();
+        int fia = -1;
+        for (int k = lane; k < La; k += 32) {
+            As[w][k] = __ldg(&t.RM0[offa + k]);
+            if (__ldg(&t.RM1[offa + k]).x == i) fia = k;
+        }
+        fia = __reduce_max_sync(0xffffffffu, fia);
+        __syncwarp();
+        int row_cnt = 0;                                                           // distinct passing candidates met by THIS filling
+        for (int base = top; base >= lo; base -= 32) {
             if (t.pmaxS[base] < s0.x) break;                                       // nothing further down reaches start_i
-            int deg = *(volatile int *)&degub[a];
-            if (deg >= t.Tedge) break;                                             // saturating: replayed in query order
+            if (*(volatile int *)&degub[a] >= t.Tedge) break;                      // saturating: replayed in query order
             const int p = base - lane;
             bool v = (p >= lo) && (p != i);
-            int4 c0 = make_int4(0, 0, 0, 0);
-            if (v) c0 = __ldg(&t.SR0[p]);
+            int4 c0 = make_int4(0, 0, 0, 0), c1 = make_int4(0, 0, 0, 0);
+            if (v) { c0 = __ldg(&t.SR0[p]); c1 = __ldg(&t.SR1[p]); }
             const int b = c0.w;
-            int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
-            v = v && (b != a) && (max(ov, 0) >= max(s0.z, c0.z));                   // this interval pair matches (cluster.py:157)
-            bool pass = false;
+            const int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
+            v = v && (b != a) && (max(ov, 0) >= max(s0.z, c0.z))                    // this interval pair matches (cluster.py:157)
+                  && difflen_ok(s1.x, s1.y, s1.z, c1.x, c1.y, c1.z);
+            bool pass = false, rowfirst = false;
             if (v) {
-                const int4 c1 = __ldg(&t.SR1[p]);
-                if (difflen_ok(s1.x, s1.y, s1.z, c1.x, c1.y, c1.z)) {
-                    const int4 rdb = __ldg(&t.RD[b]);
+                const int offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
+                // is p the first filling of b that matches filling fia?  (one count per read b and filling of a)
+                const int4 af = As[w][fia];
+                int fb_row = -1, fbp = -1;
+                for (int fb = 0; fb < Lb; fb++) {
+                    const int4 bb = __ldg(&t.RM0[offb + fb]);
+                    if (bb.y == c0.x && bb.z == c0.y && fbp < 0 && __ldg(&t.RM1[offb + fb]).x == p) fbp = fb;
+                    const int o2 = min(af.z, bb.z) - max(af.y, bb.y);
+                    if (fb_row < 0 && af.x == bb.x && max(o2, 0) >= max(af.w, bb.w)) fb_row = fb;
+                }
+                rowfirst = (fb_row == fbp);
+                if (rowfirst) {
                     int ffa, ffb;
-                    int n = greedy_ab(As[w], La, t.RM0 + rdb.x, rdb.y, &ffa, &ffb);
-                    if (ffa == fia && ffb == c1.w - rdb.x) {                         // canonical filling pair of (a, b)
-                        tests++;
-                        pass = n > 0 && (La + rdb.y - n) <= c_umax[n];               // cluster.py:165-170,218-219
-                    }
+                    const int n = greedy_ab(As[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
+                    tests++;
+                    const bool ok = n > 0 && (La + Lb - n) <= c_umax[n];              // cluster.py:165-170,218-219
+                    rowfirst = ok;
+                    pass = ok && ffa == fia && ffb == fbp;                            // canonical filling pair of (a, b)
                 }
             }
             const unsigned pm = __ballot_sync(0xffffffffu, pass);
+            row_cnt += __popc(__ballot_sync(0xffffffffu, rowfirst));
             if (pm) {
                 int old = 0;
                 if (lane == 0) old = atomicAdd(&degub[a], __popc(pm));
@@ -378,6 +407,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(Tab t, int shard, int 
                         if (k < cap_entries) entries[k] = make_int2(a, b); else atomicOr(err, EF_OVERFLOW);
                     }
                 }
+            }
+            if (row_cnt >= t.Tedge) {                                              // >= edge_threshold distinct passing reads
+                if (lane == 0) atomicMax(&degub[a], t.Tedge);
+                break;
             }
         }
     }
@@ -412,12 +445,29 @@ __device__ __forceinline__ bool visited_ba(const int4 *__restrict__ RM0, const i
 }
 
 // ---------------------------------------------------------------- stage 8: replay of saturating reads in query order
-// Persistent ticket kernel: plist holds the saturating reads in ascending query rank; a warp takes the next ticket,
-// re-runs that read's query exactly as cluster.py:197-224 would (descending sorted positions per filling, seen
-// pairs skipped, edges counted, break), and publishes the read's stops.  Whether an earlier-ranked saturating read b
-// "saw" the pair first is a function of b's stops, so a lane waits (spin on final[b]) only for smaller tickets.
+// Persistent ticket kernel: plist holds the saturating reads in ascending query rank, cut into RUNS of reads that depend on
+// each other (consecutive ranks of one PCR family, k_run_flags); a warp takes the next run and walks it back to back with
+// the band hot in L1 (several warps would only wait on each other), re-running each read's query exactly as
+// cluster.py:197-224 would (descending sorted positions per filling, seen pairs skipped, edges counted, break), and
+// publishes the read's stops.  Whether an earlier-ranked saturating read b "saw" the pair first is a function of b's stops,
+// so a lane waits (spin on final[b]) only for reads with smaller tickets, which are held by running warps: no deadlock.
 #define REPLAY_WARPS 4
-__global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, const int *__restrict__ isP,
+#define RUN_CAP 64
+// run starts: ticket k opens a new run unless its read's first filling reciprocally overlaps the previous saturating
+// read's first filling (same PCR family: they depend on each other), or the run would exceed RUN_CAP reads
+__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RD, const int4 *__restrict__ RM0, int *flag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nP) return;
+    int f = 1;
+    if (k > 0 && (k & (RUN_CAP - 1)) != 0) {
+        const int4 x = RM0[RD[plist[k - 1]].x], y = RM0[RD[plist[k]].x];
+        const int ov = min(x.z, y.z) - max(x.y, y.y);
+        if (x.x == y.x && max(ov, 0) >= max(x.w, y.w)) f = 0;
+    }
+    flag[k] = f;
+}
+__global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+                                                               const int *__restrict__ rstart, const int *__restrict__ isP,
                                                                int *stop, int *final_, unsigned *ticket, int2 *pedges,
                                                                unsigned long long *n_pedges, unsigned long long cap_pedges,
                                                                unsigned long long *n_tests, int *err) {
@@ -427,17 +477,20 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     unsigned long long tests = 0;
     for (;;) {
-        unsigned tk = 0;
-        if (lane == 0) tk = atomicAdd(ticket, 1u);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk >= (unsigned)nP) break;
-        const int a = plist[tk];
+        unsigned run = 0;
+        if (lane == 0) run = atomicAdd(ticket, 1u);
+        run = __shfl_sync(0xffffffffu, run, 0);
+        if (run >= (unsigned)nRuns) break;
+        const unsigned tk0 = (unsigned)__ldg(&rstart[run]);
+        const unsigned tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
+        for (unsigned tk = tk0; tk < tk1; tk++) {
+        const int a = __ldg(&plist[tk]);
         const int4 rda = __ldg(&t.RD[a]);
+        const int4 ria = __ldg(&t.RI[a]);                                         // {qlen2, Lq, naln|Ln}
         const int offa = rda.x, La = rda.y;
         __syncwarp();
         for (int k = lane; k < La; k += 32) { A0[w][k] = __ldg(&t.RM0[offa + k]); A1[w][k] = __ldg(&t.RM1[offa + k]); }
         __syncwarp();
-        const int4 ria = __ldg(&t.SR1[A1[w][0].x]);                               // {qlen2, Lq, naln|Ln, m} of a
         int edges = 0;
         for (int fi = 0; fi < La; fi++) {
             const int4 f = A0[w][fi];
@@ -451,38 +504,34 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
                 int b = -1;
                 if (p >= lo) {
                     const int4 c0 = __ldg(&t.SR0[p]);
+                    const int4 c1 = __ldg(&t.SR1[p]);
                     b = c0.w;
-                    if (b != a && c0.y >= f.y) {                // closed overlap (start_p <= end_f by p <= ub)
-                        const int4 c1 = __ldg(&t.SR1[p]);
-                        if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
-                            const int4 rdb = __ldg(&t.RD[b]);
-                            const int offb = rdb.x, Lb = rdb.y;
-                            bool met = false;                                          // pair already seen earlier in this very query?
-                            for (int g = 0; g < Lb && !met; g++) {
-                                const int4 bg = __ldg(&t.RM0[offb + g]);
-                                const int pg = __ldg(&t.RM1[offb + g]).x;
-                                for (int f2 = 0; f2 < fi; f2++) {
-                                    const int4 af = A0[w][f2];
-                                    if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
-                                }
-                                if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
+                    if (b != a && c0.y >= f.y                                          // closed overlap (start_p <= end_f by p <= ub)
+                        && difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
+                        const int offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
+                        const int bP = (b < a) ? __ldg(&isP[b]) : 0;
+                        bool met = false;                                              // pair already seen earlier in this very query?
+                        for (int g = 0; g < Lb && !met; g++) {
+                            const int4 bg = __ldg(&t.RM0[offb + g]);
+                            const int pg = __ldg(&t.RM1[offb + g]).x;
+                            for (int f2 = 0; f2 < fi; f2++) {
+                                const int4 af = A0[w][f2];
+                                if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
                             }
-                            if (!met) {
-                                int ffa, ffb;
-                                const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
-                                tests++;
-                                if (n > 0) {
-                                    reach = true;
-                                    if (b < a) {                                       // b queried first: did it get here?
-                                        if (!__ldg(&isP[b])) reach = false;            // never breaks -> it saw the pair
-                                        else {
-                                            while (*(volatile int *)&final_[b] == 0) __nanosleep(100);
-                                            __threadfence();
-                                            if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
-                                        }
-                                    }
-                                    edge = reach && (La + Lb - n) <= c_umax[n];
+                            if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
+                        }
+                        if (!met && (b > a || bP)) {                                   // b < a and never breaking: it saw the pair
+                            int ffa, ffb;
+                            const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
+                            tests++;
+                            if (n > 0) {
+                                reach = true;
+                                if (b < a) {                                           // b queried first: did it get here?
+                                    while (*(volatile int *)&final_[b] == 0) __nanosleep(40);
+                                    __threadfence();
+                                    if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
                                 }
+                                edge = reach && (La + Lb - n) <= c_umax[n];
                             }
                         }
                     }
@@ -513,6 +562,7 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
         __threadfence();
         __syncwarp();
         if (lane == 0) { *(volatile int *)&final_[a] = 1; }
+        }
     }
     for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
     if (lane == 0 && tests) atomicAdd(n_tests, tests);
@@ -715,59 +765,59 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(first, R); DA(last, R); DA(qmin, R); DA(qmax, R); DA(flagA, A); DA(posA, A);
     DA(P->q_of_rid, R);
     if (R > 0) {
-        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(first, R, 0x7fffffff);
-        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(last, R, -1);
-        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(qmin, R, 0x7fffffff);
-        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(qmax, R, (int)0x80000000);
-        k_fill<int><<<nblk(R, TB), TB, 0, st>>>(P->q_of_rid, R, -1);
+        KL(k_fill<int>, nblk(R, TB), TB, first, R, 0x7fffffff);
+        KL(k_fill<int>, nblk(R, TB), TB, last, R, -1);
+        KL(k_fill<int>, nblk(R, TB), TB, qmin, R, 0x7fffffff);
+        KL(k_fill<int>, nblk(R, TB), TB, qmax, R, (int)0x80000000);
+        KL(k_fill<int>, nblk(R, TB), TB, P->q_of_rid, R, -1);
     }
     if (A > 0) {
-        k_first_last<<<nblk(A, TB), TB, 0, st>>>(A, R, tb.read_id, first, last, P->err);
-        k_keep<<<nblk(A, TB), TB, 0, st>>>(A, R, tb.read_id, first, last, tb.qstart, tb.qend, flagA, qmin, qmax);
+        KL(k_first_last, nblk(A, TB), TB, A, R, tb.read_id, first, last, P->err);
+        KL(k_keep, nblk(A, TB), TB, A, R, tb.read_id, first, last, tb.qstart, tb.qend, flagA, qmin, qmax);
         int r = xscan(ctx, P, flagA, posA, A); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(posA, flagA, A, P->cnt + 0);
+        KL(k_total, 1, 1, posA, flagA, A, P->cnt + 0);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int F = P->F = (int)ctx->h_pin[0];
     if (tb.order && tb.n_order != F) return fail(ctx, FSLRC_ERR_ARG, "order has the wrong length (must equal the number of fillings)");
     DA(frow, F);
-    if (A > 0) k_compact_rows<<<nblk(A, TB), TB, 0, st>>>(A, flagA, posA, frow);
+    if (A > 0) KL(k_compact_rows, nblk(A, TB), TB, A, flagA, posA, frow);
     { int r = mark(ctx, 1); if (r) return r; }
     // ---- stage 2: data order (cluster.py:114) + mask
     int *dk = nullptr, *flagF, *posF;
     DA(flagF, F); DA(posF, F);
     if (tb.order) {
         dk = (int *)tb.order;
-        if (F > 0) k_check_order<<<nblk(F, TB), TB, 0, st>>>(F, tb.order, P->err);
+        if (F > 0) KL(k_check_order, nblk(F, TB), TB, F, tb.order, P->err);
     } else {
         int *key, *key2, *v; DA(key, F); DA(key2, F); DA(v, F); DA(dk, F);
         if (F > 0) {
-            k_start_keys<<<nblk(F, TB), TB, 0, st>>>(F, frow, tb.rstart, tb.rend, key);
-            k_iota<<<nblk(F, TB), TB, 0, st>>>(v, F);
+            KL(k_start_keys, nblk(F, TB), TB, F, frow, tb.rstart, tb.rend, key);
+            KL(k_iota, nblk(F, TB), TB, v, F);
             int r = sort_pairs<int>(ctx, P, key, key2, v, dk, F, 0, 32); if (r) return r;     // stable: ties keep bed order
         }
     }
     if (F > 0) {
-        k_mask_flags<<<nblk(F, TB), TB, 0, st>>>(F, dk, frow, tb.chrom, tb.rstart, tb.rend, pr.n_chrom, d_clen, d_cmask,
+        KL(k_mask_flags, nblk(F, TB), TB, F, dk, frow, tb.chrom, tb.rstart, tb.rend, pr.n_chrom, d_clen, d_cmask,
                                                    pr.mask_subtelomere, (long long)pr.subtel, flagF, P->err);
         int r = xscan(ctx, P, flagF, posF, F); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(posF, flagF, F, P->cnt + 1);
+        KL(k_total, 1, 1, posF, flagF, F, P->cnt + 1);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int D = P->D = (int)ctx->h_pin[1];
     int *it_rid, *it_chrom, *it_start, *it_end, *it_aln, *it_naln, *firstdp;
     DA(it_rid, D); DA(it_chrom, D); DA(it_start, D); DA(it_end, D); DA(it_aln, D); DA(it_naln, D); DA(firstdp, R);
-    if (R > 0) k_fill<int><<<nblk(R, TB), TB, 0, st>>>(firstdp, R, 0x7fffffff);
-    if (F > 0) k_build_items<<<nblk(F, TB), TB, 0, st>>>(F, dk, frow, flagF, posF, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size,
+    if (R > 0) KL(k_fill<int>, nblk(R, TB), TB, firstdp, R, 0x7fffffff);
+    if (F > 0) KL(k_build_items, nblk(F, TB), TB, F, dk, frow, flagF, posF, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size,
                                                           tb.n_alignments, it_rid, it_chrom, it_start, it_end, it_aln, it_naln, firstdp, P->err);
     { int r = mark(ctx, 2); if (r) return r; }
     // ---- stage 3: query rank + per-read lists
     int *flagD, *posD, *it_q;
     DA(flagD, D); DA(posD, D); DA(it_q, D);
     if (D > 0) {
-        k_is_first<<<nblk(D, TB), TB, 0, st>>>(D, it_rid, firstdp, flagD);
+        KL(k_is_first, nblk(D, TB), TB, D, it_rid, firstdp, flagD);
         int r = xscan(ctx, P, flagD, posD, D); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(posD, flagD, D, P->cnt + 2);
+        KL(k_total, 1, 1, posD, flagD, D, P->cnt + 2);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int Q = P->Q = (int)ctx->h_pin[2];
@@ -775,23 +825,23 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     int *qs, *rm_dp, *iotaD, *rmidx, *off, *len_end;
     DA(qs, D); DA(rm_dp, D); DA(iotaD, D); DA(rmidx, D); DA(off, Q); DA(len_end, Q);
     DA(P->RD, Q); DA(P->RI, Q);
-    if (R > 0) k_rank_reads<<<nblk(R, TB), TB, 0, st>>>(R, firstdp, posD, P->q_of_rid, P->rid_of_q);
+    if (R > 0) KL(k_rank_reads, nblk(R, TB), TB, R, firstdp, posD, P->q_of_rid, P->rid_of_q);
     if (D > 0) {
-        k_item_q<<<nblk(D, TB), TB, 0, st>>>(D, it_rid, P->q_of_rid, it_q);
-        k_iota<<<nblk(D, TB), TB, 0, st>>>(iotaD, D);
+        KL(k_item_q, nblk(D, TB), TB, D, it_rid, P->q_of_rid, it_q);
+        KL(k_iota, nblk(D, TB), TB, iotaD, D);
         int r = sort_pairs<int>(ctx, P, it_q, qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
-        k_read_bounds<<<nblk(D, TB), TB, 0, st>>>(D, qs, rm_dp, rmidx, off, len_end);
-        k_read_info<<<nblk(Q, TB), TB, 0, st>>>(Q, P->rid_of_q, off, len_end, rm_dp, it_naln, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
-        k_check_naln<<<nblk(D, TB), TB, 0, st>>>(D, it_q, it_naln, P->RI, P->err);
+        KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
+        KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, it_naln, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
+        KL(k_check_naln, nblk(D, TB), TB, D, it_q, it_naln, P->RI, P->err);
     }
     { int r = mark(ctx, 3); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
     unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1, *s_dp;
     DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D); DA(s_dp, D);
     if (D > 0) {
-        k_end_keys<<<nblk(D, TB), TB, 0, st>>>(D, it_end, ek);
+        KL(k_end_keys, nblk(D, TB), TB, D, it_end, ek);
         int r = sort_pairs<unsigned>(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
-        k_chrom_start_keys<<<nblk(D, TB), TB, 0, st>>>(D, v1, it_chrom, it_start, ck);
+        KL(k_chrom_start_keys, nblk(D, TB), TB, D, v1, it_chrom, it_start, ck);
         r = sort_pairs<unsigned long long>(ctx, P, ck, ck2, v1, s_dp, D, 0, 32 + bits_for(pr.n_chrom)); if (r) return r;
     }
     { int r = mark(ctx, 4); if (r) return r; }
@@ -801,9 +851,11 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(P->ubS, D); DA(P->pmaxS, D); DA(P->chrom_lo, pr.n_chrom); DA(P->chrom_hi, pr.n_chrom);
     if (pr.n_chrom > 0) { CK(cudaMemsetAsync(P->chrom_lo, 0, sizeof(int) * pr.n_chrom, st)); CK(cudaMemsetAsync(P->chrom_hi, 0, sizeof(int) * pr.n_chrom, st)); }
     if (D > 0) {
-        k_records<<<nblk(D, TB), TB, 0, st>>>(D, s_dp, rmidx, it_q, it_chrom, it_start, it_end, it_aln, P->RI, pr.overlap, P->SR0, P->SR1,
-                                               P->RM0, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
-        k_ub<<<nblk(D, 256), 256, 0, st>>>(D, P->SR0, P->SR1, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
+        if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
+        int *s_m; DA(s_m, D);
+        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, it_chrom, it_start, it_end, it_aln, P->RI, P->RD, pr.overlap, P->SR0, P->SR1,
+                                               P->RM0, s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
+        KL(k_ub, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
         size_t b = 0;
         CK(cub::DeviceScan::InclusiveScanByKey(nullptr, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
         int r = cub_tmp(ctx, P, b); if (r) return r;
@@ -814,7 +866,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     long long T = pr.edge_threshold;
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
     Tab &t = P->tab;
-    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RM1 = P->RM1; t.ubS = P->ubS; t.pmaxS = P->pmaxS;
+    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RI = P->RI; t.RM1 = P->RM1; t.ubS = P->ubS; t.pmaxS = P->pmaxS;
     t.s_chrom = P->s_chrom; t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
     // relation entries: every read records fewer than edge_threshold passing candidates, and never more than exist
     const unsigned long long band = (unsigned long long)ctx->h_pin[3];
@@ -837,7 +889,7 @@ static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
     if (P->D > 0) {
         int blocks = std::min(nblk(P->D, PAIR_WARPS), n_sms(ctx) * 8);
-        k_pair<<<blocks, PAIR_WARPS * 32, 0, st>>>(P->tab, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
+        KL(k_pair, blocks, PAIR_WARPS * 32, P->tab, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
                                                    P->cap_entries, (unsigned long long *)(P->cnt + 4), P->err);
     }
     return mark(ctx, 6);
@@ -850,14 +902,14 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     int *posQ;
     DA(posQ, Q);
     if (Q > 0) {
-        k_satur_flags<<<nblk(Q, TB), TB, 0, st>>>(Q, P->degub, P->Tedge, P->isP);
+        KL(k_satur_flags, nblk(Q, TB), TB, Q, P->degub, P->Tedge, P->isP);
         int r = xscan(ctx, P, P->isP, posQ, Q); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(posQ, P->isP, Q, P->cnt + 6);
+        KL(k_total, 1, 1, posQ, P->isP, Q, P->cnt + 6);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int nP = P->nP = (int)ctx->h_pin[6];
     DA(P->plist, nP);
-    if (Q > 0) k_compact_flagged<<<nblk(Q, TB), TB, 0, st>>>(Q, P->isP, posQ, P->plist);
+    if (Q > 0) KL(k_compact_flagged, nblk(Q, TB), TB, Q, P->isP, posQ, P->plist);
     // stops: a read that never breaks walks every filling's scan to the chromosome start; final = not saturating
     if (D > 0) CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st));
     if (Q > 0) CK(cudaMemsetAsync(P->final_, 0, sizeof(int) * Q, st));
@@ -869,22 +921,30 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     P->cap_pedges = std::min(capp, alt);
     DA(P->pedges, P->cap_pedges);
     if (nP > 0) {
-        int blocks = std::min(nblk(nP, REPLAY_WARPS), n_sms(ctx) * 8);
-        k_replay<<<blocks, REPLAY_WARPS * 32, 0, st>>>(P->tab, nP, P->plist, P->isP, P->stop, P->final_, P->ticket, P->pedges,
-                                                       (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err);
+        int *rflag, *rpos, *rstart;
+        DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
+        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RD, P->RM0, rflag);
+        int r = xscan(ctx, P, rflag, rpos, nP); if (r) return r;
+        KL(k_total, 1, 1, rpos, rflag, nP, P->cnt + 12);
+        KL(k_compact_flagged, nblk(nP, TB), TB, nP, rflag, rpos, rstart);
+        r = read_counts(ctx, P); if (r) return r;
+        const int nRuns = (int)ctx->h_pin[12];
+        int blocks = std::min(nblk(nRuns, REPLAY_WARPS), n_sms(ctx) * 16);
+        KL(k_replay, blocks, REPLAY_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->final_, P->ticket, P->pedges,
+           (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err);
     }
     { int r = mark(ctx, 8); if (r) return r; }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
     const unsigned long long nped = (unsigned long long)ctx->h_pin[7];
     if (Q > 0) {
-        k_iota<<<nblk(Q, TB), TB, 0, st>>>(P->parent, Q);
+        KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (nent > 0) k_union_entries<<<nblk((int64_t)nent, TB), TB, 0, st>>>(nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
+    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
                                                                            (unsigned long long *)(P->cnt + 8));
     // replayed edges are identical on every rank; rank `shard` contributes them once
-    if (nped > 0 && shard == 0) k_union_edges<<<nblk((int64_t)nped, TB), TB, 0, st>>>(nped, P->pedges, P->parent, P->ing);
+    if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing);
     (void)nshard;
     return mark(ctx, 9);
 }
@@ -897,15 +957,15 @@ static int pipe_number(fslrc_ctx *ctx, Pipe *P, int *out_cluster, int *out_n) {
     DA(isroot, Q); DA(cidx, Q); DA(csize, Q); DA(sflag, R); DA(spos, R);
     if (Q > 0) {
         CK(cudaMemsetAsync(csize, 0, sizeof(int) * Q, st));
-        k_flatten<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, isroot, csize);
+        KL(k_flatten, nblk(Q, TB), TB, Q, P->parent, P->ing, isroot, csize);
         int r = xscan(ctx, P, isroot, cidx, Q); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(cidx, isroot, Q, P->cnt + 9);
+        KL(k_total, 1, 1, cidx, isroot, Q, P->cnt + 9);
     }
     if (R > 0) {
-        k_single_flags<<<nblk(R, TB), TB, 0, st>>>(R, P->q_of_rid, P->ing, sflag);
+        KL(k_single_flags, nblk(R, TB), TB, R, P->q_of_rid, P->ing, sflag);
         int r = xscan(ctx, P, sflag, spos, R); if (r) return r;
-        k_total<<<1, 1, 0, st>>>(spos, sflag, R, P->cnt + 11);
-        k_number<<<nblk(R, TB), TB, 0, st>>>(R, P->q_of_rid, P->ing, P->parent, cidx, csize, spos, P->cnt + 9, out_cluster, out_n);
+        KL(k_total, 1, 1, spos, sflag, R, P->cnt + 11);
+        KL(k_number, nblk(R, TB), TB, R, P->q_of_rid, P->ing, P->parent, cidx, csize, spos, P->cnt + 9, out_cluster, out_n);
     }
     return mark(ctx, 10);
 }
@@ -957,7 +1017,7 @@ int fslrc_create(int device, fslrc_ctx **out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FSLRC_ERR_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) return FSLRC_ERR_CUDA;
     fslrc_ctx *ctx = new fslrc_ctx();
-    ctx->device = device; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->h_pin = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->h_pin = nullptr;
     if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
     cudaMemPool_t pool;                                   // keep freed scratch cached between calls
@@ -1073,8 +1133,8 @@ int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64
     DA(isroot, Q); DA(csize, Q); DA(fo, Q);
     if (Q > 0) {
         CK(cudaMemsetAsync(csize, 0, sizeof(int) * Q, st));
-        k_flatten<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, isroot, csize);
-        k_forest<<<nblk(Q, TB), TB, 0, st>>>(Q, P->parent, P->ing, fo, (unsigned long long *)(P->cnt + 10));
+        KL(k_flatten, nblk(Q, TB), TB, Q, P->parent, P->ing, isroot, csize);
+        KL(k_forest, nblk(Q, TB), TB, Q, P->parent, P->ing, fo, (unsigned long long *)(P->cnt + 10));
     }
     r = read_counts(ctx, P); if (r) return r;
     r = err_code(ctx); if (r) return r;
@@ -1089,10 +1149,10 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, 
     cudaStream_t st = ctx->stream;
     const int Q = P->Q, TB = 256;
     if (Q > 0) {
-        k_iota<<<nblk(Q, TB), TB, 0, st>>>(P->parent, Q);
+        KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (n_edges > 0) k_union_edges<<<nblk(n_edges, TB), TB, 0, st>>>((unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing);
+    if (n_edges > 0) KL(k_union_edges, nblk(n_edges, TB), TB, (unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing);
     int r = pipe_number(ctx, P, out_cluster, out_n_reads);
     if (!r) r = mark(ctx, 11);
     if (!r) { r = read_counts(ctx, P); if (!r) r = err_code(ctx); }
@@ -1102,6 +1162,8 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, 
     delete ctx->pipe; ctx->pipe = nullptr;
     return r;
 }
+
+long long fslrc_launch_count(const fslrc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s) {
     if (!ctx || !lane_ops_per_s) return FSLRC_ERR_ARG;

@@ -78,6 +78,13 @@ class PinnedTable:
         return 8 * self.n_reads
 
 
+class _DevView:
+    """Device memory owned by the library, exposed to torch through __cuda_array_interface__ (int32)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
 class Engine:
     def __init__(self, device=0):
         if not torch.cuda.is_available():
@@ -165,6 +172,48 @@ class Engine:
         n = table.n_reads
         return ClusterResult(ptab.out_cluster[:n].numpy().copy(), ptab.out_n_reads[:n].numpy().copy(),
                              bool(stats["no_clusters"]), stats)
+
+    # ---- multi-GPU: pair space sharded over ranks, one all-reduce + one all-gather
+    def run_sharded(self, dtab: DeviceTable, chrom_table, params: ClusterParams, rank, world, group=None):
+        """Every rank holds the whole table in HBM (dtab); the pair kernel runs on shard `rank` of `world`.
+        Exchange steps (torch.distributed, NCCL on GPUs): sum-all-reduce of the per-read passing-candidate counts,
+        then all-gather of each rank's spanning forest.  Every rank ends with the full result in dtab.out_*."""
+        import torch.distributed as dist
+        p = self._params(chrom_table, params)
+        t = self._table(dtab)
+        st = _native.Stats()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.fslrc_mg_prepare(self.ctx, C.byref(t), C.byref(p), C.c_void_p(stream)))
+        ptr, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.fslrc_mg_pair(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        if n.value > 0 and world > 1:
+            counts = torch.as_tensor(_DevView(ptr.value, (n.value,)), device=self.device)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        self._check(self.lib.fslrc_mg_replay(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        ne = int(n.value)
+        if world > 1:
+            sizes = torch.zeros(world, dtype=torch.int64, device=self.device)
+            mine = torch.tensor([ne], dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(sizes, mine, group=group)
+            sizes_h = sizes.cpu().tolist()
+            mx = max(max(sizes_h), 1)
+            send = torch.zeros(mx * 2, dtype=torch.int32, device=self.device)
+            if ne > 0:
+                send[:2 * ne] = torch.as_tensor(_DevView(ptr.value, (2 * ne,)), device=self.device)
+            recv = torch.empty(world * mx * 2, dtype=torch.int32, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            parts = [recv[r * mx * 2: r * mx * 2 + 2 * sizes_h[r]] for r in range(world)]
+            forest = torch.cat(parts).contiguous()
+            tot = int(sum(sizes_h))
+            fptr = forest.data_ptr() if tot > 0 else None
+        else:
+            tot, fptr = ne, ptr.value if ne > 0 else None
+        self._check(self.lib.fslrc_mg_finish(self.ctx, fptr, tot, dtab.out_cluster.data_ptr(), dtab.out_n_reads.data_ptr(),
+                                             C.byref(st)))
+        return st.as_dict(self.lib)
+
+    def launch_count(self):
+        return int(self.lib.fslrc_launch_count(self.ctx))
 
     def int_peak(self):
         v = C.c_double()

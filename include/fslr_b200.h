@@ -97,6 +97,8 @@ void fslrc_destroy(fslrc_ctx *ctx);
 const char *fslrc_last_error(const fslrc_ctx *ctx);
 const char *fslrc_stage_name(int stage);
 int fslrc_version(void);
+/* number of this library's own kernels launched through `ctx` so far (CUB's sort/scan kernels are not counted) */
+long long fslrc_launch_count(const fslrc_ctx *ctx);
 
 /* The whole step, main.py:233-257,334-342 (keep_fillings -> prepare_data -> build_interval_trees ->
  * query_interval_trees -> get_subgraphs -> cluster / n_reads columns), on DEVICE-resident columns.
