@@ -178,7 +178,7 @@ class Engine:
         """Every rank holds the whole table in HBM (dtab); the pair kernel runs on shard `rank` of `world`.
         Exchange steps (torch.distributed, NCCL on GPUs): sum-all-reduce of the per-read passing-candidate counts,
         then all-gather of each rank's spanning forest.  Every rank ends with the full result in dtab.out_*."""
-        import torch.distributed as dist
+        from .sharded import exchange_counts, exchange_forests
         p = self._params(chrom_table, params)
         t = self._table(dtab)
         st = _native.Stats()
@@ -187,24 +187,14 @@ class Engine:
         ptr, n = C.c_void_p(), C.c_int64()
         self._check(self.lib.fslrc_mg_pair(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
         if n.value > 0 and world > 1:
-            counts = torch.as_tensor(_DevView(ptr.value, (n.value,)), device=self.device)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+            exchange_counts(torch.as_tensor(_DevView(ptr.value, (n.value,)), device=self.device), group)
         self._check(self.lib.fslrc_mg_replay(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
         ne = int(n.value)
         if world > 1:
-            sizes = torch.zeros(world, dtype=torch.int64, device=self.device)
-            mine = torch.tensor([ne], dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(sizes, mine, group=group)
-            sizes_h = sizes.cpu().tolist()
-            mx = max(max(sizes_h), 1)
-            send = torch.zeros(mx * 2, dtype=torch.int32, device=self.device)
-            if ne > 0:
-                send[:2 * ne] = torch.as_tensor(_DevView(ptr.value, (2 * ne,)), device=self.device)
-            recv = torch.empty(world * mx * 2, dtype=torch.int32, device=self.device)
-            dist.all_gather_into_tensor(recv, send, group=group)
-            parts = [recv[r * mx * 2: r * mx * 2 + 2 * sizes_h[r]] for r in range(world)]
-            forest = torch.cat(parts).contiguous()
-            tot = int(sum(sizes_h))
+            local = (torch.as_tensor(_DevView(ptr.value, (2 * ne,)), device=self.device) if ne > 0
+                     else torch.zeros(0, dtype=torch.int32, device=self.device))
+            forest, per_rank = exchange_forests(local, group)
+            tot = int(sum(per_rank))
             fptr = forest.data_ptr() if tot > 0 else None
         else:
             tot, fptr = ne, ptr.value if ne > 0 else None

@@ -1,0 +1,58 @@
+"""The clustering block of /root/reference/fslr/main.py:190-352 around the B200 library: reads `<base>.mappings.bed`,
+clusters on the GPU, writes `<base>.mappings.cluster.bed` and `<base>.mappings.representative.bed` with the same
+columns and dtypes (float `cluster` / `n_reads`, main.py:334-349).  `chr_lengths` replaces the BAM-header lookup of
+main.py:225 (cluster.get_chromosome_lengths needs pysam).
+"""
+import json
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import cluster as gcluster
+from .table import ColumnarTable
+
+
+def cluster_step(bed_file, chr_lengths, cluster_mask="subtelomere", jaccard_cutoffs="1,1,0.66,0.66,0.66,0.5", overlap=0.8,
+                 n_alignment_diff=0.25, qlen_diff=0.04, filter_false=False, out_base=None, tie_order=None, device=0):
+    """Returns the annotated DataFrame, or None when main.py:247-249 would print "No clusters were found." and return."""
+    if isinstance(bed_file, str):
+        bed_file = pd.read_csv(bed_file, sep="\t")                               # main.py:209
+    print("Making clusters", file=sys.stderr)                                    # main.py:207
+    if filter_false:
+        bed_file = gcluster.delete_false(bed_file)                               # main.py:229-230
+    table = ColumnarTable.from_dataframe(bed_file, chr_lengths)
+    res = gcluster.cluster_table(table, cluster_mask=cluster_mask, jaccard_cutoffs=jaccard_cutoffs, overlap=overlap,
+                                 n_alignment_diff=n_alignment_diff, qlen_diff=qlen_diff, tie_order=tie_order, device=device)
+    if res.no_clusters:
+        print("No clusters were found.", file=sys.stderr)                        # main.py:247-249
+        return None
+    bed_file = bed_file.copy()
+    bed_file["cluster"] = res.cluster[table.read_id].astype(np.float64)          # main.py:334-342 (floats from the NaN merge)
+    bed_file["n_reads"] = res.n_reads[table.read_id].astype(np.float64)
+    if out_base:
+        bed_file.to_csv(f"{out_base}.mappings.cluster.bed", index=False, sep="\t")                 # main.py:349
+        rep = gcluster.choose_alignment(bed_file)                                                   # main.py:351-352
+        rep.to_csv(f"{out_base}.mappings.representative.bed", index=False, sep="\t")
+    return bed_file
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description="fslr clustering step on B200 (drop-in for `fslr --skip-alignment`'s clustering block)")
+    ap.add_argument("--bed", required=True, help="<base>.mappings.bed")
+    ap.add_argument("--chr-lengths", required=True, help="JSON {chrom: length} (BAM header lengths)")
+    ap.add_argument("--out-base", required=True)
+    ap.add_argument("--jaccard-cutoffs", default="1,1,0.66,0.66,0.66,0.5")
+    ap.add_argument("--overlap", type=float, default=0.8)
+    ap.add_argument("--n-alignment-diff", type=float, default=0.25)
+    ap.add_argument("--qlen-diff", type=float, default=0.04)
+    ap.add_argument("--cluster-mask", default="subtelomere")
+    ap.add_argument("--filter-false", action="store_true")
+    a = ap.parse_args(argv)
+    cluster_step(a.bed, json.load(open(a.chr_lengths)), a.cluster_mask, a.jaccard_cutoffs, a.overlap, a.n_alignment_diff,
+                 a.qlen_diff, a.filter_false, a.out_base)
+
+
+if __name__ == "__main__":
+    main()
