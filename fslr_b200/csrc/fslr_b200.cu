@@ -253,7 +253,8 @@ __global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const i
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
                           const int *__restrict__ it_chrom, const int *__restrict__ it_start, const int *__restrict__ it_end,
                           const int *__restrict__ it_aln, const int4 *__restrict__ RI, const int4 *__restrict__ RD, double overlap,
-                          int4 *SR0, int4 *SR1, int4 *RM0, int *s_m, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
+                          int4 *SR0, int4 *SR1, int4 *RM0, int *s_m, unsigned char *s_fi, int *s_chrom, int *s_end, int *chrom_lo,
+                          int *chrom_hi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
     int d = s_dp[p], m = rmidx[d], q = it_q[d], c = it_chrom[d];
@@ -264,6 +265,7 @@ __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__rest
     SR0[p] = make_int4(s, e, T, q);
     SR1[p] = make_int4(ri.x, ri.y, ri.z, (rd.x << 6) | ((rd.y - 1) & 63));
     s_m[p] = m;
+    s_fi[p] = (unsigned char)(m - rd.x);                             // index of this filling in its read's list
     RM0[m] = make_int4(c, s, e, T);
     s_chrom[p] = c; s_end[p] = e;
     int cprev = p > 0 ? it_chrom[s_dp[p - 1]] : -1;
@@ -289,13 +291,24 @@ __global__ void k_ub(int D, const int4 *__restrict__ SR0, const int *__restrict_
     long long s = BR(tmp).Sum(mine);
     if (threadIdx.x == 0 && s) atomicAdd(band_pairs, (unsigned long long)s);
 }
+// lb(p): first sorted position on the chromosome whose prefix-max end reaches start_p (nothing below can overlap p)
+__global__ void k_lb(int D, const int4 *__restrict__ SR0, const int *__restrict__ pmaxS, const int *__restrict__ s_chrom,
+                     const int *__restrict__ chrom_lo, int *lbS) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int st = SR0[p].x;
+    int lo = chrom_lo[s_chrom[p]], hi = p;                            // pmaxS[p] >= end_p >= start_p: the answer is <= p
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (pmaxS[mid] >= st) hi = mid; else lo = mid + 1; }
+    lbS[p] = lo;
+}
 struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 
 // ---------------------------------------------------------------- pair-level pieces
 struct Tab {                 // kernel-side view of the tables
     const int4 *SR0, *SR1, *RM0, *RD, *RI;
     const int2 *RM1;
-    const int *ubS, *pmaxS, *s_chrom, *chrom_lo;
+    const int *ubS, *lbS, *pmaxS, *s_chrom, *chrom_lo;
+    const unsigned char *s_fi;
     int D, Q, Tedge;
 };
 __constant__ int c_umax[LMAX + 1];
@@ -326,96 +339,217 @@ __device__ __forceinline__ bool difflen_ok(int qa, int Lqa, int nla, int qb, int
     return q_ok || n_ok;                                           // cluster.py:178-183 (skip only if both fail)
 }
 
-// ---------------------------------------------------------------- stage 6: pair kernel (order-free relation)
-// One warp per sorted interval i (read a, filling fia): scans a's closed band in chunks of 32 sorted positions, keeps
-// lanes whose interval reciprocally overlaps i (the only way a read pair can ever match) and evaluates pass(a -> b).
-// The pair is recorded, and counted in degub[a], by the warp that owns its lexicographically first matching filling
-// pair.  Capping: once a read has edge_threshold passing candidates it is "saturating" (replayed later in query order)
-// and its scans stop; a warp also stops when its OWN filling has edge_threshold distinct passing candidates, so a
-// filling that is never canonical (a hotspot shared by 500k reads) cannot walk its whole band.
-#define PAIR_WARPS 8
-__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair(Tab t, int shard, int nshard, int *degub, int2 *entries,
-                                                           unsigned long long *n_entries, unsigned long long cap_entries,
-                                                           unsigned long long *n_tests, int *err) {
-    __shared__ int4 As[PAIR_WARPS][LMAX];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int gw = blockIdx.x * PAIR_WARPS + w, nw = gridDim.x * PAIR_WARPS;
-    unsigned long long tests = 0;
-    for (int i = gw; i < t.D; i += nw) {
-        if (nshard > 1 && ((i >> 6) % nshard) != shard) continue;
-        const int4 s0 = __ldg(&t.SR0[i]), s1 = __ldg(&t.SR1[i]);
-        const int a = s0.w;
-        const int offa = s1.w >> 6, La = (s1.w & 63) + 1;
-        const int top = t.ubS[i];
-        const int lo = t.chrom_lo[t.s_chrom[i]];
-        __syncwarp();
-        int fia = -1;
-        for (int k = lane; k < La; k += 32) {
-            As[w][k] = __ldg(&t.RM0[offa + k]);
-            if (__ldg(&t.RM1[offa + k]).x == i) fia = k;
-        }
-        fia = __reduce_max_sync(0xffffffffu, fia);
-        __syncwarp();
-        int row_cnt = 0;                                                           // distinct passing candidates met by THIS filling
-        for (int base = top; base >= lo; base -= 32) {
-            if (t.pmaxS[base] < s0.x) break;                                       // nothing further down reaches start_i
-            if (*(volatile int *)&degub[a] >= t.Tedge) break;                      // saturating: replayed in query order
-            const int p = base - lane;
-            bool v = (p >= lo) && (p != i);
-            int4 c0 = make_int4(0, 0, 0, 0), c1 = make_int4(0, 0, 0, 0);
-            if (v) { c0 = __ldg(&t.SR0[p]); c1 = __ldg(&t.SR1[p]); }
-            const int b = c0.w;
-            const int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
-            v = v && (b != a) && (max(ov, 0) >= max(s0.z, c0.z))                    // this interval pair matches (cluster.py:157)
-                  && difflen_ok(s1.x, s1.y, s1.z, c1.x, c1.y, c1.z);
-            bool pass = false, rowfirst = false;
-            if (v) {
-                const int offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
-                // is p the first filling of b that matches filling fia?  (one count per read b and filling of a)
-                const int4 af = As[w][fia];
-                int fb_row = -1, fbp = -1;
-                for (int fb = 0; fb < Lb; fb++) {
-                    const int4 bb = __ldg(&t.RM0[offb + fb]);
-                    if (bb.y == c0.x && bb.z == c0.y && fbp < 0 && __ldg(&t.RM1[offb + fb]).x == p) fbp = fb;
-                    const int o2 = min(af.z, bb.z) - max(af.y, bb.y);
-                    if (fb_row < 0 && af.x == bb.x && max(o2, 0) >= max(af.w, bb.w)) fb_row = fb;
-                }
-                rowfirst = (fb_row == fbp);
-                if (rowfirst) {
-                    int ffa, ffb;
-                    const int n = greedy_ab(As[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
-                    tests++;
-                    const bool ok = n > 0 && (La + Lb - n) <= c_umax[n];              // cluster.py:165-170,218-219
-                    rowfirst = ok;
-                    pass = ok && ffa == fia && ffb == fbp;                            // canonical filling pair of (a, b)
-                }
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, pass);
-            row_cnt += __popc(__ballot_sync(0xffffffffu, rowfirst));
-            if (pm) {
-                int old = 0;
-                if (lane == 0) old = atomicAdd(&degub[a], __popc(pm));
-                old = __shfl_sync(0xffffffffu, old, 0);
-                const bool rec = pass && (old + __popc(pm & ((1u << lane) - 1u)) < t.Tedge);
-                const unsigned rm = __ballot_sync(0xffffffffu, rec);
-                if (rm) {
-                    unsigned long long at = 0;
-                    if (lane == 0) at = atomicAdd(n_entries, (unsigned long long)__popc(rm));
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (rec) {
-                        unsigned long long k = at + __popc(rm & ((1u << lane) - 1u));
-                        if (k < cap_entries) entries[k] = make_int2(a, b); else atomicOr(err, EF_OVERFLOW);
-                    }
-                }
-            }
-            if (row_cnt >= t.Tedge) {                                              // >= edge_threshold distinct passing reads
-                if (lane == 0) atomicMax(&degub[a], t.Tedge);
-                break;
+// ---------------------------------------------------------------- stage 6: tiled pair kernel (order-free relation)
+// A CTA owns a tile of PT_ROWS consecutive sorted intervals (one row per thread).  The union of the rows' closed bands is a
+// contiguous window of SR0 records, staged in shared memory with one TMA bulk copy (cp.async.bulk + mbarrier).
+//   phase 1 (lock step, shared memory + integer ALU only): every row walks its band PT_STEP positions per round and
+//            queues the interval pairs that reciprocally overlap (cluster.py:157) — the only way a read pair can match;
+//   phase 2 (dense): the queue is dealt out one pair per thread; a thread gathers both reads' filling lists and evaluates
+//            different_lengths_or_alignments, the greedy N-1 intersection and the per-N Jaccard cutoff for a -> b.
+// A read pair is counted/recorded once per direction, by the row that holds its lexicographically first matching filling
+// pair.  Capping: a row stops when its read reached edge_threshold passing candidates (it is replayed in query order
+// later), or when the row itself met edge_threshold distinct passing reads (then the read is saturating for certain).
+#define PT_ROWS 256
+#define PT_WIN 1024
+#define PT_STEP 4
+#define PT_QCAP (PT_ROWS * PT_STEP)
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ bool match4(const int4 a, const int4 b) {
+    return (a.x == b.x) && (max(min(a.z, b.z) - max(a.y, b.y), 0) >= max(a.w, b.w));
+}
+// a -> b for reads with <= N fillings, lists in registers.  Returns bit0: (fia, fbp) is the first filling of b matching
+// row fia; bit1: (fia, fbp) is the lexicographically first matching pair.  *n_out = greedy intersection (cluster.py:152-161).
+template <int N>
+__device__ __forceinline__ int eval_small(const int4 *__restrict__ A, int La, const int4 *__restrict__ B, int Lb, int fia, int fbp, int *n_out) {
+    int4 a[N], b[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        a[k] = k < La ? __ldg(&A[k]) : make_int4(-1, 0, 0, 0x7fffffff);
+        b[k] = k < Lb ? __ldg(&B[k]) : make_int4(-2, 0, 0, 0x7fffffff);
+    }
+    unsigned m[N];
+    unsigned mrow = 0;
+#pragma unroll
+    for (int fa = 0; fa < N; fa++) {
+        unsigned r = 0;
+#pragma unroll
+        for (int fb = 0; fb < N; fb++) r |= (match4(a[fa], b[fb]) ? 1u : 0u) << fb;
+        m[fa] = r;
+        if (fa == fia) mrow = r;
+    }
+    *n_out = 0;
+    if (mrow & ((1u << fbp) - 1u)) return 0;                       // an earlier filling of b already matches this row
+    unsigned used = 0;
+    int n = 0, ffa = -1, ffb = -1;
+#pragma unroll
+    for (int fa = 0; fa < N; fa++) {
+        if (m[fa] && ffa < 0) { ffa = fa; ffb = __ffs(m[fa]) - 1; }
+        const unsigned avail = m[fa] & ~used;
+        if (avail) { used |= avail & (0u - avail); n++; }
+    }
+    *n_out = n;
+    return 1 | ((ffa == fia && ffb == fbp) ? 2 : 0);
+}
+__device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, const int4 *__restrict__ B, int Lb, int fia, int fbp, int *n_out) {
+    const int4 af = __ldg(&A[fia]);
+    *n_out = 0;
+    for (int fb = 0; fb < fbp; fb++) if (match4(af, __ldg(&B[fb]))) return 0;
+    unsigned long long used = 0;
+    int n = 0, ffa = -1, ffb = -1;
+    for (int fa = 0; fa < La; fa++) {
+        const int4 a = __ldg(&A[fa]);
+        for (int fb = 0; fb < Lb; fb++) {
+            if (match4(a, __ldg(&B[fb]))) {
+                if (ffa < 0) { ffa = fa; ffb = fb; }
+                if (!((used >> fb) & 1ull)) { used |= 1ull << fb; n++; break; }
             }
         }
     }
-    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
-    if (lane == 0 && tests) atomicAdd(n_tests, tests);
+    *n_out = n;
+    return 1 | ((ffa == fia && ffb == fbp) ? 2 : 0);
+}
+
+__global__ void __launch_bounds__(PT_ROWS) k_pair(Tab t, int nTiles, int shard, int nshard, int *degub, int2 *entries,
+                                                   unsigned long long *n_entries, unsigned long long cap_entries,
+                                                   unsigned long long *n_tests, int *err) {
+    __shared__ __align__(128) int4 win[PT_WIN];
+    __shared__ int4 rowS0[PT_ROWS];
+    __shared__ int4 rowS1[PT_ROWS];
+    __shared__ int2 queue[PT_QCAP];
+    __shared__ int2 outq[PT_QCAP];
+    __shared__ int rowcnt[PT_ROWS];
+    __shared__ unsigned char rowfi[PT_ROWS];
+    __shared__ int qn, outn, s_whi, s_wlo;
+    __shared__ unsigned long long s_base;
+    __shared__ __align__(8) unsigned long long mbar;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned bar = smem_u32(&mbar);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    unsigned parity = 0;
+    unsigned long long tests = 0;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        if (nshard > 1 && (tile % nshard) != shard) continue;
+        const int i0 = tile * PT_ROWS, i = i0 + tid;
+        const bool valid = i < t.D;
+        int4 s0 = make_int4(0, 0, 0, -1), s1 = make_int4(0, 0, 0, 0);
+        int lb = 1, ub = 0;
+        if (valid) { s0 = __ldg(&t.SR0[i]); s1 = __ldg(&t.SR1[i]); lb = __ldg(&t.lbS[i]); ub = __ldg(&t.ubS[i]); rowfi[tid] = __ldg(&t.s_fi[i]); }
+        rowS0[tid] = s0; rowS1[tid] = s1; rowcnt[tid] = 0;
+        if (tid == 0) { qn = 0; outn = 0; s_whi = 0; s_wlo = lb; }                 // lb is monotone: row 0 has the smallest
+        __syncthreads();
+        const int wmax = __reduce_max_sync(0xffffffffu, ub);
+        if (lane == 0) atomicMax(&s_whi, wmax);
+        __syncthreads();
+        const int wlo = s_wlo;
+        const int wn = min(s_whi - wlo + 1, PT_WIN);
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // earlier generic reads of `win` are done
+            mbar_expect_tx(bar, (unsigned)wn * 16u);
+            bulk_g2s(smem_u32(win), t.SR0 + wlo, (unsigned)wn * 16u, bar);
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+        const int a = s0.w;
+        bool dead = !valid;
+        int off = 0, round = 0;
+        for (;;) {
+            // ---- phase 1: cheap interval-pair test from shared memory
+#pragma unroll
+            for (int sidx = 0; sidx < PT_STEP; sidx++) {
+                const int p = ub - off - sidx;
+                bool push = false;
+                if (!dead && p >= lb && p != i) {
+                    const int wi = p - wlo;
+                    const int4 c0 = (wi < wn) ? win[wi] : __ldg(&t.SR0[p]);
+                    const int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
+                    push = (c0.w != a) && (max(ov, 0) >= max(s0.z, c0.z));
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, push);
+                if (pm) {
+                    int at = 0;
+                    if (lane == 0) at = atomicAdd(&qn, __popc(pm));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (push) queue[at + __popc(pm & ((1u << lane) - 1u))] = make_int2(tid, p);
+                }
+            }
+            off += PT_STEP;
+            round++;
+            __syncthreads();
+            // ---- phase 2: dense evaluation of the queued pairs
+            const int nq = qn;
+            for (int base = 0; base < nq; base += PT_ROWS) {
+                const int e = base + tid;
+                if (e < nq) {
+                    const int2 rp = queue[e];
+                    const int4 r0 = rowS0[rp.x], r1 = rowS1[rp.x];
+                    const int wi = rp.y - wlo;
+                    const int4 c0 = (wi < wn) ? win[wi] : __ldg(&t.SR0[rp.y]);
+                    const int4 c1 = __ldg(&t.SR1[rp.y]);
+                    if (difflen_ok(r1.x, r1.y, r1.z, c1.x, c1.y, c1.z)) {
+                        const int offa = r1.w >> 6, La = (r1.w & 63) + 1, offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
+                        const int fia = rowfi[rp.x], fbp = __ldg(&t.s_fi[rp.y]);
+                        int n, fl;
+                        if (La <= 4 && Lb <= 4) fl = eval_small<4>(t.RM0 + offa, La, t.RM0 + offb, Lb, fia, fbp, &n);
+                        else fl = eval_general(t.RM0 + offa, La, t.RM0 + offb, Lb, fia, fbp, &n);
+                        if (fl & 1) {
+                            tests++;
+                            if (n > 0 && (La + Lb - n) <= c_umax[n]) {                  // cluster.py:165-170,218-219
+                                atomicAdd(&rowcnt[rp.x], 1);
+                                if (fl & 2) {                                          // canonical filling pair of (a, b)
+                                    const int old = atomicAdd(&degub[r0.w], 1);
+                                    if (old < t.Tedge) outq[atomicAdd(&outn, 1)] = make_int2(r0.w, c0.w);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- flush recorded pairs: one global reservation per CTA and round
+            const int on = outn;
+            if (on) {
+                if (tid == 0) s_base = atomicAdd(n_entries, (unsigned long long)on);
+                __syncthreads();
+                for (int k = tid; k < on; k += PT_ROWS) {
+                    const unsigned long long idx = s_base + k;
+                    if (idx < cap_entries) entries[idx] = outq[k]; else atomicOr(err, EF_OVERFLOW);
+                }
+            }
+            if (!dead) {
+                if (ub - off < lb) dead = true;
+                else if (rowcnt[tid] >= t.Tedge) { atomicMax(&degub[a], t.Tedge); dead = true; }
+                else if ((round & 3) == 0 && *(volatile int *)&degub[a] >= t.Tedge) dead = true;
+            }
+            __syncthreads();
+            if (tid == 0) { qn = 0; outn = 0; }
+            if (!__syncthreads_or(!dead)) break;
+        }
+    }
+    typedef cub::BlockReduce<unsigned long long, PT_ROWS> BR;
+    __shared__ typename BR::TempStorage tmp;
+    const unsigned long long ts = BR(tmp).Sum(tests);
+    if (tid == 0 && ts) atomicAdd(n_tests, ts);
 }
 
 // ---------------------------------------------------------------- stage 7: saturating set
@@ -685,7 +819,8 @@ struct Pipe {
     int *q_of_rid, *rid_of_q;
     int4 *SR0, *SR1, *RM0, *RD, *RI;
     int2 *RM1;
-    int *ubS, *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
+    int *ubS, *lbS, *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
+    unsigned char *s_fi;
     int *degub, *isP, *plist, *stop, *final_;
     int2 *entries, *pedges;
     unsigned long long cap_entries, cap_pedges;
@@ -852,21 +987,22 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (pr.n_chrom > 0) { CK(cudaMemsetAsync(P->chrom_lo, 0, sizeof(int) * pr.n_chrom, st)); CK(cudaMemsetAsync(P->chrom_hi, 0, sizeof(int) * pr.n_chrom, st)); }
     if (D > 0) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
-        int *s_m; DA(s_m, D);
+        int *s_m; DA(s_m, D); DA(P->s_fi, D); DA(P->lbS, D);
         KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, it_chrom, it_start, it_end, it_aln, P->RI, P->RD, pr.overlap, P->SR0, P->SR1,
-                                               P->RM0, s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
+                                               P->RM0, s_m, P->s_fi, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
         KL(k_ub, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
         size_t b = 0;
         CK(cub::DeviceScan::InclusiveScanByKey(nullptr, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
         int r = cub_tmp(ctx, P, b); if (r) return r;
         b = P->cub_bytes;
         CK(cub::DeviceScan::InclusiveScanByKey(P->cub_tmp, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
+        KL(k_lb, nblk(D, TB), TB, D, P->SR0, P->pmaxS, P->s_chrom, P->chrom_lo, P->lbS);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     long long T = pr.edge_threshold;
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
     Tab &t = P->tab;
-    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RI = P->RI; t.RM1 = P->RM1; t.ubS = P->ubS; t.pmaxS = P->pmaxS;
+    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RI = P->RI; t.RM1 = P->RM1; t.ubS = P->ubS; t.lbS = P->lbS; t.s_fi = P->s_fi; t.pmaxS = P->pmaxS;
     t.s_chrom = P->s_chrom; t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
     // relation entries: every read records fewer than edge_threshold passing candidates, and never more than exist
     const unsigned long long band = (unsigned long long)ctx->h_pin[3];
@@ -888,9 +1024,10 @@ static int n_sms(fslrc_ctx *ctx) {
 static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
     if (P->D > 0) {
-        int blocks = std::min(nblk(P->D, PAIR_WARPS), n_sms(ctx) * 8);
-        KL(k_pair, blocks, PAIR_WARPS * 32, P->tab, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
-                                                   P->cap_entries, (unsigned long long *)(P->cnt + 4), P->err);
+        const int nTiles = nblk(P->D, PT_ROWS);
+        int blocks = std::min(nTiles, n_sms(ctx) * 5);
+        KL(k_pair, blocks, PT_ROWS, P->tab, nTiles, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
+           P->cap_entries, (unsigned long long *)(P->cnt + 4), P->err);
     }
     return mark(ctx, 6);
 }

@@ -38,5 +38,5 @@ def exchange_forests(local_edges, group=None):
 
 
 def shard_of_position(i, world):
-    """Rank owning sorted interval position i: blocks of 64 consecutive positions, round robin (k_pair)."""
-    return (i >> 6) % world
+    """Rank owning sorted interval position i: tiles of 256 consecutive positions, round robin (k_pair)."""
+    return (i >> 8) % world
