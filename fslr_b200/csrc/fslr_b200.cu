@@ -2,8 +2,8 @@
 //
 // Replaces, behind the C ABI of include/fslr_b200.h, the reference calls of
 // /root/reference/fslr/main.py:233-257,334-342 into /root/reference/fslr/cluster.py:
-//   keep_fillings (cluster.py:14-31)           -> k_first_last, k_keep, k_compact_rows
-//   prepare_data + mask_sequences2 (:89-121)    -> k_item_keys, radix sort by start, k_mask_flags, k_build_items
+//   keep_fillings (cluster.py:14-31)           -> k_first_last, k_keep, k_fill_records
+//   prepare_data + mask_sequences2 (:89-121)    -> k_mask_flags, k_compact_fillings, radix sort by start, k_build_items
 //   query_intervals dict order (:189-191)       -> k_first_dp, k_is_first, scan, sort by query rank
 //   build_interval_trees / IntervalMap (:124-130, third-party superintervals)
 //                                               -> sort by (chrom, start, end desc, data order), k_ub, prefix-max of ends
@@ -141,59 +141,67 @@ __global__ void k_keep(int A, int R, const int *__restrict__ rid, const int *__r
     }
     flag[i] = keep;
 }
-__global__ void k_compact_rows(int A, const int *__restrict__ flag, const int *__restrict__ pos, int *frow) {
+// fillings in bed order as packed records: FR0[k] = {read_id, chrom, start, end}, FR1[k] = {aln_size, n_alignments}
+// (start/end = min/max of rstart, rend: cluster.py:111-112).  One coalesced pass over the kept rows.
+__global__ void k_fill_records(int A, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ rid,
+                               const int *__restrict__ chrom, const int *__restrict__ rstart, const int *__restrict__ rend,
+                               const int *__restrict__ aln, const int *__restrict__ naln, int n_chrom, int4 *FR0, int2 *FR1, int *err) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A && flag[i]) frow[pos[i]] = i;
+    if (i >= A || !flag[i]) return;
+    const int k = pos[i];
+    const int c = chrom[i], rs = rstart[i], re = rend[i];
+    if ((unsigned)c >= (unsigned)n_chrom || min(rs, re) < 0) atomicOr(err, EF_RANGE);
+    FR0[k] = make_int4(rid[i], c, min(rs, re), max(rs, re));
+    FR1[k] = make_int2(aln[i], naln[i]);
 }
 
 // ---------------------------------------------------------------- stage 2: prepare_data + mask (cluster.py:109-121, 89-106)
-__global__ void k_start_keys(int F, const int *__restrict__ frow, const int *__restrict__ rstart, const int *__restrict__ rend, int *key) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < F) { int r = frow[k]; key[k] = min(rstart[r], rend[r]); }
+__device__ __forceinline__ bool is_masked(const int4 f, int n_chrom, const long long *__restrict__ clen,
+                                          const unsigned char *__restrict__ cmasked, int sub_on, long long subtel) {
+    if ((unsigned)f.y >= (unsigned)n_chrom) return true;
+    bool masked = cmasked[f.y] != 0;                                          // cluster.py:96
+    const long long cl = clen[f.y];
+    if (sub_on && cl > 1000000 && ((long long)f.z < subtel || cl - (long long)f.w < subtel)) masked = true;   // :94,98-100
+    return masked;
 }
-__global__ void k_check_order(int F, const int *__restrict__ order, int *err) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < F && (unsigned)order[k] >= (unsigned)F) atomicOr(err, EF_RANGE);
-}
-__global__ void k_mask_flags(int F, const int *__restrict__ dk, const int *__restrict__ frow, const int *__restrict__ chrom,
-                             const int *__restrict__ rstart, const int *__restrict__ rend, int n_chrom,
+// flags over the fillings taken in the order `perm` (NULL = bed order)
+__global__ void k_mask_flags(int F, const int *__restrict__ perm, const int4 *__restrict__ FR0, int n_chrom,
                              const long long *__restrict__ clen, const unsigned char *__restrict__ cmasked, int sub_on,
                              long long subtel, int *flag, int *err) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= F) return;
-    int row = frow[dk[k]];
-    int c = chrom[row];
-    if ((unsigned)c >= (unsigned)n_chrom) { atomicOr(err, EF_RANGE); flag[k] = 0; return; }
-    int s = min(rstart[row], rend[row]), e = max(rstart[row], rend[row]);
-    if (s < 0) atomicOr(err, EF_RANGE);
-    bool masked = cmasked[c] != 0;                                          // cluster.py:96
-    long long cl = clen[c];
-    if (sub_on && cl > 1000000 && ((long long)s < subtel || cl - (long long)e < subtel)) masked = true;   // :94,98-100
-    flag[k] = masked ? 0 : 1;
+    int fk = k;
+    if (perm) { fk = perm[k]; if ((unsigned)fk >= (unsigned)F) { atomicOr(err, EF_RANGE); flag[k] = 0; return; } }
+    flag[k] = is_masked(FR0[fk], n_chrom, clen, cmasked, sub_on, subtel) ? 0 : 1;
 }
-// data items in data order (SoA)
-__global__ void k_build_items(int F, const int *__restrict__ dk, const int *__restrict__ frow, const int *__restrict__ flag,
-                              const int *__restrict__ dpos, const int *__restrict__ rid, const int *__restrict__ chrom,
-                              const int *__restrict__ rstart, const int *__restrict__ rend, const int *__restrict__ aln,
-                              const int *__restrict__ naln, int *it_rid, int *it_chrom, int *it_start, int *it_end, int *it_aln,
-                              int *it_naln, int *firstdp, int *err) {
+// unmasked fillings, compacted: sort key (start) + filling index, or directly the data-order list when perm is given
+__global__ void k_compact_fillings(int F, const int *__restrict__ perm, const int *__restrict__ flag, const int *__restrict__ pos,
+                                   const int4 *__restrict__ FR0, int *key, int *val) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= F || !flag[k]) return;
-    int row = frow[dk[k]], d = dpos[k];
-    int r = rid[row];
-    it_rid[d] = r; it_chrom[d] = chrom[row];
-    it_start[d] = min(rstart[row], rend[row]); it_end[d] = max(rstart[row], rend[row]);
-    int a = aln[row], n = naln[row];
-    it_aln[d] = a; it_naln[d] = n;
-    if (a <= 0 || n <= 0) atomicOr(err, EF_ZERO);
-    if (n >= 65535) atomicOr(err, EF_RANGE);
-    atomicMin(&firstdp[r], d);
+    const int fk = perm ? perm[k] : k;
+    const int u = pos[k];
+    if (key) key[u] = FR0[fk].z;
+    val[u] = fk;
+}
+// data items in data order: IT0[d] = {read_id, chrom, start, end}, IT1[d] = {aln_size, n_alignments}
+__global__ void k_build_items(int D, const int *__restrict__ dfill, const int4 *__restrict__ FR0, const int2 *__restrict__ FR1,
+                              int4 *IT0, int2 *IT1, int *firstdp, int *err) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int fk = dfill[d];
+    const int4 f0 = FR0[fk];
+    const int2 f1 = FR1[fk];
+    IT0[d] = f0; IT1[d] = f1;
+    if (f1.x <= 0 || f1.y <= 0) atomicOr(err, EF_ZERO);
+    if (f1.y >= 65535) atomicOr(err, EF_RANGE);
+    atomicMin(&firstdp[f0.x], d);
 }
 
 // ---------------------------------------------------------------- stage 3: query rank (cluster.py:189-191) + per-read lists
-__global__ void k_is_first(int D, const int *__restrict__ it_rid, const int *__restrict__ firstdp, int *flag) {
+__global__ void k_is_first(int D, const int4 *__restrict__ IT0, const int *__restrict__ firstdp, int *flag) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D) flag[d] = (firstdp[it_rid[d]] == d);
+    if (d < D) flag[d] = (firstdp[IT0[d].x] == d);
 }
 __global__ void k_rank_reads(int R, const int *__restrict__ firstdp, const int *__restrict__ rank_at, int *q_of_rid, int *rid_of_q) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,9 +211,9 @@ __global__ void k_rank_reads(int R, const int *__restrict__ firstdp, const int *
     if (f != 0x7fffffff) { q = rank_at[f]; rid_of_q[q] = r; }
     q_of_rid[r] = q;
 }
-__global__ void k_item_q(int D, const int *__restrict__ it_rid, const int *__restrict__ q_of_rid, int *it_q) {
+__global__ void k_item_q(int D, const int4 *__restrict__ IT0, const int *__restrict__ q_of_rid, int *it_q) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D) it_q[d] = q_of_rid[it_rid[d]];
+    if (d < D) it_q[d] = q_of_rid[IT0[d].x];
 }
 // rm order: items grouped by query rank, data order inside a read
 __global__ void k_read_bounds(int D, const int *__restrict__ qs /*sorted q*/, const int *__restrict__ rm_dp, int *rmidx, int *off, int *len_end) {
@@ -218,14 +226,14 @@ __global__ void k_read_bounds(int D, const int *__restrict__ qs /*sorted q*/, co
 }
 // per read: qlen2, n_alignments and their ratio thresholds (cluster.py:26-29,178-183)
 __global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *__restrict__ off, const int *__restrict__ len_end,
-                            const int *__restrict__ rm_dp, const int *__restrict__ it_naln, const int *__restrict__ qmin,
+                            const int *__restrict__ rm_dp, const int2 *__restrict__ IT1, const int *__restrict__ qmin,
                             const int *__restrict__ qmax, double qlen_c, double naln_c, int4 *RD, int4 *RI, int *err) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     int r = rid_of_q[q], o = off[q], L = len_end[q] - o;
     if (L > LMAX) atomicOr(err, EF_TOOMANY);
     long long ql = (long long)qmax[r] - (long long)qmin[r];
-    int na = it_naln[rm_dp[o]];
+    int na = IT1[rm_dp[o]].y;
     if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
     if (ql > 0x7fffffffLL) { atomicOr(err, EF_RANGE); ql = 1; }
     int Ln = thr_f64(na, naln_c);
@@ -233,54 +241,56 @@ __global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *
     RD[q] = make_int4(o, L, r, 0);
     RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), 0);
 }
-__global__ void k_check_naln(int D, const int *__restrict__ it_q, const int *__restrict__ it_naln, const int4 *__restrict__ RI, int *err) {
+__global__ void k_check_naln(int D, const int *__restrict__ it_q, const int2 *__restrict__ IT1, const int4 *__restrict__ RI, int *err) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D && (RI[it_q[d]].z & 0xffff) != it_naln[d]) atomicOr(err, EF_NALN);
+    if (d < D && (RI[it_q[d]].z & 0xffff) != IT1[d].y) atomicOr(err, EF_NALN);
 }
 
 // ---------------------------------------------------------------- stage 4/5: IntervalMap order + records + bands
-__global__ void k_end_keys(int D, const int *__restrict__ it_end, unsigned *key) {
+__global__ void k_end_keys(int D, const int4 *__restrict__ IT0, unsigned *key) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D) key[d] = ~(unsigned)it_end[d];                       // ascending ~end == end descending
+    if (d < D) key[d] = ~(unsigned)IT0[d].w;                        // ascending ~end == end descending
 }
-__global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const int *__restrict__ it_chrom, const int *__restrict__ it_start,
-                                   unsigned long long *key) {
+__global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const int4 *__restrict__ IT0, unsigned long long *key) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < D) { int d = dp_in[k]; key[k] = ((unsigned long long)(unsigned)it_chrom[d] << 32) | (unsigned)it_start[d]; }
+    if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = ((unsigned long long)(unsigned)it.y << 32) | (unsigned)it.z; }
 }
 // SR0[p] = {start, end, T, q}; SR1[p] = {qlen2, Lq, naln | Ln<<16, off<<6 | (L-1)} (off, L: the read's run in RM);
 // RM0[m] = {chrom, start, end, T}; RM1[m] = {pos, ub}
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
-                          const int *__restrict__ it_chrom, const int *__restrict__ it_start, const int *__restrict__ it_end,
-                          const int *__restrict__ it_aln, const int4 *__restrict__ RI, const int4 *__restrict__ RD, double overlap,
-                          int4 *SR0, int4 *SR1, int4 *RM0, int *s_m, unsigned char *s_fi, int *s_chrom, int *s_end, int *chrom_lo,
-                          int *chrom_hi) {
+                          const int4 *__restrict__ IT0, const int2 *__restrict__ IT1, const int4 *__restrict__ RI,
+                          const int4 *__restrict__ RD, double overlap, int4 *SR0, int4 *SR1, int4 *RM0, int *s_m,
+                          unsigned char *s_fi, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
-    int d = s_dp[p], m = rmidx[d], q = it_q[d], c = it_chrom[d];
-    int s = it_start[d], e = it_end[d];
-    int T = thr_f64(max(it_aln[d], 1), overlap);
-    int4 ri = RI[q];
-    int4 rd = RD[q];
+    const int d = s_dp[p], m = rmidx[d], q = it_q[d];
+    const int4 it = IT0[d];
+    const int c = it.y, s = it.z, e = it.w;
+    const int T = thr_f64(max(IT1[d].x, 1), overlap);
+    const int4 ri = RI[q];
+    const int4 rd = RD[q];
     SR0[p] = make_int4(s, e, T, q);
     SR1[p] = make_int4(ri.x, ri.y, ri.z, (rd.x << 6) | ((rd.y - 1) & 63));
     s_m[p] = m;
     s_fi[p] = (unsigned char)(m - rd.x);                             // index of this filling in its read's list
     RM0[m] = make_int4(c, s, e, T);
     s_chrom[p] = c; s_end[p] = e;
-    int cprev = p > 0 ? it_chrom[s_dp[p - 1]] : -1;
-    int cnext = p < D - 1 ? it_chrom[s_dp[p + 1]] : -1;
+    const int cprev = p > 0 ? IT0[s_dp[p - 1]].y : -1;
+    const int cnext = p < D - 1 ? IT0[s_dp[p + 1]].y : -1;
     if (cprev != c) chrom_lo[c] = p;
     if (cnext != c) chrom_hi[c] = p + 1;
 }
-// ub(p): last sorted position on the chromosome with start <= end_p  (IntervalMap upper bound)
+// ub(p): last sorted position on the chromosome with start <= end_p  (IntervalMap upper bound).
+// Galloping from p: the band is short, so ~2 log2(band) probes instead of log2(D).
 __global__ void k_ub(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
                      const int *__restrict__ chrom_hi, int *ubS, int2 *RM1, unsigned long long *band_pairs) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     long long mine = 0;
     if (p < D) {
-        int e = SR0[p].y;
-        int lo = p, hi = chrom_hi[s_chrom[p]];                    // invariant: start[lo] <= e, answer in [lo, hi)
+        const int e = SR0[p].y, lim = chrom_hi[s_chrom[p]];
+        int lo = p, step = 1;                                        // invariant: start[lo] <= e
+        while (lo + step < lim && SR0[lo + step].x <= e) { lo += step; step <<= 1; }
+        int hi = min(lo + step, lim);                                // start[hi] > e, or hi == lim
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (SR0[mid].x <= e) lo = mid; else hi = mid; }
         ubS[p] = lo;
         RM1[s_m[p]] = make_int2(p, lo);
@@ -296,10 +306,12 @@ __global__ void k_lb(int D, const int4 *__restrict__ SR0, const int *__restrict_
                      const int *__restrict__ chrom_lo, int *lbS) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
-    const int st = SR0[p].x;
-    int lo = chrom_lo[s_chrom[p]], hi = p;                            // pmaxS[p] >= end_p >= start_p: the answer is <= p
-    while (lo < hi) { int mid = (lo + hi) >> 1; if (pmaxS[mid] >= st) hi = mid; else lo = mid + 1; }
-    lbS[p] = lo;
+    const int st = SR0[p].x, clo = chrom_lo[s_chrom[p]];
+    int hi = p, step = 1;                                            // invariant: pmaxS[hi] >= st (pmaxS[p] >= end_p >= start_p)
+    while (hi - step >= clo && pmaxS[hi - step] >= st) { hi -= step; step <<= 1; }
+    int lo = max(hi - step, clo - 1);                                // pmaxS[lo] < st, or lo == clo - 1
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pmaxS[mid] >= st) hi = mid; else lo = mid; }
+    lbS[p] = hi;
 }
 struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 
@@ -896,7 +908,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         CK(cudaMemcpyAsync(d_cmask, pr.chrom_masked, pr.n_chrom, cudaMemcpyHostToDevice, st));
     }
     // ---- stage 1: keep_fillings
-    int *first, *last, *qmin, *qmax, *flagA, *posA, *frow;
+    int *first, *last, *qmin, *qmax, *flagA, *posA;
     DA(first, R); DA(last, R); DA(qmin, R); DA(qmax, R); DA(flagA, A); DA(posA, A);
     DA(P->q_of_rid, R);
     if (R > 0) {
@@ -915,42 +927,40 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int F = P->F = (int)ctx->h_pin[0];
     if (tb.order && tb.n_order != F) return fail(ctx, FSLRC_ERR_ARG, "order has the wrong length (must equal the number of fillings)");
-    DA(frow, F);
-    if (A > 0) KL(k_compact_rows, nblk(A, TB), TB, A, flagA, posA, frow);
+    int4 *FR0; int2 *FR1;
+    DA(FR0, F); DA(FR1, F);
+    if (A > 0) KL(k_fill_records, nblk(A, TB), TB, A, flagA, posA, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size, tb.n_alignments,
+                  pr.n_chrom, FR0, FR1, P->err);
     { int r = mark(ctx, 1); if (r) return r; }
-    // ---- stage 2: data order (cluster.py:114) + mask
-    int *dk = nullptr, *flagF, *posF;
+    // ---- stage 2: mask (cluster.py:89-106; dropping masked fillings before or after the sort is the same list) + data order
+    // (cluster.py:114): the caller's permutation, or a stable radix sort by start (ties keep bed order)
+    int *flagF, *posF;
     DA(flagF, F); DA(posF, F);
-    if (tb.order) {
-        dk = (int *)tb.order;
-        if (F > 0) KL(k_check_order, nblk(F, TB), TB, F, tb.order, P->err);
-    } else {
-        int *key, *key2, *v; DA(key, F); DA(key2, F); DA(v, F); DA(dk, F);
-        if (F > 0) {
-            KL(k_start_keys, nblk(F, TB), TB, F, frow, tb.rstart, tb.rend, key);
-            KL(k_iota, nblk(F, TB), TB, v, F);
-            int r = sort_pairs<int>(ctx, P, key, key2, v, dk, F, 0, 32); if (r) return r;     // stable: ties keep bed order
-        }
-    }
     if (F > 0) {
-        KL(k_mask_flags, nblk(F, TB), TB, F, dk, frow, tb.chrom, tb.rstart, tb.rend, pr.n_chrom, d_clen, d_cmask,
-                                                   pr.mask_subtelomere, (long long)pr.subtel, flagF, P->err);
+        KL(k_mask_flags, nblk(F, TB), TB, F, tb.order, FR0, pr.n_chrom, d_clen, d_cmask, pr.mask_subtelomere, (long long)pr.subtel, flagF, P->err);
         int r = xscan(ctx, P, flagF, posF, F); if (r) return r;
         KL(k_total, 1, 1, posF, flagF, F, P->cnt + 1);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int D = P->D = (int)ctx->h_pin[1];
-    int *it_rid, *it_chrom, *it_start, *it_end, *it_aln, *it_naln, *firstdp;
-    DA(it_rid, D); DA(it_chrom, D); DA(it_start, D); DA(it_end, D); DA(it_aln, D); DA(it_naln, D); DA(firstdp, R);
+    int *dfill; DA(dfill, D);
+    if (tb.order) {
+        if (F > 0) KL(k_compact_fillings, nblk(F, TB), TB, F, tb.order, flagF, posF, FR0, (int *)nullptr, dfill);
+    } else {
+        int *key, *key2, *v; DA(key, D); DA(key2, D); DA(v, D);
+        if (F > 0) KL(k_compact_fillings, nblk(F, TB), TB, F, (const int *)nullptr, flagF, posF, FR0, key, v);
+        int r = sort_pairs<int>(ctx, P, key, key2, v, dfill, D, 0, 32); if (r) return r;
+    }
+    int4 *IT0; int2 *IT1; int *firstdp;
+    DA(IT0, D); DA(IT1, D); DA(firstdp, R);
     if (R > 0) KL(k_fill<int>, nblk(R, TB), TB, firstdp, R, 0x7fffffff);
-    if (F > 0) KL(k_build_items, nblk(F, TB), TB, F, dk, frow, flagF, posF, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size,
-                                                          tb.n_alignments, it_rid, it_chrom, it_start, it_end, it_aln, it_naln, firstdp, P->err);
+    if (D > 0) KL(k_build_items, nblk(D, TB), TB, D, dfill, FR0, FR1, IT0, IT1, firstdp, P->err);
     { int r = mark(ctx, 2); if (r) return r; }
     // ---- stage 3: query rank + per-read lists
     int *flagD, *posD, *it_q;
     DA(flagD, D); DA(posD, D); DA(it_q, D);
     if (D > 0) {
-        KL(k_is_first, nblk(D, TB), TB, D, it_rid, firstdp, flagD);
+        KL(k_is_first, nblk(D, TB), TB, D, IT0, firstdp, flagD);
         int r = xscan(ctx, P, flagD, posD, D); if (r) return r;
         KL(k_total, 1, 1, posD, flagD, D, P->cnt + 2);
     }
@@ -962,21 +972,21 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(P->RD, Q); DA(P->RI, Q);
     if (R > 0) KL(k_rank_reads, nblk(R, TB), TB, R, firstdp, posD, P->q_of_rid, P->rid_of_q);
     if (D > 0) {
-        KL(k_item_q, nblk(D, TB), TB, D, it_rid, P->q_of_rid, it_q);
+        KL(k_item_q, nblk(D, TB), TB, D, IT0, P->q_of_rid, it_q);
         KL(k_iota, nblk(D, TB), TB, iotaD, D);
         int r = sort_pairs<int>(ctx, P, it_q, qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
         KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
-        KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, it_naln, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
-        KL(k_check_naln, nblk(D, TB), TB, D, it_q, it_naln, P->RI, P->err);
+        KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
+        KL(k_check_naln, nblk(D, TB), TB, D, it_q, IT1, P->RI, P->err);
     }
     { int r = mark(ctx, 3); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
     unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1, *s_dp;
     DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D); DA(s_dp, D);
     if (D > 0) {
-        KL(k_end_keys, nblk(D, TB), TB, D, it_end, ek);
+        KL(k_end_keys, nblk(D, TB), TB, D, IT0, ek);
         int r = sort_pairs<unsigned>(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
-        KL(k_chrom_start_keys, nblk(D, TB), TB, D, v1, it_chrom, it_start, ck);
+        KL(k_chrom_start_keys, nblk(D, TB), TB, D, v1, IT0, ck);
         r = sort_pairs<unsigned long long>(ctx, P, ck, ck2, v1, s_dp, D, 0, 32 + bits_for(pr.n_chrom)); if (r) return r;
     }
     { int r = mark(ctx, 4); if (r) return r; }
@@ -988,7 +998,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (D > 0) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
         int *s_m; DA(s_m, D); DA(P->s_fi, D); DA(P->lbS, D);
-        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, it_chrom, it_start, it_end, it_aln, P->RI, P->RD, pr.overlap, P->SR0, P->SR1,
+        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, P->RD, pr.overlap, P->SR0, P->SR1,
                                                P->RM0, s_m, P->s_fi, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
         KL(k_ub, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
         size_t b = 0;
