@@ -352,20 +352,16 @@ __device__ __forceinline__ bool difflen_ok(int qa, int Lqa, int nla, int qb, int
 }
 
 // ---------------------------------------------------------------- stage 6: tiled pair kernel (order-free relation)
-// A CTA owns a tile of PT_ROWS consecutive sorted intervals (one row per thread).  The union of the rows' closed bands is a
-// contiguous window of SR0 records, staged in shared memory with one TMA bulk copy (cp.async.bulk + mbarrier).
-//   phase 1 (lock step, shared memory + integer ALU only): every row walks its band PT_STEP positions per round and
-//            queues the interval pairs that reciprocally overlap (cluster.py:157) — the only way a read pair can match;
-//   phase 2 (dense): the queue is dealt out one pair per thread; a thread gathers both reads' filling lists and evaluates
+// A WARP owns a tile of 32 consecutive sorted intervals (one row per lane) and runs on its own (no CTA barrier anywhere).
+// The union of the rows' closed bands is a contiguous window of SR0 records, staged in shared memory with one TMA bulk
+// copy per tile (cp.async.bulk + the warp's mbarrier).
+//   phase 1 (shared memory + integer ALU only): every row walks its band PW_STEP positions per round and queues the
+//            interval pairs that reciprocally overlap (cluster.py:157) — the only way a read pair can match;
+//   phase 2 (dense): the queue is dealt out one pair per lane; a lane gathers both reads' filling lists and evaluates
 //            different_lengths_or_alignments, the greedy N-1 intersection and the per-N Jaccard cutoff for a -> b.
 // A read pair is counted/recorded once per direction, by the row that holds its lexicographically first matching filling
 // pair.  Capping: a row stops when its read reached edge_threshold passing candidates (it is replayed in query order
 // later), or when the row itself met edge_threshold distinct passing reads (then the read is saturating for certain).
-#define PT_ROWS 256
-#define PT_WIN 1024
-#define PT_STEP 4
-#define PT_QCAP (PT_ROWS * PT_STEP)
-
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -441,127 +437,139 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
     return 1 | ((ffa == fia && ffb == fbp) ? 2 : 0);
 }
 
-__global__ void __launch_bounds__(PT_ROWS) k_pair(Tab t, int nTiles, int shard, int nshard, int *degub, int2 *entries,
-                                                   unsigned long long *n_entries, unsigned long long cap_entries,
-                                                   unsigned long long *n_tests, int *err) {
-    __shared__ __align__(128) int4 win[PT_WIN];
-    __shared__ int4 rowS0[PT_ROWS];
-    __shared__ int4 rowS1[PT_ROWS];
-    __shared__ int2 queue[PT_QCAP];
-    __shared__ int2 outq[PT_QCAP];
-    __shared__ int rowcnt[PT_ROWS];
-    __shared__ unsigned char rowfi[PT_ROWS];
-    __shared__ int qn, outn, s_whi, s_wlo;
-    __shared__ unsigned long long s_base;
-    __shared__ __align__(8) unsigned long long mbar;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const unsigned bar = smem_u32(&mbar);
-    if (tid == 0) mbar_init(bar, 1);
-    __syncthreads();
+#define PW_WARPS 8
+#define PW_WIN 128
+#define PW_STEP 8
+#define PW_QCAP (32 * PW_STEP)
+#define PW_CHUNK 256            // output slots a warp reserves at a time (>= PW_QCAP)
+
+__global__ void __launch_bounds__(PW_WARPS * 32) k_pair(Tab t, int nTiles, int shard, int nshard, int *degub, int2 *entries,
+                                                         unsigned long long *n_slots, unsigned long long cap_entries,
+                                                         unsigned long long *n_tests, unsigned long long *n_real, int *err) {
+    __shared__ __align__(128) int4 win[PW_WARPS][PW_WIN];
+    __shared__ int2 queue[PW_WARPS][PW_QCAP];
+    __shared__ unsigned short outq[PW_WARPS][PW_QCAP];
+    __shared__ int rowcnt[PW_WARPS][32];
+    __shared__ __align__(8) unsigned long long mbar[PW_WARPS];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const unsigned bar = smem_u32(&mbar[w]);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
     unsigned parity = 0;
-    unsigned long long tests = 0;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        if (nshard > 1 && (tile % nshard) != shard) continue;
-        const int i0 = tile * PT_ROWS, i = i0 + tid;
+    unsigned long long tests = 0, real = 0, chunk_base = 0;
+    int chunk_used = PW_CHUNK;                                                     // nothing reserved yet
+    for (int tile = blockIdx.x * PW_WARPS + w; tile < nTiles; tile += gridDim.x * PW_WARPS) {
+        if (nshard > 1 && ((tile >> 3) % nshard) != shard) continue;                 // 256-row groups, round robin over ranks
+        const int i = tile * 32 + lane;
         const bool valid = i < t.D;
         int4 s0 = make_int4(0, 0, 0, -1), s1 = make_int4(0, 0, 0, 0);
-        int lb = 1, ub = 0;
-        if (valid) { s0 = __ldg(&t.SR0[i]); s1 = __ldg(&t.SR1[i]); lb = __ldg(&t.lbS[i]); ub = __ldg(&t.ubS[i]); rowfi[tid] = __ldg(&t.s_fi[i]); }
-        rowS0[tid] = s0; rowS1[tid] = s1; rowcnt[tid] = 0;
-        if (tid == 0) { qn = 0; outn = 0; s_whi = 0; s_wlo = lb; }                 // lb is monotone: row 0 has the smallest
-        __syncthreads();
-        const int wmax = __reduce_max_sync(0xffffffffu, ub);
-        if (lane == 0) atomicMax(&s_whi, wmax);
-        __syncthreads();
-        const int wlo = s_wlo;
-        const int wn = min(s_whi - wlo + 1, PT_WIN);
-        if (tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // earlier generic reads of `win` are done
+        int lb = 0x7fffffff, ub = 0, fia = 0;
+        if (valid) { s0 = __ldg(&t.SR0[i]); s1 = __ldg(&t.SR1[i]); lb = __ldg(&t.lbS[i]); ub = __ldg(&t.ubS[i]); fia = __ldg(&t.s_fi[i]); }
+        const int wlo = __shfl_sync(FULL, lb, 0);                                  // lb is monotone: row 0 has the smallest
+        const int wn = min(__reduce_max_sync(FULL, ub) - wlo + 1, PW_WIN);
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // earlier generic reads of the window are done
             mbar_expect_tx(bar, (unsigned)wn * 16u);
-            bulk_g2s(smem_u32(win), t.SR0 + wlo, (unsigned)wn * 16u, bar);
+            bulk_g2s(smem_u32(win[w]), t.SR0 + wlo, (unsigned)wn * 16u, bar);
         }
+        rowcnt[w][lane] = 0;
         mbar_wait(bar, parity);
         parity ^= 1u;
         const int a = s0.w;
         bool dead = !valid;
         int off = 0, round = 0;
         for (;;) {
-            // ---- phase 1: cheap interval-pair test from shared memory
+            // ---- phase 1: cheap interval-pair test out of the staged window
+            int qn = 0;
 #pragma unroll
-            for (int sidx = 0; sidx < PT_STEP; sidx++) {
+            for (int sidx = 0; sidx < PW_STEP; sidx++) {
                 const int p = ub - off - sidx;
                 bool push = false;
                 if (!dead && p >= lb && p != i) {
                     const int wi = p - wlo;
-                    const int4 c0 = (wi < wn) ? win[wi] : __ldg(&t.SR0[p]);
+                    const int4 c0 = (wi < wn) ? win[w][wi] : __ldg(&t.SR0[p]);
                     const int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
-                    push = (c0.w != a) && (max(ov, 0) >= max(s0.z, c0.z));
+                    push = (c0.w != a) && (max(ov, 0) >= max(s0.z, c0.z));           // cluster.py:157 for this interval pair
                 }
-                const unsigned pm = __ballot_sync(0xffffffffu, push);
-                if (pm) {
-                    int at = 0;
-                    if (lane == 0) at = atomicAdd(&qn, __popc(pm));
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (push) queue[at + __popc(pm & ((1u << lane) - 1u))] = make_int2(tid, p);
-                }
+                const unsigned pm = __ballot_sync(FULL, push);
+                if (push) queue[w][qn + __popc(pm & ltmask)] = make_int2(lane, p);
+                qn += __popc(pm);
             }
-            off += PT_STEP;
+            off += PW_STEP;
             round++;
-            __syncthreads();
-            // ---- phase 2: dense evaluation of the queued pairs
-            const int nq = qn;
-            for (int base = 0; base < nq; base += PT_ROWS) {
-                const int e = base + tid;
-                if (e < nq) {
-                    const int2 rp = queue[e];
-                    const int4 r0 = rowS0[rp.x], r1 = rowS1[rp.x];
-                    const int wi = rp.y - wlo;
-                    const int4 c0 = (wi < wn) ? win[wi] : __ldg(&t.SR0[rp.y]);
+            __syncwarp();
+            // ---- phase 2: dense evaluation, one queued pair per lane
+            int on = 0;
+            for (int base = 0; base < qn; base += 32) {
+                const int e = base + lane;
+                const bool act = e < qn;
+                const int2 rp = act ? queue[w][e] : make_int2(lane, i);
+                const int ra = __shfl_sync(FULL, a, rp.x);
+                const int r1x = __shfl_sync(FULL, s1.x, rp.x), r1y = __shfl_sync(FULL, s1.y, rp.x);
+                const int r1z = __shfl_sync(FULL, s1.z, rp.x), r1w = __shfl_sync(FULL, s1.w, rp.x);
+                const int rfia = __shfl_sync(FULL, fia, rp.x);
+                bool rec = false;
+                if (act) {
                     const int4 c1 = __ldg(&t.SR1[rp.y]);
-                    if (difflen_ok(r1.x, r1.y, r1.z, c1.x, c1.y, c1.z)) {
-                        const int offa = r1.w >> 6, La = (r1.w & 63) + 1, offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
-                        const int fia = rowfi[rp.x], fbp = __ldg(&t.s_fi[rp.y]);
+                    if (difflen_ok(r1x, r1y, r1z, c1.x, c1.y, c1.z)) {
+                        const int offa = r1w >> 6, La = (r1w & 63) + 1, offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
+                        const int fbp = __ldg(&t.s_fi[rp.y]);
                         int n, fl;
-                        if (La <= 4 && Lb <= 4) fl = eval_small<4>(t.RM0 + offa, La, t.RM0 + offb, Lb, fia, fbp, &n);
-                        else fl = eval_general(t.RM0 + offa, La, t.RM0 + offb, Lb, fia, fbp, &n);
+                        if (La <= 4 && Lb <= 4) fl = eval_small<4>(t.RM0 + offa, La, t.RM0 + offb, Lb, rfia, fbp, &n);
+                        else fl = eval_general(t.RM0 + offa, La, t.RM0 + offb, Lb, rfia, fbp, &n);
                         if (fl & 1) {
                             tests++;
                             if (n > 0 && (La + Lb - n) <= c_umax[n]) {                  // cluster.py:165-170,218-219
-                                atomicAdd(&rowcnt[rp.x], 1);
-                                if (fl & 2) {                                          // canonical filling pair of (a, b)
-                                    const int old = atomicAdd(&degub[r0.w], 1);
-                                    if (old < t.Tedge) outq[atomicAdd(&outn, 1)] = make_int2(r0.w, c0.w);
-                                }
+                                atomicAdd(&rowcnt[w][rp.x], 1);
+                                if (fl & 2) rec = atomicAdd(&degub[ra], 1) < t.Tedge;   // canonical filling pair of (a, b)
                             }
                         }
                     }
                 }
+                const unsigned om = __ballot_sync(FULL, rec);
+                if (rec) outq[w][on + __popc(om & ltmask)] = (unsigned short)e;
+                on += __popc(om);
             }
-            __syncthreads();
-            // ---- flush recorded pairs: one global reservation per CTA and round
-            const int on = outn;
+            __syncwarp();
+            // ---- record: the warp fills output chunks it reserved with one global atomic per PW_CHUNK pairs
             if (on) {
-                if (tid == 0) s_base = atomicAdd(n_entries, (unsigned long long)on);
-                __syncthreads();
-                for (int k = tid; k < on; k += PT_ROWS) {
-                    const unsigned long long idx = s_base + k;
-                    if (idx < cap_entries) entries[idx] = outq[k]; else atomicOr(err, EF_OVERFLOW);
+                if (chunk_used + on > PW_CHUNK) {
+                    for (int k = chunk_used + lane; k < PW_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
+                    if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)PW_CHUNK);
+                    chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                    chunk_used = 0;
+                    if (chunk_base + PW_CHUNK > cap_entries) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; on = 0; }
                 }
+                for (int kb = 0; kb < on; kb += 32) {
+                    const int k = kb + lane;
+                    const bool act = k < on;
+                    const int2 rp = act ? queue[w][outq[w][k]] : make_int2(lane, i);
+                    const int ra = __shfl_sync(FULL, a, rp.x);
+                    if (act) {
+                        const int wi = rp.y - wlo;
+                        const int rb = (wi < wn) ? win[w][wi].w : __ldg(&t.SR0[rp.y]).w;
+                        entries[chunk_base + chunk_used + k] = make_int2(ra, rb);
+                    }
+                }
+                chunk_used += on;
+                real += (lane == 0) ? on : 0;
             }
             if (!dead) {
                 if (ub - off < lb) dead = true;
-                else if (rowcnt[tid] >= t.Tedge) { atomicMax(&degub[a], t.Tedge); dead = true; }
-                else if ((round & 3) == 0 && *(volatile int *)&degub[a] >= t.Tedge) dead = true;
+                else if (rowcnt[w][lane] >= t.Tedge) { atomicMax(&degub[a], t.Tedge); dead = true; }
+                else if ((round & 3) == 1 && *(volatile int *)&degub[a] >= t.Tedge) dead = true;
             }
-            __syncthreads();
-            if (tid == 0) { qn = 0; outn = 0; }
-            if (!__syncthreads_or(!dead)) break;
+            if (!__any_sync(FULL, !dead)) break;
+            __syncwarp();
         }
+        __syncwarp();
     }
-    typedef cub::BlockReduce<unsigned long long, PT_ROWS> BR;
-    __shared__ typename BR::TempStorage tmp;
-    const unsigned long long ts = BR(tmp).Sum(tests);
-    if (tid == 0 && ts) atomicAdd(n_tests, ts);
+    if (chunk_used < PW_CHUNK)
+        for (int k = chunk_used + lane; k < PW_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
+    for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
+    if (lane == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
 }
 
 // ---------------------------------------------------------------- stage 7: saturating set
@@ -741,7 +749,7 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
     if (k < n) {
         const int2 ab = entries[k];
         const int a = ab.x, b = ab.y;
-        if (!isP[a]) {
+        if (a >= 0 && !isP[a]) {
             if (b > a) e = true;
             else if (isP[b]) {
                 const int4 rda = t.RD[a], rdb = t.RD[b];
@@ -825,7 +833,7 @@ struct Pipe {
     // inputs (device)
     fslrc_table tb;
     fslrc_params pr;
-    int A, R, F, D, Q, nP, Tedge;
+    int A, R, F, D, Q, nP, Tedge, pair_blocks;
     int *err;
     int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entries,6 nP,7 pedges,8 edges,9 ncl,10 forest, 11 clustered
     int *q_of_rid, *rid_of_q;
@@ -889,6 +897,11 @@ static int err_code(fslrc_ctx *ctx) {
     if (e & EF_TOOMANY) return fail(ctx, FSLRC_ERR_TOO_MANY_FILLINGS, "a read has more than 64 fillings");
     if (e & EF_NALN) return fail(ctx, FSLRC_ERR_NALN_NOT_CONSTANT, "n_alignments is not constant over the rows of a read");
     return fail(ctx, FSLRC_ERR_OVERFLOW, "internal edge buffer overflow");
+}
+static int n_sms(fslrc_ctx *ctx) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
+    return n;
 }
 static int bits_for(int64_t n) { int b = 1; while ((1ll << b) < n && b < 32) b++; return b; }
 
@@ -1017,27 +1030,22 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     // relation entries: every read records fewer than edge_threshold passing candidates, and never more than exist
     const unsigned long long band = (unsigned long long)ctx->h_pin[3];
     unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * (unsigned long long)P->Tedge : 0ull;
-    P->cap_entries = std::min<unsigned long long>(capT, 2ull * band) + 64;
+    P->pair_blocks = std::max(1, std::min(nblk(nblk(D, 32), PW_WARPS), n_sms(ctx) * 4));
+    P->cap_entries = std::min<unsigned long long>(capT, 2ull * band) + (unsigned long long)PW_CHUNK * PW_WARPS * P->pair_blocks + 64;
     DA(P->entries, P->cap_entries);
     DA(P->degub, Q); DA(P->isP, Q); DA(P->stop, D); DA(P->final_, Q); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
     if (Q > 0) CK(cudaMemsetAsync(P->degub, 0, sizeof(int) * Q, st));
     return mark(ctx, 5);
 }
 
-static int n_sms(fslrc_ctx *ctx) {
-    int n = 148;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
-    return n;
-}
 
 // ---- stage 6: pair kernel on one shard
 static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
     if (P->D > 0) {
-        const int nTiles = nblk(P->D, PT_ROWS);
-        int blocks = std::min(nTiles, n_sms(ctx) * 5);
-        KL(k_pair, blocks, PT_ROWS, P->tab, nTiles, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
-           P->cap_entries, (unsigned long long *)(P->cnt + 4), P->err);
+        const int nTiles = nblk(P->D, 32);
+        KL(k_pair, P->pair_blocks, PW_WARPS * 32, P->tab, nTiles, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
+           P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
     }
     return mark(ctx, 6);
 }
@@ -1122,7 +1130,7 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     const int64_t *h = ctx->h_pin;
     memset(s, 0, sizeof(*s));
     s->n_fillings = P->F; s->n_intervals = P->D; s->n_query_reads = P->Q;
-    s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[5]; s->saturating_reads = P->nP;
+    s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[13]; s->saturating_reads = P->nP;
     s->edges = h[8] + h[7]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
     s->no_clusters = h[9] == 0;
     for (int i = 0; i < FSLRC_N_STAGES; i++) {
