@@ -620,20 +620,28 @@ __global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *_
     }
     flag[k] = f;
 }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+#define RP_CHUNK 128            // edge slots a warp reserves at a time (>= 32)
 __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
                                                                const int *__restrict__ rstart, const int *__restrict__ isP,
-                                                               int *stop, int *final_, unsigned *ticket, int2 *pedges,
-                                                               unsigned long long *n_pedges, unsigned long long cap_pedges,
+                                                               const int *__restrict__ posQ, int *stop, int *final_, unsigned *ticket,
+                                                               int2 *pedges, unsigned long long *n_slots, unsigned long long cap_pedges,
                                                                unsigned long long *n_tests, int *err) {
     __shared__ int4 A0[REPLAY_WARPS][LMAX];
     __shared__ int2 A1[REPLAY_WARPS][LMAX];
     __shared__ int Astop[REPLAY_WARPS][LMAX];
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned long long tests = 0;
+    unsigned long long tests = 0, chunk_base = 0;
+    int chunk_used = RP_CHUNK;
     for (;;) {
         unsigned run = 0;
         if (lane == 0) run = atomicAdd(ticket, 1u);
-        run = __shfl_sync(0xffffffffu, run, 0);
+        run = __shfl_sync(FULL, run, 0);
         if (run >= (unsigned)nRuns) break;
         const unsigned tk0 = (unsigned)__ldg(&rstart[run]);
         const unsigned tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
@@ -664,33 +672,87 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
                         && difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
                         const int offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
                         const int bP = (b < a) ? __ldg(&isP[b]) : 0;
-                        bool met = false;                                              // pair already seen earlier in this very query?
-                        for (int g = 0; g < Lb && !met; g++) {
-                            const int4 bg = __ldg(&t.RM0[offb + g]);
-                            const int pg = __ldg(&t.RM1[offb + g]).x;
-                            for (int f2 = 0; f2 < fi; f2++) {
-                                const int4 af = A0[w][f2];
-                                if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
-                            }
-                            if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
-                        }
-                        if (!met && (b > a || bP)) {                                   // b < a and never breaking: it saw the pair
-                            int ffa, ffb;
-                            const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
-                            tests++;
-                            if (n > 0) {
-                                reach = true;
-                                if (b < a) {                                           // b queried first: did it get here?
-                                    while (*(volatile int *)&final_[b] == 0) __nanosleep(40);
-                                    __threadfence();
-                                    if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
+                        if (b > a || bP) {                                             // b < a and never breaking: it saw the pair
+                            if (La <= 4 && Lb <= 4) {
+                                // ---- lists in registers, everything unrolled
+                                int4 bg[4]; int2 bq[4];
+#pragma unroll
+                                for (int g = 0; g < 4; g++) {
+                                    bg[g] = g < Lb ? __ldg(&t.RM0[offb + g]) : make_int4(-2, 0, 0, 0x7fffffff);
+                                    bq[g] = g < Lb ? __ldg(&t.RM1[offb + g]) : make_int2(-1, -1);
                                 }
-                                edge = reach && (La + Lb - n) <= c_umax[n];
+                                bool met = false;                                      // pair already seen earlier in this very query?
+                                unsigned m[4];
+#pragma unroll
+                                for (int fa = 0; fa < 4; fa++) {
+                                    const int4 af = fa < La ? A0[w][fa] : make_int4(-1, 0, 0, 0x7fffffff);
+                                    const int aub = A1[w][fa].y, ast = Astop[w][fa];
+                                    unsigned r = 0;
+#pragma unroll
+                                    for (int g = 0; g < 4; g++) {
+                                        r |= (match4(af, bg[g]) ? 1u : 0u) << g;
+                                        met |= (fa < fi) && af.x == bg[g].x && ast <= bq[g].x && bq[g].x <= aub && bg[g].z >= af.y;
+                                    }
+                                    m[fa] = r;
+                                }
+#pragma unroll
+                                for (int g = 0; g < 4; g++) met |= bg[g].x == f.x && bq[g].x > p && bq[g].x <= top && bg[g].z >= f.y;
+                                if (!met) {
+                                    unsigned used = 0; int n = 0;
+#pragma unroll
+                                    for (int fa = 0; fa < 4; fa++) { const unsigned av = m[fa] & ~used; if (av) { used |= av & (0u - av); n++; } }
+                                    tests++;
+                                    if (n > 0) {
+                                        reach = true;
+                                        if (b < a) {                                   // b queried first: did it get here?
+                                            if ((unsigned)__ldg(&posQ[b]) < tk0)       // b belongs to another warp's run: wait for it
+                                                while (ld_acquire(&final_[b]) == 0) __nanosleep(40);
+                                            bool vis = false;
+#pragma unroll
+                                            for (int g = 0; g < 4; g++) {
+                                                const int sf = g < Lb ? __ldcg(&stop[offb + g]) : 0x7fffffff;
+#pragma unroll
+                                                for (int fa = 0; fa < 4; fa++) {
+                                                    const int4 af = fa < La ? A0[w][fa] : make_int4(-1, 0, 0, 0);
+                                                    const int pa = A1[w][fa].x;
+                                                    vis |= af.x == bg[g].x && sf <= pa && pa <= bq[g].y && af.z >= bg[g].y;
+                                                }
+                                            }
+                                            if (vis) reach = false;
+                                        }
+                                        edge = reach && (La + Lb - n) <= c_umax[n];
+                                    }
+                                }
+                            } else {
+                                bool met = false;
+                                for (int g = 0; g < Lb && !met; g++) {
+                                    const int4 bg = __ldg(&t.RM0[offb + g]);
+                                    const int pg = __ldg(&t.RM1[offb + g]).x;
+                                    for (int f2 = 0; f2 < fi; f2++) {
+                                        const int4 af = A0[w][f2];
+                                        if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
+                                    }
+                                    if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
+                                }
+                                if (!met) {
+                                    int ffa, ffb;
+                                    const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
+                                    tests++;
+                                    if (n > 0) {
+                                        reach = true;
+                                        if (b < a) {
+                                            if ((unsigned)__ldg(&posQ[b]) < tk0)
+                                                while (ld_acquire(&final_[b]) == 0) __nanosleep(40);
+                                            if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
+                                        }
+                                        edge = reach && (La + Lb - n) <= c_umax[n];
+                                    }
+                                }
                             }
                         }
                     }
                 }
-                const unsigned M = __ballot_sync(0xffffffffu, reach), E = __ballot_sync(0xffffffffu, edge);
+                const unsigned M = __ballot_sync(FULL, reach), E = __ballot_sync(FULL, edge);
                 int brk = -1;
                 for (unsigned mm = M; mm; mm &= mm - 1) {                              // cluster.py:219-224 in scan order
                     const int l = __ffs(mm) - 1;
@@ -698,13 +760,16 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
                 }
                 const unsigned Euse = brk >= 0 ? (E & ((2u << brk) - 1u)) : E;
                 if (Euse) {
-                    unsigned long long at = 0;
-                    if (lane == 0) at = atomicAdd(n_pedges, (unsigned long long)__popc(Euse));
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if ((Euse >> lane) & 1u) {
-                        unsigned long long k = at + __popc(Euse & ((1u << lane) - 1u));
-                        if (k < cap_pedges) pedges[k] = make_int2(a, b); else atomicOr(err, EF_OVERFLOW);
+                    const int ne = __popc(Euse);
+                    if (chunk_used + ne > RP_CHUNK) {                                  // reserve a fresh chunk, pad the old one
+                        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
+                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                        chunk_used = 0;
+                        if (chunk_base + RP_CHUNK > cap_pedges) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
                     }
+                    if ((Euse >> lane) & 1u) pedges[chunk_base + chunk_used + __popc(Euse & ((1u << lane) - 1u))] = make_int2(a, b);
+                    chunk_used += ne;
                 }
                 edges += __popc(Euse);
                 if (brk >= 0) { stopf = base - brk; break; }
@@ -712,13 +777,17 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
             if (lane == 0) Astop[w][fi] = stopf;
             __syncwarp();
         }
-        for (int k = lane; k < La; k += 32) stop[offa + k] = Astop[w][k];
+        for (int k = lane; k < La; k += 32) __stcg(&stop[offa + k], Astop[w][k]);
+        __syncwarp();                                                              // later reads of this run see the stops (L2)
+        }
+        // publish the whole run: one fence, then the final flags (reads of other runs wait on these)
         __threadfence();
         __syncwarp();
-        if (lane == 0) { *(volatile int *)&final_[a] = 1; }
-        }
+        for (unsigned tk = tk0 + lane; tk < tk1; tk += 32) *(volatile int *)&final_[__ldg(&plist[tk])] = 1;
     }
-    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(0xffffffffu, tests, o);
+    if (chunk_used < RP_CHUNK)
+        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
+    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(FULL, tests, o);
     if (lane == 0 && tests) atomicAdd(n_tests, tests);
 }
 
@@ -770,12 +839,19 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
     const unsigned m = __ballot_sync(0xffffffffu, e);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_edges, (unsigned long long)__popc(m));
 }
-__global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing) {
+__global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing, unsigned long long *n_edges) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const int2 ab = edges[k];
-    ing[ab.x] = 1; ing[ab.y] = 1;
-    uf_union(parent, ab.x, ab.y);
+    bool e = false;
+    if (k < n) {
+        const int2 ab = edges[k];
+        if (ab.x >= 0) {                                                            // skip chunk padding
+            e = true;
+            ing[ab.x] = 1; ing[ab.y] = 1;
+            uf_union(parent, ab.x, ab.y);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0 && m && n_edges) atomicAdd(n_edges, (unsigned long long)__popc(m));
 }
 __global__ void k_flatten(int Q, int *parent, const int *__restrict__ ing, int *isroot, int *csize) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1073,7 +1149,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
     unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
     unsigned long long alt = 2ull * (unsigned long long)ctx->h_pin[3] + 64;
-    P->cap_pedges = std::min(capp, alt);
+    P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * REPLAY_WARPS * (n_sms(ctx) * 16 + 1);
     DA(P->pedges, P->cap_pedges);
     if (nP > 0) {
         int *rflag, *rpos, *rstart;
@@ -1085,7 +1161,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, REPLAY_WARPS), n_sms(ctx) * 16);
-        KL(k_replay, blocks, REPLAY_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->final_, P->ticket, P->pedges,
+        KL(k_replay, blocks, REPLAY_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, posQ, P->stop, P->final_, P->ticket, P->pedges,
            (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err);
     }
     { int r = mark(ctx, 8); if (r) return r; }
@@ -1099,7 +1175,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
                                                                            (unsigned long long *)(P->cnt + 8));
     // replayed edges are identical on every rank; rank `shard` contributes them once
-    if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing);
+    if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));
     (void)nshard;
     return mark(ctx, 9);
 }
@@ -1131,7 +1207,7 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     memset(s, 0, sizeof(*s));
     s->n_fillings = P->F; s->n_intervals = P->D; s->n_query_reads = P->Q;
     s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[13]; s->saturating_reads = P->nP;
-    s->edges = h[8] + h[7]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
+    s->edges = h[8]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
     s->no_clusters = h[9] == 0;
     for (int i = 0; i < FSLRC_N_STAGES; i++) {
         float ms = 0.f;
@@ -1307,7 +1383,7 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, 
         KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (n_edges > 0) KL(k_union_edges, nblk(n_edges, TB), TB, (unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing);
+    if (n_edges > 0) KL(k_union_edges, nblk(n_edges, TB), TB, (unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing, (unsigned long long *)nullptr);
     int r = pipe_number(ctx, P, out_cluster, out_n_reads);
     if (!r) r = mark(ctx, 11);
     if (!r) { r = read_counts(ctx, P); if (!r) r = err_code(ctx); }
