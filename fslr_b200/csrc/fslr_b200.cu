@@ -27,6 +27,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include <algorithm>
 #include "fslr_b200.h"
@@ -224,22 +225,22 @@ __global__ void k_read_bounds(int D, const int *__restrict__ qs /*sorted q*/, co
     if (m == 0 || qs[m - 1] != q) off[q] = m;
     if (m == D - 1 || qs[m + 1] != q) len_end[q] = m + 1;
 }
-// per read: qlen2, n_alignments and their ratio thresholds (cluster.py:26-29,178-183)
+// per read: RI[q] = {qlen2, Lq, n_alignments | Ln << 16, off << 6 | (L - 1)}: the ratio thresholds of
+// cluster.py:26-29,178-183 and where the read's fillings live in read-major order
 __global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *__restrict__ off, const int *__restrict__ len_end,
                             const int *__restrict__ rm_dp, const int2 *__restrict__ IT1, const int *__restrict__ qmin,
-                            const int *__restrict__ qmax, double qlen_c, double naln_c, int4 *RD, int4 *RI, int *err) {
+                            const int *__restrict__ qmax, double qlen_c, double naln_c, int4 *RI, int *err) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= Q) return;
     int r = rid_of_q[q], o = off[q], L = len_end[q] - o;
-    if (L > LMAX) atomicOr(err, EF_TOOMANY);
+    if (L > LMAX) { atomicOr(err, EF_TOOMANY); L = LMAX; }
     long long ql = (long long)qmax[r] - (long long)qmin[r];
     int na = IT1[rm_dp[o]].y;
     if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
     if (ql > 0x7fffffffLL) { atomicOr(err, EF_RANGE); ql = 1; }
     int Ln = thr_f64(na, naln_c);
     if (Ln > 65535) Ln = 65535;
-    RD[q] = make_int4(o, L, r, 0);
-    RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), 0);
+    RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), (int)(((unsigned)o << 6) | (unsigned)((L - 1) & 63)));
 }
 __global__ void k_check_naln(int D, const int *__restrict__ it_q, const int2 *__restrict__ IT1, const int4 *__restrict__ RI, int *err) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -255,12 +256,14 @@ __global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const i
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = ((unsigned long long)(unsigned)it.y << 32) | (unsigned)it.z; }
 }
-// SR0[p] = {start, end, T, q}; SR1[p] = {qlen2, Lq, naln | Ln<<16, off<<6 | (L-1)} (off, L: the read's run in RM);
-// RM0[m] = {chrom, start, end, T}; RM1[m] = {pos, ub}
+// SR0[p] = {start, end, T, q | fi << 26} (fi = index of the filling in its read's list); SR1[p] = the read's RI record;
+// RM[2m] = {chrom, start, end, T}, RM[2m+1] = {pos, ub (closed band, replay), lbT, ubT (tight band, pair kernel)}: one
+// 32-byte sector per filling in read-major order, written once by k_bands
+#define QMASK 0x3ffffff
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
                           const int4 *__restrict__ IT0, const int2 *__restrict__ IT1, const int4 *__restrict__ RI,
-                          const int4 *__restrict__ RD, double overlap, int4 *SR0, int4 *SR1, int4 *RM0, int *s_m,
-                          unsigned char *s_fi, int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
+                          double overlap, int4 *SR0, int4 *SR1, int *s_m,
+                          int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
     const int d = s_dp[p], m = rmidx[d], q = it_q[d];
@@ -268,72 +271,82 @@ __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__rest
     const int c = it.y, s = it.z, e = it.w;
     const int T = thr_f64(max(IT1[d].x, 1), overlap);
     const int4 ri = RI[q];
-    const int4 rd = RD[q];
-    SR0[p] = make_int4(s, e, T, q);
-    SR1[p] = make_int4(ri.x, ri.y, ri.z, (rd.x << 6) | ((rd.y - 1) & 63));
+    const int fi = m - (int)((unsigned)ri.w >> 6);                   // index of this filling in its read's list
+    SR0[p] = make_int4(s, e, T, (int)((unsigned)q | ((unsigned)fi << 26)));
+    SR1[p] = ri;
     s_m[p] = m;
-    s_fi[p] = (unsigned char)(m - rd.x);                             // index of this filling in its read's list
-    RM0[m] = make_int4(c, s, e, T);
     s_chrom[p] = c; s_end[p] = e;
     const int cprev = p > 0 ? IT0[s_dp[p - 1]].y : -1;
     const int cnext = p < D - 1 ? IT0[s_dp[p + 1]].y : -1;
     if (cprev != c) chrom_lo[c] = p;
     if (cnext != c) chrom_hi[c] = p + 1;
 }
-// ub(p): last sorted position on the chromosome with start <= end_p  (IntervalMap upper bound).
-// Galloping from p: the band is short, so ~2 log2(band) probes instead of log2(D).
-__global__ void k_ub(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
-                     const int *__restrict__ chrom_hi, int *ubS, int2 *RM1, unsigned long long *band_pairs) {
+// Bands of sorted position p, and the read-major record of its filling.
+// ub(p): last sorted position on the chromosome with start <= end_p (IntervalMap upper bound), by galloping
+// from p (the band is short: ~2 log2(band) probes instead of log2(D)).  Tight band [lbT, ubT]: the positions whose
+// interval can reciprocally overlap p by >= T_p (cluster.py:157): above p, start <= end_p - T_p (inside [p, ub]); below p,
+// nothing before the first position whose prefix-max end reaches start_p + T_p.
+__global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
+                        const int *__restrict__ pmaxS, const int *__restrict__ chrom_lo, const int *__restrict__ chrom_hi,
+                        int4 *RM, unsigned long long *band_pairs, unsigned long long *tight_pairs) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    long long mine = 0;
+    long long mine = 0, mineT = 0;
     if (p < D) {
-        const int e = SR0[p].y, lim = chrom_hi[s_chrom[p]];
+        const int4 me = SR0[p];
+        const int c = s_chrom[p];
+        const int e = me.y, lim = chrom_hi[c], clo = chrom_lo[c];
         int lo = p, step = 1;                                        // invariant: start[lo] <= e
         while (lo + step < lim && SR0[lo + step].x <= e) { lo += step; step <<= 1; }
         int hi = min(lo + step, lim);                                // start[hi] > e, or hi == lim
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (SR0[mid].x <= e) lo = mid; else hi = mid; }
-        ubS[p] = lo;
-        RM1[s_m[p]] = make_int2(p, lo);
+        const long long et = (long long)e - (long long)me.z;        // T = 0 (overlap <= 0): the closed band
+        int tl = p, th = lo + 1;                                     // start[tl] <= et or tl == p; start[th] > et or th == ub + 1
+        while (th - tl > 1) { int mid = (tl + th) >> 1; if ((long long)SR0[mid].x <= et) tl = mid; else th = mid; }
+        const long long st = (long long)me.x + (long long)me.z;
+        int lb = p;
+        if (p > clo && (long long)pmaxS[p - 1] >= st) {
+            lb = p - 1;
+            int stp = 1;                                             // invariant: pmaxS[lb] >= st
+            while (lb - stp >= clo && (long long)pmaxS[lb - stp] >= st) { lb -= stp; stp <<= 1; }
+            int l2 = max(lb - stp, clo - 1);                         // pmaxS[l2] < st, or l2 == clo - 1
+            while (lb - l2 > 1) { int mid = (l2 + lb) >> 1; if ((long long)pmaxS[mid] >= st) lb = mid; else l2 = mid; }
+        }
+        const int m = s_m[p];
+        RM[2 * m] = make_int4(c, me.x, me.y, me.z);
+        RM[2 * m + 1] = make_int4(p, lo, lb, tl);
         mine = lo - p;
+        mineT = tl - lb;
     }
     typedef cub::BlockReduce<long long, 256> BR;
     __shared__ typename BR::TempStorage tmp;
     long long s = BR(tmp).Sum(mine);
-    if (threadIdx.x == 0 && s) atomicAdd(band_pairs, (unsigned long long)s);
-}
-// lb(p): first sorted position on the chromosome whose prefix-max end reaches start_p (nothing below can overlap p)
-__global__ void k_lb(int D, const int4 *__restrict__ SR0, const int *__restrict__ pmaxS, const int *__restrict__ s_chrom,
-                     const int *__restrict__ chrom_lo, int *lbS) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= D) return;
-    const int st = SR0[p].x, clo = chrom_lo[s_chrom[p]];
-    int hi = p, step = 1;                                            // invariant: pmaxS[hi] >= st (pmaxS[p] >= end_p >= start_p)
-    while (hi - step >= clo && pmaxS[hi - step] >= st) { hi -= step; step <<= 1; }
-    int lo = max(hi - step, clo - 1);                                // pmaxS[lo] < st, or lo == clo - 1
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pmaxS[mid] >= st) hi = mid; else lo = mid; }
-    lbS[p] = hi;
+    __syncthreads();
+    long long s2 = BR(tmp).Sum(mineT);
+    if (threadIdx.x == 0) { if (s) atomicAdd(band_pairs, (unsigned long long)s); if (s2) atomicAdd(tight_pairs, (unsigned long long)s2); }
 }
 struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 
 // ---------------------------------------------------------------- pair-level pieces
 struct Tab {                 // kernel-side view of the tables
-    const int4 *SR0, *SR1, *RM0, *RD, *RI;
-    const int2 *RM1;
-    const int *ubS, *lbS, *pmaxS, *s_chrom, *chrom_lo;
-    const unsigned char *s_fi;
+    const int4 *SR0, *SR1, *RM, *RI;
+    const int *pmaxS, *chrom_lo;
     int D, Q, Tedge;
 };
+// read-major filling records (see k_bands)
+__device__ __forceinline__ int4 rm0(const Tab &t, int m) { return __ldg(&t.RM[2 * m]); }                            // {chrom, start, end, T}
+__device__ __forceinline__ int2 rm1(const Tab &t, int m) { return __ldg((const int2 *)&t.RM[2 * m + 1]); }          // {pos, ub}
+__device__ __forceinline__ int2 rm2(const Tab &t, int m) { return __ldg((const int2 *)&t.RM[2 * m + 1] + 1); }      // {lbT, ubT}
 __constant__ int c_umax[LMAX + 1];
 
-// a (query, its fillings A[0..La) in shared memory) against b's fillings in RM0[offb..offb+Lb):
-// greedy first-fit count of cluster.py:152-161 plus the lexicographically first matching filling pair
-__device__ __forceinline__ int greedy_ab(const int4 *A, int La, const int4 *__restrict__ B, int Lb, int *first_fa, int *first_fb) {
+// a (query) against b, both as read-major records (RM + 2 * off, stride 2): greedy first-fit count of cluster.py:152-161
+// plus the lexicographically first matching filling pair
+__device__ __forceinline__ int greedy_ab(const int4 *__restrict__ A, int La, const int4 *__restrict__ B, int Lb, int *first_fa, int *first_fb) {
     unsigned long long used = 0;
     int n = 0, ffa = -1, ffb = -1;
     for (int fa = 0; fa < La; fa++) {
-        int4 a = A[fa];
+        int4 a = __ldg(&A[2 * fa]);
         for (int fb = 0; fb < Lb; fb++) {
-            int4 b = __ldg(&B[fb]);
+            int4 b = __ldg(&B[2 * fb]);
             int ov = min(a.z, b.z) - max(a.y, b.y);
             bool m = (a.x == b.x) && (max(ov, 0) >= max(a.w, b.w));
             if (m) {
@@ -351,85 +364,72 @@ __device__ __forceinline__ bool difflen_ok(int qa, int Lqa, int nla, int qb, int
     return q_ok || n_ok;                                           // cluster.py:178-183 (skip only if both fail)
 }
 
-// ---------------------------------------------------------------- stage 6: tiled pair kernel (order-free relation)
-// A WARP owns a tile of 32 consecutive sorted intervals (one row per lane) and runs on its own (no CTA barrier anywhere).
-// The union of the rows' closed bands is a contiguous window of SR0 records, staged in shared memory with one TMA bulk
-// copy per tile (cp.async.bulk + the warp's mbarrier).
-//   phase 1 (shared memory + integer ALU only): every row walks its band PW_STEP positions per round and queues the
-//            interval pairs that reciprocally overlap (cluster.py:157) — the only way a read pair can match;
-//   phase 2 (dense): the queue is dealt out one pair per lane; a lane gathers both reads' filling lists and evaluates
-//            different_lengths_or_alignments, the greedy N-1 intersection and the per-N Jaccard cutoff for a -> b.
-// A read pair is counted/recorded once per direction, by the row that holds its lexicographically first matching filling
-// pair.  Capping: a row stops when its read reached edge_threshold passing candidates (it is replayed in query order
-// later), or when the row itself met edge_threshold distinct passing reads (then the read is saturating for certain).
+// ---------------------------------------------------------------- stage 6: read-major pair kernel (order-free relation)
+// A GROUP of 8 lanes owns one query read a (4 reads per warp, consecutive query ranks = usually one PCR family, so the
+// groups of a warp run in step).  For every filling of a the group walks the filling's TIGHT band [lbT, ubT] of sorted
+// interval records (the only positions whose interval can reciprocally overlap it by >= --overlap, cluster.py:157) with
+// coalesced int4 loads, 8 positions per step.  A hit names a partner read b; the lane gathers b's filling list and
+// evaluates a -> b once: different_lengths_or_alignments (cluster.py:178-183), the greedy N-1 intersection
+// (cluster.py:152-161) and the per-N Jaccard cutoff (cluster.py:165-170,218-219).  "Once" = at the lexicographically
+// first matching filling pair of (a, b); a small per-group hash of partners already settled filters the later hits
+// before any gather (a filter only: a miss costs a re-evaluation that the canonical-pair rule then discards).
+// Passing pairs are appended to the relation list through warp-aggregated chunk reservations; a read stops as soon as
+// edge_threshold partners passed (it is saturating: replayed in query order later, its entries are ignored).
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
 __device__ __forceinline__ bool match4(const int4 a, const int4 b) {
     return (a.x == b.x) && (max(min(a.z, b.z) - max(a.y, b.y), 0) >= max(a.w, b.w));
 }
-// a -> b for reads with <= N fillings, lists in registers.  Returns bit0: (fia, fbp) is the first filling of b matching
-// row fia; bit1: (fia, fbp) is the lexicographically first matching pair.  *n_out = greedy intersection (cluster.py:152-161).
-template <int N>
-__device__ __forceinline__ int eval_small(const int4 *__restrict__ A, int La, const int4 *__restrict__ B, int Lb, int fia, int fbp, int *n_out) {
-    int4 a[N], b[N];
+// cluster.py:157 for fillings {chrom, start, end, T}: with --overlap > 0 every T >= 1, so max(ov, 0) >= T <=> ov >= T;
+// ALLMATCH (--overlap <= 0, all T = 0): any two fillings on one chromosome match
+template <bool ALLMATCH>
+__device__ __forceinline__ bool matchT(const int4 a, const int4 b) {
+    if (ALLMATCH) return a.x == b.x;
+    return (a.x == b.x) && ((min(a.z, b.z) - max(a.y, b.y)) >= max(a.w, b.w));
+}
+// a -> b for reads with <= 4 fillings, lists in registers.  Returns bit0: evaluated, bit1: (fia, fbp) is the canonical
+// (lexicographically first) band hit of the pair.  *n_out = greedy intersection (cluster.py:152-161).
+template <bool ALLMATCH>
+__device__ __forceinline__ int eval_small(const int4 *A, int La, const int4 *__restrict__ B, int Lb, int fia, int fbp, int *n_out) {
+    int4 a[4], b[4];
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-        a[k] = k < La ? __ldg(&A[k]) : make_int4(-1, 0, 0, 0x7fffffff);
-        b[k] = k < Lb ? __ldg(&B[k]) : make_int4(-2, 0, 0, 0x7fffffff);
+    for (int k = 0; k < 4; k++) {
+        a[k] = k < La ? A[k] : make_int4(-1, 0, 0, 0x7fffffff);
+        b[k] = k < Lb ? __ldg(&B[2 * k]) : make_int4(-2, 0, 0, 0x7fffffff);   // B: read-major records, stride 2
     }
-    unsigned m[N];
-    unsigned mrow = 0;
+    unsigned m[4], h[4];
 #pragma unroll
-    for (int fa = 0; fa < N; fa++) {
-        unsigned r = 0;
+    for (int fa = 0; fa < 4; fa++) {
+        unsigned r = 0, hr = 0;
 #pragma unroll
-        for (int fb = 0; fb < N; fb++) r |= (match4(a[fa], b[fb]) ? 1u : 0u) << fb;
-        m[fa] = r;
-        if (fa == fia) mrow = r;
+        for (int fb = 0; fb < 4; fb++) {
+            r |= (matchT<ALLMATCH>(a[fa], b[fb]) ? 1u : 0u) << fb;
+            if (ALLMATCH) hr |= ((a[fa].x == b[fb].x && min(a[fa].z, b[fb].z) - max(a[fa].y, b[fb].y) >= 0) ? 1u : 0u) << fb;
+        }
+        m[fa] = r; h[fa] = ALLMATCH ? hr : r;                        // h: matching pairs that are band hits (closed overlap)
     }
-    *n_out = 0;
-    if (mrow & ((1u << fbp) - 1u)) return 0;                       // an earlier filling of b already matches this row
     unsigned used = 0;
     int n = 0, ffa = -1, ffb = -1;
 #pragma unroll
-    for (int fa = 0; fa < N; fa++) {
-        if (m[fa] && ffa < 0) { ffa = fa; ffb = __ffs(m[fa]) - 1; }
+    for (int fa = 0; fa < 4; fa++) {
+        if (h[fa] && ffa < 0) { ffa = fa; ffb = __ffs(h[fa]) - 1; }
         const unsigned avail = m[fa] & ~used;
         if (avail) { used |= avail & (0u - avail); n++; }
     }
     *n_out = n;
     return 1 | ((ffa == fia && ffb == fbp) ? 2 : 0);
 }
+template <bool ALLMATCH>
 __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, const int4 *__restrict__ B, int Lb, int fia, int fbp, int *n_out) {
-    const int4 af = __ldg(&A[fia]);
-    *n_out = 0;
-    for (int fb = 0; fb < fbp; fb++) if (match4(af, __ldg(&B[fb]))) return 0;
     unsigned long long used = 0;
     int n = 0, ffa = -1, ffb = -1;
     for (int fa = 0; fa < La; fa++) {
-        const int4 a = __ldg(&A[fa]);
+        const int4 a = __ldg(&A[2 * fa]);                               // A, B: read-major records, stride 2
+        bool taken = false;
         for (int fb = 0; fb < Lb; fb++) {
-            if (match4(a, __ldg(&B[fb]))) {
-                if (ffa < 0) { ffa = fa; ffb = fb; }
-                if (!((used >> fb) & 1ull)) { used |= 1ull << fb; n++; break; }
+            const int4 b = __ldg(&B[2 * fb]);
+            if (matchT<ALLMATCH>(a, b)) {
+                if (ffa < 0 && (!ALLMATCH || min(a.z, b.z) - max(a.y, b.y) >= 0)) { ffa = fa; ffb = fb; }
+                if (!taken && !((used >> fb) & 1ull)) { used |= 1ull << fb; n++; taken = true; if (ffa >= 0) break; }
             }
         }
     }
@@ -437,260 +437,440 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
     return 1 | ((ffa == fia && ffb == fbp) ? 2 : 0);
 }
 
-#define PW_WARPS 8
-#define PW_WIN 128
-#define PW_STEP 8
-#define PW_QCAP (32 * PW_STEP)
-#define PW_CHUNK 256            // output slots a warp reserves at a time (>= PW_QCAP)
+#define PK_WARPS 8
+#define PK_GROUPS (PK_WARPS * 4)
+#define PK_HASH 64              // settled-partner filter slots per group
+#define PK_CHUNK 256            // relation-entry slots a warp reserves at a time (>= 32)
 
-__global__ void __launch_bounds__(PW_WARPS * 32) k_pair(Tab t, int nTiles, int shard, int nshard, int *degub, int2 *entries,
+template <bool ALLMATCH>
+__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int nshard, int *isP, int2 *entries,
                                                          unsigned long long *n_slots, unsigned long long cap_entries,
                                                          unsigned long long *n_tests, unsigned long long *n_real, int *err) {
-    __shared__ __align__(128) int4 win[PW_WARPS][PW_WIN];
-    __shared__ int2 queue[PW_WARPS][PW_QCAP];
-    __shared__ unsigned short outq[PW_WARPS][PW_QCAP];
-    __shared__ int rowcnt[PW_WARPS][32];
-    __shared__ __align__(8) unsigned long long mbar[PW_WARPS];
+    __shared__ int4 sA[PK_GROUPS][4];
+    __shared__ int2 sBand[PK_GROUPS][4];
+    __shared__ int2 sHash[PK_GROUPS][PK_HASH];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned ltmask = (1u << lane) - 1u;
-    const unsigned bar = smem_u32(&mbar[w]);
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    unsigned parity = 0;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, g = lane >> 3, grp = w * 4 + g;
+    const unsigned ltmask = (1u << lane) - 1u, gmask = 0xffu << (g * 8);
     unsigned long long tests = 0, real = 0, chunk_base = 0;
-    int chunk_used = PW_CHUNK;                                                     // nothing reserved yet
-    for (int tile = blockIdx.x * PW_WARPS + w; tile < nTiles; tile += gridDim.x * PW_WARPS) {
-        if (nshard > 1 && ((tile >> 3) % nshard) != shard) continue;                 // 256-row groups, round robin over ranks
-        const int i = tile * 32 + lane;
-        const bool valid = i < t.D;
-        int4 s0 = make_int4(0, 0, 0, -1), s1 = make_int4(0, 0, 0, 0);
-        int lb = 0x7fffffff, ub = 0, fia = 0;
-        if (valid) { s0 = __ldg(&t.SR0[i]); s1 = __ldg(&t.SR1[i]); lb = __ldg(&t.lbS[i]); ub = __ldg(&t.ubS[i]); fia = __ldg(&t.s_fi[i]); }
-        const int wlo = __shfl_sync(FULL, lb, 0);                                  // lb is monotone: row 0 has the smallest
-        const int wn = min(__reduce_max_sync(FULL, ub) - wlo + 1, PW_WIN);
-        if (lane == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // earlier generic reads of the window are done
-            mbar_expect_tx(bar, (unsigned)wn * 16u);
-            bulk_g2s(smem_u32(win[w]), t.SR0 + wlo, (unsigned)wn * 16u, bar);
-        }
-        rowcnt[w][lane] = 0;
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-        const int a = s0.w;
-        bool dead = !valid;
-        int off = 0, round = 0;
-        for (;;) {
-            // ---- phase 1: cheap interval-pair test out of the staged window
-            int qn = 0;
-#pragma unroll
-            for (int sidx = 0; sidx < PW_STEP; sidx++) {
-                const int p = ub - off - sidx;
-                bool push = false;
-                if (!dead && p >= lb && p != i) {
-                    const int wi = p - wlo;
-                    const int4 c0 = (wi < wn) ? win[w][wi] : __ldg(&t.SR0[p]);
-                    const int ov = min(s0.y, c0.y) - max(s0.x, c0.x);
-                    push = (c0.w != a) && (max(ov, 0) >= max(s0.z, c0.z));           // cluster.py:157 for this interval pair
-                }
-                const unsigned pm = __ballot_sync(FULL, push);
-                if (push) queue[w][qn + __popc(pm & ltmask)] = make_int2(lane, p);
-                qn += __popc(pm);
+    int chunk_used = PK_CHUNK;                                                     // nothing reserved yet
+    for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
+    const int stride = gridDim.x * PK_GROUPS;
+    for (int q0 = blockIdx.x * PK_GROUPS; q0 < t.Q; q0 += stride) {                // block-uniform trip count
+        const int q = q0 + grp;
+        const bool live = q < t.Q && (nshard <= 1 || ((q >> 8) % nshard) == shard); // 256-read groups, round robin over ranks
+        int4 ri = make_int4(0, 0, 0, 0);
+        if (live) ri = __ldg(&t.RI[q]);
+        const int off = (int)((unsigned)ri.w >> 6), La = live ? (ri.w & 63) + 1 : 0;
+        __syncwarp();
+        if (gl < min(La, 4)) { sA[grp][gl] = rm0(t, off + gl); sBand[grp][gl] = rm2(t, off + gl); }
+        __syncwarp();
+        int cnt = 0;
+        const int maxLa = __reduce_max_sync(FULL, La);
+        for (int fi = 0; fi < maxLa; fi++) {
+            const bool fact = fi < La && cnt < t.Tedge;
+            int4 f = make_int4(0, 0, 0, 0);
+            int2 band = make_int2(1, 0);
+            if (fact) {
+                if (La <= 4) { f = sA[grp][fi]; band = sBand[grp][fi]; }
+                else { f = rm0(t, off + fi); band = rm2(t, off + fi); }
             }
-            off += PW_STEP;
-            round++;
-            __syncwarp();
-            // ---- phase 2: dense evaluation, one queued pair per lane
-            int on = 0;
-            for (int base = 0; base < qn; base += 32) {
-                const int e = base + lane;
-                const bool act = e < qn;
-                const int2 rp = act ? queue[w][e] : make_int2(lane, i);
-                const int ra = __shfl_sync(FULL, a, rp.x);
-                const int r1x = __shfl_sync(FULL, s1.x, rp.x), r1y = __shfl_sync(FULL, s1.y, rp.x);
-                const int r1z = __shfl_sync(FULL, s1.z, rp.x), r1w = __shfl_sync(FULL, s1.w, rp.x);
-                const int rfia = __shfl_sync(FULL, fia, rp.x);
-                bool rec = false;
-                if (act) {
-                    const int4 c1 = __ldg(&t.SR1[rp.y]);
-                    if (difflen_ok(r1x, r1y, r1z, c1.x, c1.y, c1.z)) {
-                        const int offa = r1w >> 6, La = (r1w & 63) + 1, offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
-                        const int fbp = __ldg(&t.s_fi[rp.y]);
-                        int n, fl;
-                        if (La <= 4 && Lb <= 4) fl = eval_small<4>(t.RM0 + offa, La, t.RM0 + offb, Lb, rfia, fbp, &n);
-                        else fl = eval_general(t.RM0 + offa, La, t.RM0 + offb, Lb, rfia, fbp, &n);
-                        if (fl & 1) {
-                            tests++;
-                            if (n > 0 && (La + Lb - n) <= c_umax[n]) {                  // cluster.py:165-170,218-219
-                                atomicAdd(&rowcnt[w][rp.x], 1);
-                                if (fl & 2) rec = atomicAdd(&degub[ra], 1) < t.Tedge;   // canonical filling pair of (a, b)
+            for (int ch = 0;; ch++) {
+                const int p = band.x + ch * 8 + gl;
+                const bool v = fact && cnt < t.Tedge && p <= band.y;
+                if (!__any_sync(FULL, v)) break;                                    // every group of the warp is through its band
+                int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
+                if (v) c0 = __ldg(&t.SR0[p]);
+                const int b = c0.w & QMASK;
+                bool pass = false;
+                if (v && b != q && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z)) {   // cluster.py:157 for this interval pair
+                    int2 *hs = &sHash[grp][b & (PK_HASH - 1)];
+                    const int2 hv = *hs;
+                    if (hv.x != b || hv.y != q) {                                   // not settled earlier in this read's pass
+                        const int4 c1 = __ldg(&t.SR1[p]);
+                        bool settled = true;
+                        if (difflen_ok(ri.x, ri.y, ri.z, c1.x, c1.y, c1.z)) {
+                            const int offb = (int)((unsigned)c1.w >> 6), Lb = (c1.w & 63) + 1;
+                            const int fbp = (int)((unsigned)c0.w >> 26);
+                            int n, fl;
+                            if (La <= 4 && Lb <= 4) fl = eval_small<ALLMATCH>(sA[grp], La, t.RM + 2 * offb, Lb, fi, fbp, &n);
+                            else fl = eval_general<ALLMATCH>(t.RM + 2 * off, La, t.RM + 2 * offb, Lb, fi, fbp, &n);
+                            settled = (fl & 2) != 0;
+                            if (settled) {
+                                tests++;
+                                pass = n > 0 && (La + Lb - n) <= c_umax[n];         // cluster.py:165-170,218-219
                             }
                         }
+                        if (settled) *hs = make_int2(b, q);
                     }
                 }
-                const unsigned om = __ballot_sync(FULL, rec);
-                if (rec) outq[w][on + __popc(om & ltmask)] = (unsigned short)e;
-                on += __popc(om);
-            }
-            __syncwarp();
-            // ---- record: the warp fills output chunks it reserved with one global atomic per PW_CHUNK pairs
-            if (on) {
-                if (chunk_used + on > PW_CHUNK) {
-                    for (int k = chunk_used + lane; k < PW_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
-                    if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)PW_CHUNK);
-                    chunk_base = __shfl_sync(FULL, chunk_base, 0);
-                    chunk_used = 0;
-                    if (chunk_base + PW_CHUNK > cap_entries) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; on = 0; }
-                }
-                for (int kb = 0; kb < on; kb += 32) {
-                    const int k = kb + lane;
-                    const bool act = k < on;
-                    const int2 rp = act ? queue[w][outq[w][k]] : make_int2(lane, i);
-                    const int ra = __shfl_sync(FULL, a, rp.x);
-                    if (act) {
-                        const int wi = rp.y - wlo;
-                        const int rb = (wi < wn) ? win[w][wi].w : __ldg(&t.SR0[rp.y]).w;
-                        entries[chunk_base + chunk_used + k] = make_int2(ra, rb);
+                const unsigned pm = __ballot_sync(FULL, pass);
+                if (pm) {                                                           // warp-aggregated append to the relation list
+                    const int n = __popc(pm);
+                    if (chunk_used + n > PK_CHUNK) {
+                        for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
+                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)PK_CHUNK);
+                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                        chunk_used = 0;
+                        if (chunk_base + PK_CHUNK > cap_entries) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
                     }
+                    if (pass) entries[chunk_base + chunk_used + __popc(pm & ltmask)] = make_int2(q, b);
+                    chunk_used += n;
+                    real += (lane == 0) ? n : 0;
+                    cnt += __popc(pm & gmask);
                 }
-                chunk_used += on;
-                real += (lane == 0) ? on : 0;
+                __syncwarp();                                                       // filter updates visible to the next step
             }
-            if (!dead) {
-                if (ub - off < lb) dead = true;
-                else if (rowcnt[w][lane] >= t.Tedge) { atomicMax(&degub[a], t.Tedge); dead = true; }
-                else if ((round & 3) == 1 && *(volatile int *)&degub[a] >= t.Tedge) dead = true;
-            }
-            if (!__any_sync(FULL, !dead)) break;
-            __syncwarp();
         }
-        __syncwarp();
+        if (live && gl == 0) isP[q] = cnt >= t.Tedge;
     }
-    if (chunk_used < PW_CHUNK)
-        for (int k = chunk_used + lane; k < PW_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
+    if (chunk_used < PK_CHUNK)
+        for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
     for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
     if (lane == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
 }
 
 // ---------------------------------------------------------------- stage 7: saturating set
-__global__ void k_satur_flags(int Q, const int *__restrict__ degub, int Tedge, int *isP) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < Q) isP[q] = degub[q] >= Tedge;
-}
 __global__ void k_compact_flagged(int n, const int *__restrict__ flag, const int *__restrict__ pos, int *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) out[pos[i]] = i;
 }
 
-// did read b's own query scan reach one of a's intervals?  (stops of b must be final)
-__device__ __forceinline__ bool visited_ba(const int4 *__restrict__ RM0, const int2 *__restrict__ RM1, const int *stop, int offb, int Lb,
-                                           const int4 *A0, const int2 *A1, int La) {
-    for (int f = 0; f < Lb; f++) {
-        const int4 bf = __ldg(&RM0[offb + f]);
-        const int ubf = __ldg(&RM1[offb + f]).y;
-        const int sf = __ldcg(&stop[offb + f]);
-        for (int g = 0; g < La; g++) {
-            const int4 ag = A0[g];
-            const int pg = A1[g].x;
-            if (ag.x == bf.x && sf <= pg && pg <= ubf && ag.z >= bf.y) return true;
-        }
-    }
-    return false;
-}
-
 // ---------------------------------------------------------------- stage 8: replay of saturating reads in query order
-// Persistent ticket kernel: plist holds the saturating reads in ascending query rank, cut into RUNS of reads that depend on
-// each other (consecutive ranks of one PCR family, k_run_flags); a warp takes the next run and walks it back to back with
-// the band hot in L1 (several warps would only wait on each other), re-running each read's query exactly as
-// cluster.py:197-224 would (descending sorted positions per filling, seen pairs skipped, edges counted, break), and
-// publishes the read's stops.  Whether an earlier-ranked saturating read b "saw" the pair first is a function of b's stops,
-// so a lane waits (spin on final[b]) only for reads with smaller tickets, which are held by running warps: no deadlock.
-#define REPLAY_WARPS 4
+// plist holds the saturating reads in ascending query rank, cut into RUNS of reads that depend on each other (consecutive
+// ranks of one PCR family, k_run_flags).  A GROUP of 8 lanes takes the next run (ticket) and walks its reads back to back,
+// re-running each read's query exactly as cluster.py:197-224 would: per filling, the closed band is walked downwards from
+// ub, 8 sorted positions per step; pairs already seen are skipped, edges counted, and the scan breaks at edge_threshold.
+// All a later query can observe of this is one integer per filling — the position where the scan stopped — published in
+// stop[] (-1 until known).  Whether an earlier-ranked saturating read b "saw" the pair first is a function of b's stops.
+//
+// The kernel is a non-blocking state machine: the 4 groups of a warp advance one step per loop iteration in lock step;
+// a step whose outcome depends on a stop that is not published yet commits only the candidates before it (scan order)
+// and is retried on the next iteration — nobody spins, so groups can never block one another, and a group only ever
+// depends on reads of smaller tickets (held by resident groups) or on earlier reads of its own run.
+#define RG_WARPS 4
+#define RG_GROUPS (RG_WARPS * 4)
 #define RUN_CAP 64
+#define RP_CHUNK 64             // edge slots a group reserves at a time (>= 8)
+enum { RF_TESTED = 1, RF_REACH = 2, RF_EDGE = 4, RF_UNRES = 8 };
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(int *p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // run starts: ticket k opens a new run unless its read's first filling reciprocally overlaps the previous saturating
-// read's first filling (same PCR family: they depend on each other), or the run would exceed RUN_CAP reads
-__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RD, const int4 *__restrict__ RM0, int *flag) {
+// read's first filling (same PCR family: they depend on each other), or the run would exceed RUN_CAP reads.
+// Also marks the stops of every saturating read as "not known yet".
+__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RI, const int4 *__restrict__ RM, int *flag, int *stop) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nP) return;
+    const int w = RI[plist[k]].w;
+    const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1;
+    for (int j = 0; j < L; j++) stop[off + j] = -1;
     int f = 1;
     if (k > 0 && (k & (RUN_CAP - 1)) != 0) {
-        const int4 x = RM0[RD[plist[k - 1]].x], y = RM0[RD[plist[k]].x];
+        const int4 x = RM[2 * ((unsigned)RI[plist[k - 1]].w >> 6)], y = RM[2 * off];
         const int ov = min(x.z, y.z) - max(x.y, y.y);
         if (x.x == y.x && max(ov, 0) >= max(x.w, y.w)) f = 0;
     }
     flag[k] = f;
 }
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// one candidate b of read a's filling scan when either read has more than 4 fillings (lists stay in global memory)
+__device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
+                                                const int4 f, int top, int p, int b, int offb, int Lb) {
+    for (int g = 0; g < Lb; g++) {                                                 // pair already seen earlier in this very query?
+        const int4 bg = rm0(t, offb + g);
+        const int pg = rm1(t, offb + g).x;
+        for (int f2 = 0; f2 < fi; f2++) {
+            const int4 af = rm0(t, offa + f2);
+            if (af.x == bg.x && ownStop[f2] <= pg && pg <= rm1(t, offa + f2).y && bg.z >= af.y) return 0;
+        }
+        if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) return 0;
+    }
+    int ffa, ffb;
+    const int n = greedy_ab(t.RM + 2 * offa, La, t.RM + 2 * offb, Lb, &ffa, &ffb);
+    if (n == 0) return RF_TESTED;
+    if (b < a) {                                                                   // b queried first: did its scans get here?
+        bool vis = false, unres = false;
+        for (int g = 0; g < Lb; g++) {
+            const int4 bf = rm0(t, offb + g);
+            const int ubf = rm1(t, offb + g).y;
+            const int sf = ld_relaxed(&stop[offb + g]);
+            for (int fa = 0; fa < La; fa++) {
+                const int4 ag = rm0(t, offa + fa);
+                const int pa = rm1(t, offa + fa).x;
+                if (ag.x == bf.x && pa <= ubf && ag.z >= bf.y) { if (sf < 0) unres = true; else if (sf <= pa) vis = true; }
+            }
+        }
+        if (vis) return RF_TESTED;
+        if (unres) return RF_TESTED | RF_UNRES;
+    }
+    return RF_TESTED | RF_REACH | ((La + Lb - n) <= c_umax[n] ? RF_EDGE : 0);
 }
-#define RP_CHUNK 128            // edge slots a warp reserves at a time (>= 32)
-__global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
-                                                               const int *__restrict__ rstart, const int *__restrict__ isP,
-                                                               const int *__restrict__ posQ, int *stop, int *final_, unsigned *ticket,
-                                                               int2 *pedges, unsigned long long *n_slots, unsigned long long cap_pedges,
-                                                               unsigned long long *n_tests, int *err) {
-    __shared__ int4 A0[REPLAY_WARPS][LMAX];
-    __shared__ int2 A1[REPLAY_WARPS][LMAX];
-    __shared__ int Astop[REPLAY_WARPS][LMAX];
+// Two ways to re-run one read's query:
+//   LIST mode (the normal case): the only candidates that can ever matter to a's query are intervals of reads b that share
+//     a reciprocally overlapping filling pair with a (n_i > 0, cluster.py:216) — everything else is skipped by the reference
+//     before it touches `edges` or the break.  Those partners all sit in a's TIGHT bands, so the group first builds a's
+//     partner list (<= RP_K reads, each evaluated once: greedy intersection + Jaccard cutoff), then replays every filling's
+//     scan over the partners only: a partner is first met at its highest interval inside the filling's closed band, the
+//     partners are ranked by that position (descending = scan order) and the break position follows from prefix counts —
+//     one step per filling, however long the closed band is.
+//   WALK mode (reads with too many partners, e.g. a 500k-read hotspot, or --overlap <= 0): the closed band is walked
+//     downwards 8 sorted positions per step and every candidate is evaluated; such reads break after a few steps.
+#define RP_K 64                 // partners a read may have in LIST mode
+static_assert(RP_K <= RP_CHUNK && RP_K <= 64, "list-mode edges of one filling must fit one chunk and one 64-bit mask");
+#define RP_TIGHT_MAX 512        // tight-band positions above which the partner list is not even attempted
+template <bool ALLMATCH>
+__global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+                                                           const int *__restrict__ rstart, const int *__restrict__ isP, int *stop,
+                                                           unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
+                                                           unsigned long long cap_pedges, unsigned long long *n_tests, int *err,
+                                                           unsigned long long *dbg) {
+    __shared__ int4 sA0[RG_GROUPS][4];
+    __shared__ int2 sA1[RG_GROUPS][4];
+    __shared__ int sStop[RG_GROUPS][LMAX];
+    __shared__ int sPb[RG_GROUPS][RP_K];                                           // partner read (query rank)
+    __shared__ int sPw[RG_GROUPS][RP_K];                                           // its off << 6 | L - 1
+    __shared__ int sKey[RG_GROUPS][RP_K];                                          // first-visit position in the current filling's scan
+    __shared__ unsigned char sPf[RG_GROUPS][RP_K];                                 // 1 visited by a, 2 edge if reached, 4 b saw a, 8 b did not
+    __shared__ int2 sHash[RG_GROUPS][PK_HASH];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, gsh = lane & 24, grp = w * 4 + (lane >> 3);
+    const unsigned gmask = 0xffu << gsh;
+    // group state (identical in the 8 lanes of a group)
+    int phase = 0;                      // 0 next read, 1 walk: next filling, 2 walk: scanning, 3 finished, 4 list: build, 5 list: filling
+    unsigned tk = 0, tk1 = 0;
+    int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0;
+    int nPart = 0, bfi = 0, bp = 1, bend = 0;
+    int4 ria = make_int4(0, 0, 0, 0), f = make_int4(0, 0, 0, 0);
     unsigned long long tests = 0, chunk_base = 0;
+    unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
+    int d_fsteps = 0, d_fstall = 0;
     int chunk_used = RP_CHUNK;
+    for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
     for (;;) {
-        unsigned run = 0;
-        if (lane == 0) run = atomicAdd(ticket, 1u);
-        run = __shfl_sync(FULL, run, 0);
-        if (run >= (unsigned)nRuns) break;
-        const unsigned tk0 = (unsigned)__ldg(&rstart[run]);
-        const unsigned tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
-        for (unsigned tk = tk0; tk < tk1; tk++) {
-        const int a = __ldg(&plist[tk]);
-        const int4 rda = __ldg(&t.RD[a]);
-        const int4 ria = __ldg(&t.RI[a]);                                         // {qlen2, Lq, naln|Ln}
-        const int offa = rda.x, La = rda.y;
         __syncwarp();
-        for (int k = lane; k < La; k += 32) { A0[w][k] = __ldg(&t.RM0[offa + k]); A1[w][k] = __ldg(&t.RM1[offa + k]); }
+        d_iter += lane == 0;
+        if (phase == 0) {
+            if (tk == tk1) {                                                       // run finished: take the next ticket
+                unsigned run = 0;
+                if (gl == 0) run = atomicAdd(ticket, 1u);
+                run = __shfl_sync(gmask, run, gsh);
+                if (run >= (unsigned)nRuns) phase = 3;
+                else {
+                    tk = (unsigned)__ldg(&rstart[run]);
+                    tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
+                }
+            }
+            if (phase == 0) {
+                a = __ldg(&plist[tk]);
+                ria = __ldg(&t.RI[a]);                                             // {qlen2, Lq, naln | Ln << 16, off << 6 | L - 1}
+                offa = (int)((unsigned)ria.w >> 6); La = (ria.w & 63) + 1;
+                fi = 0; edges = 0;
+                if (La <= 4 && gl < La) { sA0[grp][gl] = rm0(t, offa + gl); sA1[grp][gl] = rm1(t, offa + gl); }
+                phase = 1;
+                if (!ALLMATCH) {                                                   // few tight-band positions: try the partner list
+                    int ts = 0;
+                    for (int k = gl; k < La; k += 8) { const int2 bd = rm2(t, offa + k); ts += bd.y - bd.x + 1; }
+                    ts += __shfl_xor_sync(gmask, ts, 1); ts += __shfl_xor_sync(gmask, ts, 2); ts += __shfl_xor_sync(gmask, ts, 4);
+                    if (ts <= RP_TIGHT_MAX) { phase = 4; nPart = 0; bfi = -1; bp = 1; bend = 0; }
+                }
+            }
+        }
+        if (__all_sync(FULL, phase == 3)) break;
         __syncwarp();
-        int edges = 0;
-        for (int fi = 0; fi < La; fi++) {
-            const int4 f = A0[w][fi];
-            const int top = A1[w][fi].y;
-            const int lo = t.chrom_lo[f.x];
-            int stopf = lo;
-            for (int base = top; base >= lo; base -= 32) {
-                if (t.pmaxS[base] < f.y) break;
-                const int p = base - lane;
-                bool reach = false, edge = false;
-                int b = -1;
+        bool stalled = false;
+        // ------------------------------------------------------------ LIST mode: build the partner list
+        if (phase == 4) {
+            while (bp > bend && bfi < La) {                                        // next filling's tight band
+                bfi++;
+                if (bfi < La) { const int2 bd = rm2(t, offa + bfi); bp = bd.x; bend = bd.y; f = rm0(t, offa + bfi); }
+            }
+            if (bfi >= La) { phase = 5; fi = 0; }
+            else {
+                const int p = bp + gl;
+                bool part = false, eflag = false;
+                int b = -1, wb = 0;
+                if (p <= bend) {
+                    const int4 c0 = __ldg(&t.SR0[p]);
+                    b = c0.w & QMASK;
+                    if (b != a && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z)) {   // cluster.py:157 for this interval pair
+                        int2 *hs = &sHash[grp][b & (PK_HASH - 1)];
+                        const int2 hv = *hs;
+                        if (hv.x != b || hv.y != a) {
+                            const int4 c1 = __ldg(&t.SR1[p]);
+                            bool settled = true;                                    // b < a and never breaking: it saw the pair
+                            if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z) && (b > a || __ldg(&isP[b]))) {
+                                wb = c1.w;
+                                const int offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
+                                const int fbp = (int)((unsigned)c0.w >> 26);
+                                int n, fl;
+                                if (La <= 4 && Lb <= 4) fl = eval_small<false>(sA0[grp], La, t.RM + 2 * offb, Lb, bfi, fbp, &n);
+                                else fl = eval_general<false>(t.RM + 2 * offa, La, t.RM + 2 * offb, Lb, bfi, fbp, &n);
+                                settled = (fl & 2) != 0;
+                                if (settled) { part = true; eflag = (La + Lb - n) <= c_umax[n]; }   // n >= 1: this very pair matches
+                            }
+                            if (settled) *hs = make_int2(b, a);
+                        }
+                    }
+                }
+                const unsigned pm = (__ballot_sync(gmask, part) >> gsh) & 0xffu;
+                if (gl == 0) tests += __popc(pm);
+                if (nPart + __popc(pm) > RP_K) { phase = 1; fi = 0; }              // too many partners: walk the bands instead
+                else {
+                    if (part) {
+                        const int j = nPart + __popc(pm & ((1u << gl) - 1u));
+                        sPb[grp][j] = b; sPw[grp][j] = wb; sPf[grp][j] = eflag ? 2 : 0;
+                    }
+                    nPart += __popc(pm);
+                    bp += 8;
+                }
+                if (gl == 0) d_steps++;
+            }
+        }
+        // ------------------------------------------------------------ LIST mode: one filling's scan over the partners
+        else if (phase == 5) {
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; }
+            else { f = rm0(t, offa + fi); top = rm1(t, offa + fi).y; }
+            lo = __ldg(&t.chrom_lo[f.x]);
+            // pass 1: where does the scan first meet each partner; did an earlier-ranked partner's own query see a first?
+            for (int j = gl; j < nPart; j += 8) {
+                int fl = sPf[grp][j], key = -1;
+                if (!(fl & 1)) {
+                    const int b = sPb[grp][j], wb = sPw[grp][j];
+                    const int offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
+                    for (int g = 0; g < Lb; g++) {
+                        const int4 i0 = rm0(t, offb + g);
+                        const int pg = rm1(t, offb + g).x;
+                        if (i0.x == f.x && pg <= top && i0.z >= f.y) key = max(key, pg);    // closed overlap with this filling
+                    }
+                    if (key >= 0 && b < a && !(fl & 12)) {
+                        bool vis = false, unres = false;
+                        for (int g = 0; g < Lb; g++) {
+                            const int4 i0 = rm0(t, offb + g);
+                            const int ubg = rm1(t, offb + g).y;
+                            const int sf = ld_relaxed(&stop[offb + g]);
+                            for (int fa = 0; fa < La; fa++) {
+                                const int4 ag = rm0(t, offa + fa);
+                                const int pa = rm1(t, offa + fa).x;
+                                if (ag.x == i0.x && pa <= ubg && ag.z >= i0.y) { if (sf < 0) unres = true; else if (sf <= pa) vis = true; }
+                            }
+                        }
+                        if (vis) fl |= 4; else if (!unres) fl |= 8;
+                        sPf[grp][j] = (unsigned char)fl;
+                    }
+                }
+                sKey[grp][j] = key;
+            }
+            __syncwarp(gmask);
+            // pass 2: rank the met partners by position (descending = scan order) and build the reach / edge / undecided masks
+            unsigned long long Rm = 0, Em = 0, Um = 0;
+            for (int j = gl; j < nPart; j += 8) {
+                const int key = sKey[grp][j];
+                if (key < 0) continue;
+                int rank = 0;
+                for (int k = 0; k < nPart; k++) rank += sKey[grp][k] > key;
+                const int fl = sPf[grp][j];
+                const bool later = sPb[grp][j] > a;
+                const unsigned long long bit = 1ull << rank;
+                if (!later && !(fl & 12)) Um |= bit;
+                else if (later || (fl & 8)) { Rm |= bit; if (fl & 2) Em |= bit; }
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                Rm |= __shfl_xor_sync(gmask, Rm, o); Em |= __shfl_xor_sync(gmask, Em, o); Um |= __shfl_xor_sync(gmask, Um, o);
+            }
+            const int nres = Um ? __ffsll((long long)Um) - 1 : 64;
+            const unsigned long long rmask = nres >= 64 ? ~0ull : ((1ull << nres) - 1ull);
+            int brk = -1;
+            for (unsigned long long mm = Rm & rmask; mm; mm &= mm - 1) {           // cluster.py:219-224 in scan order
+                const int l = __ffsll((long long)mm) - 1;
+                if (edges + __popcll(Em & ((2ull << l) - 1ull)) >= t.Tedge) { brk = l; break; }
+            }
+            if (gl == 0) d_steps++;
+            if (brk < 0 && Um) { stalled = true; if (gl == 0) d_stall++; }         // an undecided partner comes first: retry later
+            else {
+                const unsigned long long cmask = brk >= 0 ? ((2ull << brk) - 1ull) : ~0ull;
+                const unsigned long long Ec = Em & cmask;
+                const int ne = __popcll(Ec);
+                if (ne && chunk_used + ne > RP_CHUNK) {                            // reserve a fresh chunk, pad the old one (ne <= RP_K <= RP_CHUNK)
+                    for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+                    if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                    chunk_base = __shfl_sync(gmask, chunk_base, gsh);
+                    chunk_used = 0;
+                    if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                }
+                int stopf = lo;
+                for (int j = gl; j < nPart; j += 8) {
+                    const int key = sKey[grp][j];
+                    if (key < 0) continue;
+                    int rank = 0;
+                    for (int k = 0; k < nPart; k++) rank += sKey[grp][k] > key;
+                    if (!((cmask >> rank) & 1ull)) continue;
+                    sPf[grp][j] |= 1;                                              // a's query has now seen this pair
+                    if ((Ec >> rank) & 1ull) pedges[chunk_base + chunk_used + __popcll(Ec & ((1ull << rank) - 1ull))] = make_int2(a, sPb[grp][j]);
+                    if (rank == brk) stopf = key;
+                }
+                chunk_used += ne;
+                edges += ne;
+                if (brk >= 0) {                                                    // the owner of the break position tells the group
+                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 1));
+                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 2));
+                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 4));
+                }
+                if (gl == 0) { sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); }
+                fi++;
+                if (fi == La) { tk++; phase = 0; }
+            }
+        }
+        // ------------------------------------------------------------ WALK mode
+        else {
+        if (phase == 1) {
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; }
+            else { f = rm0(t, offa + fi); top = rm1(t, offa + fi).y; }
+            lo = __ldg(&t.chrom_lo[f.x]);
+            base = top;
+            phase = 2;
+        }
+        if (phase == 2) {
+            int stopf = -1;                                                        // >= 0: this filling's scan ended there
+            unsigned Ecommit = 0;
+            int b = -1;
+            if (base < lo || __ldg(&t.pmaxS[base]) < f.y) stopf = lo;              // nothing at or below base overlaps the filling
+            else {
+                const int p = base - gl;
+                int fl = 0;
                 if (p >= lo) {
                     const int4 c0 = __ldg(&t.SR0[p]);
                     const int4 c1 = __ldg(&t.SR1[p]);
-                    b = c0.w;
-                    if (b != a && c0.y >= f.y                                          // closed overlap (start_p <= end_f by p <= ub)
+                    b = c0.w & QMASK;
+                    if (b != a && c0.y >= f.y                                      // closed overlap (start_p <= end_f by p <= ub)
                         && difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
-                        const int offb = c1.w >> 6, Lb = (c1.w & 63) + 1;
-                        const int bP = (b < a) ? __ldg(&isP[b]) : 0;
-                        if (b > a || bP) {                                             // b < a and never breaking: it saw the pair
-                            if (La <= 4 && Lb <= 4) {
-                                // ---- lists in registers, everything unrolled
-                                int4 bg[4]; int2 bq[4];
+                        const int offb = (int)((unsigned)c1.w >> 6), Lb = (c1.w & 63) + 1;
+                        if (La <= 4 && Lb <= 4) {
+                            // ---- lists in registers, everything unrolled; all loads of this candidate are issued together
+                            const int bP = (b < a) ? __ldg(&isP[b]) : 1;           // b < a and never breaking: it saw the pair
+                            int4 bg[4]; int2 bq[4]; int sb[4];
 #pragma unroll
-                                for (int g = 0; g < 4; g++) {
-                                    bg[g] = g < Lb ? __ldg(&t.RM0[offb + g]) : make_int4(-2, 0, 0, 0x7fffffff);
-                                    bq[g] = g < Lb ? __ldg(&t.RM1[offb + g]) : make_int2(-1, -1);
-                                }
-                                bool met = false;                                      // pair already seen earlier in this very query?
+                            for (int g = 0; g < 4; g++) {
+                                bg[g] = g < Lb ? rm0(t, offb + g) : make_int4(-2, 0, 0, 0x7fffffff);
+                                bq[g] = g < Lb ? rm1(t, offb + g) : make_int2(-1, -1);
+                                sb[g] = (b < a && g < Lb) ? ld_relaxed(&stop[offb + g]) : 0x7fffffff;
+                            }
+                            if (bP) {
+                                bool met = false;                                  // pair already seen earlier in this very query?
                                 unsigned m[4];
 #pragma unroll
                                 for (int fa = 0; fa < 4; fa++) {
-                                    const int4 af = fa < La ? A0[w][fa] : make_int4(-1, 0, 0, 0x7fffffff);
-                                    const int aub = A1[w][fa].y, ast = Astop[w][fa];
+                                    const int4 af = fa < La ? sA0[grp][fa] : make_int4(-1, 0, 0, 0x7fffffff);
+                                    const int aub = sA1[grp][fa].y, ast = sStop[grp][fa];
                                     unsigned r = 0;
 #pragma unroll
                                     for (int g = 0; g < 4; g++) {
-                                        r |= (match4(af, bg[g]) ? 1u : 0u) << g;
+                                        r |= (matchT<ALLMATCH>(af, bg[g]) ? 1u : 0u) << g;
                                         met |= (fa < fi) && af.x == bg[g].x && ast <= bq[g].x && bq[g].x <= aub && bg[g].z >= af.y;
                                     }
                                     m[fa] = r;
@@ -701,94 +881,87 @@ __global__ void __launch_bounds__(REPLAY_WARPS * 32) k_replay(Tab t, int nP, con
                                     unsigned used = 0; int n = 0;
 #pragma unroll
                                     for (int fa = 0; fa < 4; fa++) { const unsigned av = m[fa] & ~used; if (av) { used |= av & (0u - av); n++; } }
-                                    tests++;
+                                    fl = RF_TESTED;
                                     if (n > 0) {
-                                        reach = true;
-                                        if (b < a) {                                   // b queried first: did it get here?
-                                            if ((unsigned)__ldg(&posQ[b]) < tk0)       // b belongs to another warp's run: wait for it
-                                                while (ld_acquire(&final_[b]) == 0) __nanosleep(40);
-                                            bool vis = false;
+                                        bool vis = false, unres = false;
+                                        if (b < a) {                               // b queried first: did its scans get here?
 #pragma unroll
                                             for (int g = 0; g < 4; g++) {
-                                                const int sf = g < Lb ? __ldcg(&stop[offb + g]) : 0x7fffffff;
 #pragma unroll
                                                 for (int fa = 0; fa < 4; fa++) {
-                                                    const int4 af = fa < La ? A0[w][fa] : make_int4(-1, 0, 0, 0);
-                                                    const int pa = A1[w][fa].x;
-                                                    vis |= af.x == bg[g].x && sf <= pa && pa <= bq[g].y && af.z >= bg[g].y;
+                                                    const int4 af = fa < La ? sA0[grp][fa] : make_int4(-1, 0, 0, 0);
+                                                    const int pa = sA1[grp][fa].x;
+                                                    if (af.x == bg[g].x && pa <= bq[g].y && af.z >= bg[g].y) {
+                                                        if (sb[g] < 0) unres = true; else if (sb[g] <= pa) vis = true;
+                                                    }
                                                 }
                                             }
-                                            if (vis) reach = false;
                                         }
-                                        edge = reach && (La + Lb - n) <= c_umax[n];
-                                    }
-                                }
-                            } else {
-                                bool met = false;
-                                for (int g = 0; g < Lb && !met; g++) {
-                                    const int4 bg = __ldg(&t.RM0[offb + g]);
-                                    const int pg = __ldg(&t.RM1[offb + g]).x;
-                                    for (int f2 = 0; f2 < fi; f2++) {
-                                        const int4 af = A0[w][f2];
-                                        if (af.x == bg.x && Astop[w][f2] <= pg && pg <= A1[w][f2].y && bg.z >= af.y) { met = true; break; }
-                                    }
-                                    if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) met = true;
-                                }
-                                if (!met) {
-                                    int ffa, ffb;
-                                    const int n = greedy_ab(A0[w], La, t.RM0 + offb, Lb, &ffa, &ffb);
-                                    tests++;
-                                    if (n > 0) {
-                                        reach = true;
-                                        if (b < a) {
-                                            if ((unsigned)__ldg(&posQ[b]) < tk0)
-                                                while (ld_acquire(&final_[b]) == 0) __nanosleep(40);
-                                            if (visited_ba(t.RM0, t.RM1, stop, offb, Lb, A0[w], A1[w], La)) reach = false;
-                                        }
-                                        edge = reach && (La + Lb - n) <= c_umax[n];
+                                        if (vis) { }
+                                        else if (unres) fl |= RF_UNRES;
+                                        else fl |= RF_REACH | ((La + Lb - n) <= c_umax[n] ? RF_EDGE : 0);
                                     }
                                 }
                             }
+                        } else if (b > a || __ldg(&isP[b])) {
+                            fl = replay_eval_general(t, stop, sStop[grp], a, offa, La, fi, f, top, p, b, offb, Lb);
                         }
                     }
                 }
-                const unsigned M = __ballot_sync(FULL, reach), E = __ballot_sync(FULL, edge);
+                const unsigned U = (__ballot_sync(gmask, fl & RF_UNRES) >> gsh) & 0xffu;
+                const unsigned M = (__ballot_sync(gmask, fl & RF_REACH) >> gsh) & 0xffu;
+                const unsigned E = (__ballot_sync(gmask, fl & RF_EDGE) >> gsh) & 0xffu;
+                const unsigned Tm = (__ballot_sync(gmask, fl & RF_TESTED) >> gsh) & 0xffu;
+                const int nres = U ? __ffs(U) - 1 : 8;                             // candidates before the first undecided one
+                const unsigned rmask = (1u << nres) - 1u;
                 int brk = -1;
-                for (unsigned mm = M; mm; mm &= mm - 1) {                              // cluster.py:219-224 in scan order
+                for (unsigned mm = M & rmask; mm; mm &= mm - 1) {                  // cluster.py:219-224 in scan order
                     const int l = __ffs(mm) - 1;
                     if (edges + __popc(E & ((2u << l) - 1u)) >= t.Tedge) { brk = l; break; }
                 }
-                const unsigned Euse = brk >= 0 ? (E & ((2u << brk) - 1u)) : E;
-                if (Euse) {
-                    const int ne = __popc(Euse);
-                    if (chunk_used + ne > RP_CHUNK) {                                  // reserve a fresh chunk, pad the old one
-                        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
-                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
-                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
-                        chunk_used = 0;
-                        if (chunk_base + RP_CHUNK > cap_pedges) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
-                    }
-                    if ((Euse >> lane) & 1u) pedges[chunk_base + chunk_used + __popc(Euse & ((1u << lane) - 1u))] = make_int2(a, b);
-                    chunk_used += ne;
-                }
-                edges += __popc(Euse);
-                if (brk >= 0) { stopf = base - brk; break; }
+                const unsigned cmask = brk >= 0 ? ((2u << brk) - 1u) : rmask;
+                Ecommit = E & cmask;
+                if (gl == 0) tests += __popc(Tm & cmask);
+                edges += __popc(Ecommit);
+                if (brk >= 0) stopf = base - brk;
+                else { base -= nres; stalled = nres == 0; }
+                if (gl == 0) { d_steps++; d_stall += stalled; }
+                d_fsteps++; d_fstall += stalled;
             }
-            if (lane == 0) Astop[w][fi] = stopf;
-            __syncwarp();
+            if (Ecommit) {
+                const int ne = __popc(Ecommit);
+                if (chunk_used + ne > RP_CHUNK) {                                  // reserve a fresh chunk, pad the old one
+                    for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+                    if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                    chunk_base = __shfl_sync(gmask, chunk_base, gsh);
+                    chunk_used = 0;
+                    if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                }
+                if ((Ecommit >> gl) & 1u) pedges[chunk_base + chunk_used + __popc(Ecommit & ((1u << gl) - 1u))] = make_int2(a, b);
+                chunk_used += ne;
+            }
+            if (stopf >= 0) {                                                      // publish the stop; next filling / read
+                if (gl == 0) { sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); }
+                if (dbg && gl == 0 && d_fsteps > 2000) {
+                    if (atomicMax(dbg + 4, (unsigned long long)d_fsteps) < (unsigned long long)d_fsteps) {
+                        dbg[5] = a; dbg[6] = fi; dbg[7] = top - lo; dbg[8] = d_fstall; dbg[9] = top - stopf; dbg[10] = edges; dbg[11] = La;
+                    }
+                }
+                d_fsteps = 0; d_fstall = 0;
+                fi++;
+                if (fi == La) { tk++; phase = 0; } else phase = 1;
+            }
         }
-        for (int k = lane; k < La; k += 32) __stcg(&stop[offa + k], Astop[w][k]);
-        __syncwarp();                                                              // later reads of this run see the stops (L2)
         }
-        // publish the whole run: one fence, then the final flags (reads of other runs wait on these)
-        __threadfence();
-        __syncwarp();
-        for (unsigned tk = tk0 + lane; tk < tk1; tk += 32) *(volatile int *)&final_[__ldg(&plist[tk])] = 1;
+        if (__all_sync(FULL, stalled || phase == 3)) { __nanosleep(100); d_sleep += lane == 0; }
     }
     if (chunk_used < RP_CHUNK)
-        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
+        for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
     for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(FULL, tests, o);
     if (lane == 0 && tests) atomicAdd(n_tests, tests);
+    for (int o = 16; o; o >>= 1) { d_iter += __shfl_down_sync(FULL, d_iter, o); d_steps += __shfl_down_sync(FULL, d_steps, o);
+                                   d_stall += __shfl_down_sync(FULL, d_stall, o); d_sleep += __shfl_down_sync(FULL, d_sleep, o); }
+    if (lane == 0 && dbg) { atomicAdd(dbg, d_iter); atomicAdd(dbg + 1, d_steps); atomicAdd(dbg + 2, d_stall); atomicAdd(dbg + 3, d_sleep); }
 }
 
 // ---------------------------------------------------------------- stage 9: union-find (root = smallest query rank)
@@ -821,14 +994,15 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
         if (a >= 0 && !isP[a]) {
             if (b > a) e = true;
             else if (isP[b]) {
-                const int4 rda = t.RD[a], rdb = t.RD[b];
+                const int wa = t.RI[a].w, wb = t.RI[b].w;
+                const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
                 e = true;
-                for (int f = 0; f < rdb.y && e; f++) {
-                    const int4 bf = t.RM0[rdb.x + f];
-                    const int ubf = t.RM1[rdb.x + f].y, sf = stop[rdb.x + f];
-                    for (int g = 0; g < rda.y; g++) {
-                        const int4 ag = t.RM0[rda.x + g];
-                        const int pg = t.RM1[rda.x + g].x;
+                for (int f = 0; f < Lb && e; f++) {
+                    const int4 bf = rm0(t, offb + f);
+                    const int ubf = rm1(t, offb + f).y, sf = stop[offb + f];
+                    for (int g = 0; g < La; g++) {
+                        const int4 ag = rm0(t, offa + g);
+                        const int pg = rm1(t, offa + g).x;
                         if (ag.x == bf.x && sf <= pg && pg <= ubf && ag.z >= bf.y) { e = false; break; }
                     }
                 }
@@ -911,13 +1085,12 @@ struct Pipe {
     fslrc_params pr;
     int A, R, F, D, Q, nP, Tedge, pair_blocks;
     int *err;
-    int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entries,6 nP,7 pedges,8 edges,9 ncl,10 forest, 11 clustered
+    int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entry slots,6 nP,7 pedge slots,8 edges,9 ncl,10 forest,
+                             //                  11 singletons, 12 runs, 13 entries, 14 tight band
     int *q_of_rid, *rid_of_q;
-    int4 *SR0, *SR1, *RM0, *RD, *RI;
-    int2 *RM1;
-    int *ubS, *lbS, *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
-    unsigned char *s_fi;
-    int *degub, *isP, *plist, *stop, *final_;
+    int4 *SR0, *SR1, *RM, *RI;
+    int *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
+    int *isP, *plist, *stop;
     int2 *entries, *pedges;
     unsigned long long cap_entries, cap_pedges;
     int *parent, *ing;
@@ -960,13 +1133,13 @@ static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const K *kin, K *kout, const int 
     return 0;
 }
 static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
-    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_pin + 16, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 32 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 32, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 static int err_code(fslrc_ctx *ctx) {
-    int e = (int)(ctx->h_pin[16] & 0xffffffff);
+    int e = (int)(ctx->h_pin[32] & 0xffffffff);
     if (!e) return 0;
     if (e & EF_RANGE) return fail(ctx, FSLRC_ERR_RANGE, "a table value is out of range (read_id/chrom id, negative coordinate, n_alignments >= 65535 or a bad `order`)");
     if (e & EF_ZERO) return fail(ctx, FSLRC_ERR_ZERO_DIVISOR, "aln_size, qlen2 or n_alignments <= 0 on a filling (the reference raises ZeroDivisionError)");
@@ -986,9 +1159,9 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
     cudaStream_t st = ctx->stream;
     const int A = P->A, R = P->R, TB = 256;
-    DA(P->err, 1); DA(P->cnt, 16);
+    DA(P->err, 1); DA(P->cnt, 32);
     CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(P->cnt, 0, 16 * sizeof(int64_t), st));
+    CK(cudaMemsetAsync(P->cnt, 0, 32 * sizeof(int64_t), st));
     CK(cudaMemcpyToSymbolAsync(c_umax, pr.umax, sizeof(int) * (LMAX + 1), 0, cudaMemcpyHostToDevice, st));
     long long *d_clen; unsigned char *d_cmask;
     DA(d_clen, pr.n_chrom); DA(d_cmask, pr.n_chrom);
@@ -1058,14 +1231,14 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(P->rid_of_q, Q);
     int *qs, *rm_dp, *iotaD, *rmidx, *off, *len_end;
     DA(qs, D); DA(rm_dp, D); DA(iotaD, D); DA(rmidx, D); DA(off, Q); DA(len_end, Q);
-    DA(P->RD, Q); DA(P->RI, Q);
+    DA(P->RI, Q);
     if (R > 0) KL(k_rank_reads, nblk(R, TB), TB, R, firstdp, posD, P->q_of_rid, P->rid_of_q);
     if (D > 0) {
         KL(k_item_q, nblk(D, TB), TB, D, IT0, P->q_of_rid, it_q);
         KL(k_iota, nblk(D, TB), TB, iotaD, D);
         int r = sort_pairs<int>(ctx, P, it_q, qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
         KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
-        KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RD, P->RI, P->err);
+        KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RI, P->err);
         KL(k_check_naln, nblk(D, TB), TB, D, it_q, IT1, P->RI, P->err);
     }
     { int r = mark(ctx, 3); if (r) return r; }
@@ -1081,36 +1254,37 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     { int r = mark(ctx, 4); if (r) return r; }
     // ---- stage 5: records, thresholds, bands
     int *s_end;
-    DA(P->SR0, D); DA(P->SR1, D); DA(P->RM0, D); DA(P->RM1, D); DA(P->s_chrom, D); DA(s_end, D);
-    DA(P->ubS, D); DA(P->pmaxS, D); DA(P->chrom_lo, pr.n_chrom); DA(P->chrom_hi, pr.n_chrom);
+    DA(P->SR0, D); DA(P->SR1, D); DA(P->RM, 2 * (int64_t)D); DA(P->s_chrom, D); DA(s_end, D);
+    DA(P->pmaxS, D); DA(P->chrom_lo, pr.n_chrom); DA(P->chrom_hi, pr.n_chrom);
     if (pr.n_chrom > 0) { CK(cudaMemsetAsync(P->chrom_lo, 0, sizeof(int) * pr.n_chrom, st)); CK(cudaMemsetAsync(P->chrom_hi, 0, sizeof(int) * pr.n_chrom, st)); }
     if (D > 0) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
-        int *s_m; DA(s_m, D); DA(P->s_fi, D); DA(P->lbS, D);
-        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, P->RD, pr.overlap, P->SR0, P->SR1,
-                                               P->RM0, s_m, P->s_fi, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
-        KL(k_ub, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->chrom_hi, P->ubS, P->RM1, (unsigned long long *)(P->cnt + 3));
+        int *s_m; DA(s_m, D);
+        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
+                                               s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
         size_t b = 0;
         CK(cub::DeviceScan::InclusiveScanByKey(nullptr, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
         int r = cub_tmp(ctx, P, b); if (r) return r;
         b = P->cub_bytes;
         CK(cub::DeviceScan::InclusiveScanByKey(P->cub_tmp, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
-        KL(k_lb, nblk(D, TB), TB, D, P->SR0, P->pmaxS, P->s_chrom, P->chrom_lo, P->lbS);
+        KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM,
+           (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14));
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     long long T = pr.edge_threshold;
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
     Tab &t = P->tab;
-    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM0 = P->RM0; t.RD = P->RD; t.RI = P->RI; t.RM1 = P->RM1; t.ubS = P->ubS; t.lbS = P->lbS; t.s_fi = P->s_fi; t.pmaxS = P->pmaxS;
-    t.s_chrom = P->s_chrom; t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
-    // relation entries: every read records fewer than edge_threshold passing candidates, and never more than exist
-    const unsigned long long band = (unsigned long long)ctx->h_pin[3];
-    unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * (unsigned long long)P->Tedge : 0ull;
-    P->pair_blocks = std::max(1, std::min(nblk(nblk(D, 32), PW_WARPS), n_sms(ctx) * 4));
-    P->cap_entries = std::min<unsigned long long>(capT, 2ull * band) + (unsigned long long)PW_CHUNK * PW_WARPS * P->pair_blocks + 64;
+    t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM = P->RM; t.RI = P->RI; t.pmaxS = P->pmaxS;
+    t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
+    // relation entries: a read records at most edge_threshold + 7 passing partners (one step past the threshold), and every
+    // entry is a distinct (filling of a, band position) hit
+    const unsigned long long tight = (unsigned long long)ctx->h_pin[14];
+    unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * ((unsigned long long)P->Tedge + 7ull) : 0ull;
+    P->pair_blocks = std::max(1, std::min(nblk(Q, PK_GROUPS), n_sms(ctx) * 8));
+    P->cap_entries = std::min<unsigned long long>(capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks + 64;
     DA(P->entries, P->cap_entries);
-    DA(P->degub, Q); DA(P->isP, Q); DA(P->stop, D); DA(P->final_, Q); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
-    if (Q > 0) CK(cudaMemsetAsync(P->degub, 0, sizeof(int) * Q, st));
+    DA(P->isP, Q); DA(P->stop, D); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
+    if (Q > 0) CK(cudaMemsetAsync(P->isP, 0, sizeof(int) * Q, st));
     return mark(ctx, 5);
 }
 
@@ -1118,22 +1292,24 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
 // ---- stage 6: pair kernel on one shard
 static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
-    if (P->D > 0) {
-        const int nTiles = nblk(P->D, 32);
-        KL(k_pair, P->pair_blocks, PW_WARPS * 32, P->tab, nTiles, shard, nshard, P->degub, P->entries, (unsigned long long *)(P->cnt + 5),
-           P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
+    if (P->Q > 0) {
+        if (P->pr.overlap > 0.0)
+            KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+               P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
+        else
+            KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+               P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
     }
     return mark(ctx, 6);
 }
 
-// ---- stages 7-9 (after degub is complete): saturating set, replay, union-find
+// ---- stages 7-9 (after isP is complete): saturating set, replay, union-find
 static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
     const int Q = P->Q, D = P->D, TB = 256;
     int *posQ;
     DA(posQ, Q);
     if (Q > 0) {
-        KL(k_satur_flags, nblk(Q, TB), TB, Q, P->degub, P->Tedge, P->isP);
         int r = xscan(ctx, P, P->isP, posQ, Q); if (r) return r;
         KL(k_total, 1, 1, posQ, P->isP, Q, P->cnt + 6);
     }
@@ -1141,40 +1317,44 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     const int nP = P->nP = (int)ctx->h_pin[6];
     DA(P->plist, nP);
     if (Q > 0) KL(k_compact_flagged, nblk(Q, TB), TB, Q, P->isP, posQ, P->plist);
-    // stops: a read that never breaks walks every filling's scan to the chromosome start; final = not saturating
+    // stops: a read that never breaks walks every filling's scan to the chromosome start (0 <= any position)
     if (D > 0) CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st));
-    if (Q > 0) CK(cudaMemsetAsync(P->final_, 0, sizeof(int) * Q, st));
     CK(cudaMemsetAsync(P->ticket, 0, sizeof(unsigned), st));
     { int r = mark(ctx, 7); if (r) return r; }
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
+    const int replay_blocks_max = n_sms(ctx) * 8;
     unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
     unsigned long long alt = 2ull * (unsigned long long)ctx->h_pin[3] + 64;
-    P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * REPLAY_WARPS * (n_sms(ctx) * 16 + 1);
+    P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * RG_GROUPS * (replay_blocks_max + 1);
     DA(P->pedges, P->cap_pedges);
     if (nP > 0) {
         int *rflag, *rpos, *rstart;
         DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
-        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RD, P->RM0, rflag);
+        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, rflag, P->stop);
         int r = xscan(ctx, P, rflag, rpos, nP); if (r) return r;
         KL(k_total, 1, 1, rpos, rflag, nP, P->cnt + 12);
         KL(k_compact_flagged, nblk(nP, TB), TB, nP, rflag, rpos, rstart);
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
-        int blocks = std::min(nblk(nRuns, REPLAY_WARPS), n_sms(ctx) * 16);
-        KL(k_replay, blocks, REPLAY_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, posQ, P->stop, P->final_, P->ticket, P->pedges,
-           (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err);
+        int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
+        if (P->pr.overlap > 0.0)
+            KL(k_replay<false>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->ticket, P->pedges,
+               (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
+        else
+            KL(k_replay<true>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->ticket, P->pedges,
+               (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
     }
     { int r = mark(ctx, 8); if (r) return r; }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
-    const unsigned long long nped = (unsigned long long)ctx->h_pin[7];
+    const unsigned long long nped = std::min<unsigned long long>((unsigned long long)ctx->h_pin[7], P->cap_pedges);
     if (Q > 0) {
         KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
     if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
                                                                            (unsigned long long *)(P->cnt + 8));
-    // replayed edges are identical on every rank; rank `shard` contributes them once
+    // replayed edges are identical on every rank; rank 0 contributes them once
     if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));
     (void)nshard;
     return mark(ctx, 9);
@@ -1209,6 +1389,10 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[13]; s->saturating_reads = P->nP;
     s->edges = h[8]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
     s->no_clusters = h[9] == 0;
+    if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld\n",
+                                       (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12]);
+    if (getenv("FSLRC_DEBUG") && h[20]) fprintf(stderr, "[fslrc] longest walk: %lld steps (stalled %lld) read %lld filling %lld/%lld band %lld walked %lld edges %lld\n",
+                                       (long long)h[20], (long long)h[24], (long long)h[21], (long long)h[22], (long long)h[27], (long long)h[23], (long long)h[25], (long long)h[26]);
     for (int i = 0; i < FSLRC_N_STAGES; i++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { ms = 0.f; cudaGetLastError(); }
@@ -1350,7 +1534,7 @@ int fslrc_mg_pair(fslrc_ctx *ctx, int rank, int world, int32_t **counts, int64_t
     CK(cudaSetDevice(ctx->device));
     int r = pipe_pair(ctx, P, rank, world); if (r) return r;
     CK(cudaStreamSynchronize(ctx->stream));
-    *counts = P->degub; *n_counts = P->Q;
+    *counts = P->isP; *n_counts = P->Q;
     return 0;
 }
 int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64_t *n_forest_edges) {

@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/fslr/cluster.py,
 through oracle/ref_harness.py) in the build container.  Run from the repo root:
 
-    python tests/golden/make_golden.py [--only small|configs]
+    python tests/golden/make_golden.py [--only small|wide|configs]
 
 Each case stores its input columns, the option strings, the permutation the reference's own
 unstable sort produced on the generating host (cluster.py:114 — host dependent, so it is part of
@@ -229,6 +229,56 @@ def small_cases():
     save(os.path.join(HERE, "small_cases.npz"), cases)
 
 
+def wide_table(rng):
+    """Reads with up to 9 fillings (device paths for > 4 fillings), bigger duplicate families (many saturating reads),
+    fillings of one read that overlap each other (one partner hit by several fillings) and partial structure sharing."""
+    n_reads = int(rng.integers(30, 161))
+    n_struct = int(rng.integers(1, 5))
+    chroms = ["chr1", "chr2", "chrX"]
+    structs = []
+    for _ in range(n_struct):
+        L = int(rng.integers(1, 10))
+        st = []
+        for _ in range(L):
+            c = chroms[int(rng.integers(0, 3))]
+            s = int(rng.integers(600_000, 600_300)) if rng.random() < 0.6 else int(rng.integers(600_000, 700_000))
+            st.append((c, s, int(rng.integers(80, 500))))
+        structs.append(st)
+    if n_struct > 1 and rng.random() < 0.5:                       # a structure sharing a prefix with another one
+        structs[-1] = structs[0][: max(1, len(structs[0]) // 2)] + structs[-1][:3]
+    rows = []
+    jit = int(rng.integers(0, 12))
+    for r in range(n_reads):
+        st = list(structs[int(rng.integers(0, n_struct))])
+        if rng.random() < 0.1 and len(st) > 1:
+            st.pop(int(rng.integers(0, len(st))))
+        fl = []
+        for c, s, ln in st[:9]:
+            s2 = s + int(rng.integers(-jit, jit + 1))
+            e2 = s2 + ln + int(rng.integers(-jit, jit + 1))
+            if e2 <= s2:
+                e2 = s2 + 5
+            fl.append((c, s2, e2, max(1, abs(e2 - s2) + int(rng.integers(-2, 3)))))
+        rows += read_rows("%06d" % rng.integers(0, 10**6) + "w%d" % r, fl, n_aln=len(fl) + 2)
+    df = frame(rows)
+    df = df.sort_values(["n_alignments", "qname", "qstart"], ascending=[False, True, True]).reset_index(drop=True)
+    lens = {"chr1": 100_000_000, "chr2": 90_000_000, "chrX": 900_000, "chr9": 100_000_000, "chr10": 100_000_000}
+    return df, lens
+
+
+def wide_cases():
+    cases = []
+    rng = np.random.default_rng(20261019)
+    cut_lists = ["1,1,0.66,0.66,0.66,0.5", "0.5", "1,0.5,0.34", "0.2"]
+    for i in range(120):
+        df, lens = wide_table(rng)
+        opts = dict(edge_threshold=int(rng.choice([1, 2, 3, 10, 10])), jaccard_cutoffs=cut_lists[i % 4],
+                    overlap=float(rng.choice([0.8, 0.5, 0.95, 0.0, -0.5])), cluster_mask="subtelomere" if i % 5 else "",
+                    qlen_diff=float(rng.choice([0.04, 0.2])), n_alignment_diff=float(rng.choice([0.25, 0.5])))
+        cases.append(run_case("wide%03d" % i, df, lens, opts))
+    save(os.path.join(HERE, "wide_cases.npz"), cases)
+
+
 def config_cases():
     """Named configs at the sizes the Python reference finishes in minutes; inputs are regenerated
     from the seed at test time, so only the sort permutation and the expected outputs are stored."""
@@ -259,5 +309,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "small"):
         small_cases()
+    if a.only in ("", "wide"):
+        wide_cases()
     if a.only in ("", "configs"):
         config_cases()

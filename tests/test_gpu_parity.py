@@ -35,6 +35,18 @@ def test_golden_small_cases(engine):
     assert not failed, "%d/%d cases differ: %s" % (len(failed), len(cases), failed[:5])
 
 
+def test_golden_wide_cases(engine):
+    """> 4 fillings per read (general device paths), --overlap <= 0, many saturating reads."""
+    cases = golden_io.load("wide_cases.npz")
+    failed = []
+    for c in cases:
+        try:
+            _check_case(engine, c)
+        except AssertionError as e:
+            failed.append(str(e))
+    assert not failed, "%d/%d cases differ: %s" % (len(failed), len(cases), failed[:5])
+
+
 @pytest.mark.parametrize("idx", range(8))
 def test_golden_config_cases(engine, idx):
     cases = golden_io.load("config_cases.npz")
