@@ -441,48 +441,73 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 #define PK_GROUPS (PK_WARPS * 4)
 #define PK_HASH 64              // settled-partner filter slots per group
 #define PK_CHUNK 256            // relation-entry slots a warp reserves at a time (>= 32)
+#define RP_K 32                 // partners a saturating read may have for the replay's LIST mode
+#define PL_CHUNK 512            // partner records a warp reserves at a time (>= 4 * RP_K)
+#define RP_KL (RP_K / 8)         // partners per lane of a replay group
+
+// Partner record of a saturating read a (replay LIST mode): everything the replay needs to know about partner b without
+// touching b's geometry again.  r0 = {b | edge << 31, off_b << 6 | L_b - 1, cg, 0}, r1 = {key[0..3]}:
+//   edge    a -> b passes the Jaccard cutoff (cluster.py:218-219),
+//   cg      nibble g: 4 | fa* when filling g of b overlaps (closed intervals) a filling of a, fa* = the overlapped filling of
+//           a with the highest sorted position: b's scan of g saw a iff it got down to that position,
+//   key[fa] the highest sorted position of an interval of b inside the closed band of a's filling fa (-1: none): where
+//           a's scan of fa first meets b.
+struct PLInfo { unsigned long long off; int n; int pad; };
 
 template <bool ALLMATCH>
-__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int nshard, int *isP, int2 *entries,
+__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int nshard, int lists_only, int *isP, int2 *entries,
                                                          unsigned long long *n_slots, unsigned long long cap_entries,
+                                                         int4 *PL, PLInfo *plinfo, unsigned long long *pl_slots, unsigned long long cap_pl,
                                                          unsigned long long *n_tests, unsigned long long *n_real, int *err) {
     __shared__ int4 sA[PK_GROUPS][4];
-    __shared__ int2 sBand[PK_GROUPS][4];
+    __shared__ int4 sB[PK_GROUPS][4];                                              // {lbT, ubT, pos, ub} of a's fillings
     __shared__ int2 sHash[PK_GROUPS][PK_HASH];
+    __shared__ int2 sPart[PK_GROUPS][RP_K];                                        // {b | edge << 31, off_b << 6 | L_b - 1}
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, g = lane >> 3, grp = w * 4 + g;
     const unsigned ltmask = (1u << lane) - 1u, gmask = 0xffu << (g * 8);
-    unsigned long long tests = 0, real = 0, chunk_base = 0;
-    int chunk_used = PK_CHUNK;                                                     // nothing reserved yet
+    unsigned long long tests = 0, real = 0, chunk_base = 0, pl_base = 0;
+    int chunk_used = PK_CHUNK, pl_used = PL_CHUNK;                                 // nothing reserved yet
     for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
     const int stride = gridDim.x * PK_GROUPS;
     for (int q0 = blockIdx.x * PK_GROUPS; q0 < t.Q; q0 += stride) {                // block-uniform trip count
         const int q = q0 + grp;
-        const bool live = q < t.Q && (nshard <= 1 || ((q >> 8) % nshard) == shard); // 256-read groups, round robin over ranks
+        const bool mine = nshard <= 1 || ((q >> 8) % nshard) == shard;             // 256-read groups, round robin over ranks
+        // pass 0: the reads of this shard; pass 1 (multi-GPU, after the exchange of isP): partner lists of the saturating
+        // reads the other shards own
+        const bool live = q < t.Q && (lists_only ? (!mine && __ldg(&isP[q]) != 0) : mine);
         int4 ri = make_int4(0, 0, 0, 0);
         if (live) ri = __ldg(&t.RI[q]);
         const int off = (int)((unsigned)ri.w >> 6), La = live ? (ri.w & 63) + 1 : 0;
         __syncwarp();
-        if (gl < min(La, 4)) { sA[grp][gl] = rm0(t, off + gl); sBand[grp][gl] = rm2(t, off + gl); }
+        if (gl < min(La, 4)) {
+            sA[grp][gl] = rm0(t, off + gl);
+            const int2 pu = rm1(t, off + gl), bd = rm2(t, off + gl);
+            sB[grp][gl] = make_int4(bd.x, bd.y, pu.x, pu.y);
+        }
         __syncwarp();
-        int cnt = 0;
+        int cnt = lists_only ? t.Tedge : 0;                                        // passing partners so far
+        int nPart = 0;                                                             // partners buffered for the replay; -1: too many / too long
         const int maxLa = __reduce_max_sync(FULL, La);
         for (int fi = 0; fi < maxLa; fi++) {
-            const bool fact = fi < La && cnt < t.Tedge;
+            // a read keeps scanning while it may still be non-saturating (its entries must be complete) or while its
+            // partner list is still within bounds (the replay wants all of it)
+            bool fact = fi < La && (cnt < t.Tedge || nPart >= 0);
             int4 f = make_int4(0, 0, 0, 0);
             int2 band = make_int2(1, 0);
             if (fact) {
-                if (La <= 4) { f = sA[grp][fi]; band = sBand[grp][fi]; }
-                else { f = rm0(t, off + fi); band = rm2(t, off + fi); }
+                if (La <= 4) { f = sA[grp][fi]; band = make_int2(sB[grp][fi].x, sB[grp][fi].y); }
+                else { f = rm0(t, off + fi); band = rm2(t, off + fi); nPart = -1; fact = cnt < t.Tedge; }
             }
             for (int ch = 0;; ch++) {
                 const int p = band.x + ch * 8 + gl;
-                const bool v = fact && cnt < t.Tedge && p <= band.y;
+                const bool v = fact && (cnt < t.Tedge || nPart >= 0) && p <= band.y;
                 if (!__any_sync(FULL, v)) break;                                    // every group of the warp is through its band
                 int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
                 if (v) c0 = __ldg(&t.SR0[p]);
                 const int b = c0.w & QMASK;
-                bool pass = false;
+                bool pass = false, part = false, longb = false;
+                int wb = 0;
                 if (v && b != q && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z)) {   // cluster.py:157 for this interval pair
                     int2 *hs = &sHash[grp][b & (PK_HASH - 1)];
                     const int2 hv = *hs;
@@ -490,22 +515,36 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
                         const int4 c1 = __ldg(&t.SR1[p]);
                         bool settled = true;
                         if (difflen_ok(ri.x, ri.y, ri.z, c1.x, c1.y, c1.z)) {
-                            const int offb = (int)((unsigned)c1.w >> 6), Lb = (c1.w & 63) + 1;
+                            wb = c1.w;
+                            const int offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
                             const int fbp = (int)((unsigned)c0.w >> 26);
                             int n, fl;
                             if (La <= 4 && Lb <= 4) fl = eval_small<ALLMATCH>(sA[grp], La, t.RM + 2 * offb, Lb, fi, fbp, &n);
-                            else fl = eval_general<ALLMATCH>(t.RM + 2 * off, La, t.RM + 2 * offb, Lb, fi, fbp, &n);
+                            else { fl = eval_general<ALLMATCH>(t.RM + 2 * off, La, t.RM + 2 * offb, Lb, fi, fbp, &n); longb = true; }
                             settled = (fl & 2) != 0;
                             if (settled) {
                                 tests++;
+                                part = n > 0;                                       // the pair can be an effective candidate (cluster.py:216)
                                 pass = n > 0 && (La + Lb - n) <= c_umax[n];         // cluster.py:165-170,218-219
                             }
                         }
                         if (settled) *hs = make_int2(b, q);
                     }
                 }
+                // ---- partner buffer (only used if the read turns out saturating)
+                const unsigned am = __ballot_sync(FULL, part) & gmask, lm = __ballot_sync(FULL, longb) & gmask;
+                if (am) {
+                    const int na = __popc(am);
+                    if (ALLMATCH || nPart < 0 || lm || nPart + na > RP_K) nPart = -1;
+                    else {
+                        if (part) sPart[grp][nPart + __popc(am & ltmask)] = make_int2((int)((unsigned)b | (pass ? 0x80000000u : 0u)), wb);
+                        nPart += na;
+                    }
+                }
+                // ---- relation entries of reads still below the threshold: warp-aggregated append
+                pass = pass && !lists_only && cnt < t.Tedge;
                 const unsigned pm = __ballot_sync(FULL, pass);
-                if (pm) {                                                           // warp-aggregated append to the relation list
+                if (pm) {
                     const int n = __popc(pm);
                     if (chunk_used + n > PK_CHUNK) {
                         for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
@@ -522,7 +561,48 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
                 __syncwarp();                                                       // filter updates visible to the next step
             }
         }
-        if (live && gl == 0) isP[q] = cnt >= t.Tedge;
+        // ---- saturating read: publish its partner records for the replay
+        const bool sat = live && cnt >= t.Tedge;
+        if (live && gl == 0 && !lists_only) isP[q] = sat;
+        const int nrec = (sat && nPart > 0) ? nPart : 0;
+        int tot = nrec;                                                             // records of the warp's 4 groups
+        tot = __shfl_sync(FULL, tot, 0) + __shfl_sync(FULL, tot, 8) + __shfl_sync(FULL, tot, 16) + __shfl_sync(FULL, tot, 24);
+        if (tot) {
+            if (pl_used + tot > PL_CHUNK) {
+                if (lane == 0) pl_base = atomicAdd(pl_slots, (unsigned long long)PL_CHUNK);
+                pl_base = __shfl_sync(FULL, pl_base, 0);
+                pl_used = 0;
+                if (pl_base + PL_CHUNK > cap_pl) { if (lane == 0) atomicOr(err, EF_OVERFLOW); pl_base = 0; }
+            }
+            int before = 0;                                                         // records of the lower groups
+            for (int gg = 0; gg < 3; gg++) { const int x = __shfl_sync(FULL, nrec, gg * 8); if (gg < g) before += x; }
+            const unsigned long long my0 = pl_base + pl_used + before;
+            pl_used += tot;
+            for (int j = gl; j < nrec; j += 8) {
+                const int2 pr = sPart[grp][j];
+                const int offb = (int)((unsigned)pr.y >> 6), Lb = (pr.y & 63) + 1;
+                int key[4] = {-1, -1, -1, -1};
+                unsigned cg = 0;
+                for (int gb = 0; gb < Lb; gb++) {
+                    const int4 i0 = rm0(t, offb + gb);
+                    const int pg = rm1(t, offb + gb).x;
+                    int best = -1, bestfa = 0;
+#pragma unroll
+                    for (int fa = 0; fa < 4; fa++) {
+                        const int4 af = sA[grp][fa];
+                        if (fa < La && af.x == i0.x && af.y <= i0.z && af.z >= i0.y) {   // closed overlap: a scan of one visits the other
+                            key[fa] = max(key[fa], pg);
+                            if (sB[grp][fa].z > best) { best = sB[grp][fa].z; bestfa = fa; }
+                        }
+                    }
+                    if (best >= 0) cg |= (4u | (unsigned)bestfa) << (4 * gb);
+                }
+                PL[2 * (my0 + j)] = make_int4(pr.x, pr.y, (int)cg, 0);
+                PL[2 * (my0 + j) + 1] = make_int4(key[0], key[1], key[2], key[3]);
+            }
+            if (sat && gl == 0) { PLInfo pi; pi.off = my0; pi.n = nPart; pi.pad = 0; plinfo[q] = pi; }
+        }
+        if (sat && nPart <= 0 && gl == 0) { PLInfo pi; pi.off = 0; pi.n = nPart < 0 ? -1 : 0; pi.pad = 0; plinfo[q] = pi; }
     }
     if (chunk_used < PK_CHUNK)
         for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
@@ -551,6 +631,7 @@ __global__ void k_compact_flagged(int n, const int *__restrict__ flag, const int
 #define RG_WARPS 4
 #define RG_GROUPS (RG_WARPS * 4)
 #define RUN_CAP 64
+#define RUN_LONG 1
 #define RP_CHUNK 64             // edge slots a group reserves at a time (>= 8)
 enum { RF_TESTED = 1, RF_REACH = 2, RF_EDGE = 4, RF_UNRES = 8 };
 __device__ __forceinline__ int ld_relaxed(const int *p) {
@@ -561,22 +642,37 @@ __device__ __forceinline__ int ld_relaxed(const int *p) {
 __device__ __forceinline__ void st_relaxed(int *p, int v) {
     asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// run starts: ticket k opens a new run unless its read's first filling reciprocally overlaps the previous saturating
-// read's first filling (same PCR family: they depend on each other), or the run would exceed RUN_CAP reads.
-// Also marks the stops of every saturating read as "not known yet".
-__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RI, const int4 *__restrict__ RM, int *flag, int *stop) {
+// stop words: >= 0 final stop position of a filling's scan; < 0 while unknown: -2 - x means "every candidate at a
+// position >= x has been visited already" (progress of a long walk), STOP_UNSTARTED = nothing known yet.
+#define STOP_UNSTARTED ((int)0x80000000)
+__device__ __forceinline__ int stop_reached(int v) { return v >= 0 ? v : -2 - v; }   // lowest position known to be visited
+// streak starts: ticket k continues the previous saturating read's streak iff their first fillings reciprocally overlap
+// (same PCR family: they depend on each other).  Also marks the stops of every saturating read as unknown.
+__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RI, const int4 *__restrict__ RM, int *flag,
+                            int *stop, int *stopS) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nP) return;
     const int w = RI[plist[k]].w;
     const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1;
-    for (int j = 0; j < L; j++) stop[off + j] = -1;
+    for (int j = 0; j < L; j++) { stop[off + j] = STOP_UNSTARTED; stopS[RM[2 * (off + j) + 1].x] = STOP_UNSTARTED; }
     int f = 1;
-    if (k > 0 && (k & (RUN_CAP - 1)) != 0) {
+    if (k > 0) {
         const int4 x = RM[2 * ((unsigned)RI[plist[k - 1]].w >> 6)], y = RM[2 * off];
         const int ov = min(x.z, y.z) - max(x.y, y.y);
         if (x.x == y.x && max(ov, 0) >= max(x.w, y.w)) f = 0;
     }
     flag[k] = f;
+}
+// runs: a streak of up to RUN_CAP reads is one run (one group walks it back to back: its reads wait on each other
+// anyway); a longer streak is a giant clique whose reads mostly do NOT depend on each other — cut it into runs of RUN_LONG
+__global__ void k_run_cut(int nP, const int *__restrict__ sflag, const int *__restrict__ spos, const int *__restrict__ sstart,
+                          const int64_t *__restrict__ n_streaks, int *rflag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nP) return;
+    const int sid = spos[k] + sflag[k] - 1;
+    const int start = sstart[sid], end = (sid + 1 < (int)*n_streaks) ? sstart[sid + 1] : nP;
+    const int cap = (end - start) > RUN_CAP ? RUN_LONG : RUN_CAP;
+    rflag[k] = ((k - start) % cap) == 0;
 }
 // one candidate b of read a's filling scan when either read has more than 4 fillings (lists stay in global memory)
 __device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
@@ -602,7 +698,7 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, c
             for (int fa = 0; fa < La; fa++) {
                 const int4 ag = rm0(t, offa + fa);
                 const int pa = rm1(t, offa + fa).x;
-                if (ag.x == bf.x && pa <= ubf && ag.z >= bf.y) { if (sf < 0) unres = true; else if (sf <= pa) vis = true; }
+                if (ag.x == bf.x && pa <= ubf && ag.z >= bf.y) { if (stop_reached(sf) <= pa) vis = true; else if (sf < 0) unres = true; }
             }
         }
         if (vis) return RF_TESTED;
@@ -613,44 +709,49 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, c
 // Two ways to re-run one read's query:
 //   LIST mode (the normal case): the only candidates that can ever matter to a's query are intervals of reads b that share
 //     a reciprocally overlapping filling pair with a (n_i > 0, cluster.py:216) — everything else is skipped by the reference
-//     before it touches `edges` or the break.  Those partners all sit in a's TIGHT bands, so the group first builds a's
-//     partner list (<= RP_K reads, each evaluated once: greedy intersection + Jaccard cutoff), then replays every filling's
-//     scan over the partners only: a partner is first met at its highest interval inside the filling's closed band, the
-//     partners are ranked by that position (descending = scan order) and the break position follows from prefix counts —
-//     one step per filling, however long the closed band is.
-//   WALK mode (reads with too many partners, e.g. a 500k-read hotspot, or --overlap <= 0): the closed band is walked
-//     downwards 8 sorted positions per step and every candidate is evaluated; such reads break after a few steps.
-#define RP_K 64                 // partners a read may have in LIST mode
-static_assert(RP_K <= RP_CHUNK && RP_K <= 64, "list-mode edges of one filling must fit one chunk and one 64-bit mask");
-#define RP_TIGHT_MAX 512        // tight-band positions above which the partner list is not even attempted
+//     before it touches `edges` or the break.  The pair kernel already met and evaluated all of them and left one record
+//     per partner (<= RP_K): the group loads the records and replays every filling's scan over the partners only.  A
+//     partner is first met at its highest interval inside the filling's closed band (key), scan order = descending key,
+//     and the break position follows from a selection over the keys — one step per filling, however long the band is.
+//   WALK mode (reads with too many partners, e.g. a 500k-read hotspot, more than 4 fillings, or --overlap <= 0): the
+//     closed band is walked downwards 8 sorted positions per step and every candidate is evaluated; candidates whose own
+//     scan of that very interval already passed a's filling are skipped on two coalesced loads, 64 positions per step.
+static_assert(RP_K <= RP_CHUNK && 4 * RP_K <= PL_CHUNK, "chunk sizes");
+// group-wide max over the 8 lanes of a group
+__device__ __forceinline__ int gmax8(unsigned gmask, int v) {
+    v = max(v, __shfl_xor_sync(gmask, v, 1)); v = max(v, __shfl_xor_sync(gmask, v, 2)); v = max(v, __shfl_xor_sync(gmask, v, 4));
+    return v;
+}
 template <bool ALLMATCH>
-__global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
-                                                           const int *__restrict__ rstart, const int *__restrict__ isP, int *stop,
-                                                           unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
+__global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+                                                           const int *__restrict__ rstart, const int *__restrict__ isP,
+                                                           const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
+                                                           int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
                                                            unsigned long long cap_pedges, unsigned long long *n_tests, int *err,
                                                            unsigned long long *dbg) {
     __shared__ int4 sA0[RG_GROUPS][4];
     __shared__ int2 sA1[RG_GROUPS][4];
     __shared__ int sStop[RG_GROUPS][LMAX];
-    __shared__ int sPb[RG_GROUPS][RP_K];                                           // partner read (query rank)
-    __shared__ int sPw[RG_GROUPS][RP_K];                                           // its off << 6 | L - 1
-    __shared__ int sKey[RG_GROUPS][RP_K];                                          // first-visit position in the current filling's scan
-    __shared__ unsigned char sPf[RG_GROUPS][RP_K];                                 // 1 visited by a, 2 edge if reached, 4 b saw a, 8 b did not
-    __shared__ int2 sHash[RG_GROUPS][PK_HASH];
+    __shared__ int4 sP0[RG_GROUPS][RP_K];    // partner records: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}; flags: 1 visited by a,
+    __shared__ int4 sP1[RG_GROUPS][RP_K];    //   4 b saw a first, 8 b did not;  {key[0..3]}
+    __shared__ int sKey[RG_GROUPS][RP_K];    // first-visit position in the current filling's scan
+    __shared__ int sRecTag[RG_GROUPS][32];   // the reads this group replayed last (direct mapped by rank & 31) and their final
+    __shared__ int4 sRecStop[RG_GROUPS][32]; //   stops: partners of one run mostly look each other up here, not in global memory
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, gsh = lane & 24, grp = w * 4 + (lane >> 3);
     const unsigned gmask = 0xffu << gsh;
     // group state (identical in the 8 lanes of a group)
     int phase = 0;                      // 0 next read, 1 walk: next filling, 2 walk: scanning, 3 finished, 4 list: build, 5 list: filling
     unsigned tk = 0, tk1 = 0;
-    int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0;
-    int nPart = 0, bfi = 0, bp = 1, bend = 0;
+    int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0, posf = 0;
+    int nPart = 0;
+    bool wide = false;
     int4 ria = make_int4(0, 0, 0, 0), f = make_int4(0, 0, 0, 0);
     unsigned long long tests = 0, chunk_base = 0;
     unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
     int d_fsteps = 0, d_fstall = 0;
     int chunk_used = RP_CHUNK;
-    for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
+    for (int k = gl; k < 32; k += 8) sRecTag[grp][k] = -1;
     for (;;) {
         __syncwarp();
         d_iter += lane == 0;
@@ -672,156 +773,151 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
                 fi = 0; edges = 0;
                 if (La <= 4 && gl < La) { sA0[grp][gl] = rm0(t, offa + gl); sA1[grp][gl] = rm1(t, offa + gl); }
                 phase = 1;
-                if (!ALLMATCH) {                                                   // few tight-band positions: try the partner list
-                    int ts = 0;
-                    for (int k = gl; k < La; k += 8) { const int2 bd = rm2(t, offa + k); ts += bd.y - bd.x + 1; }
-                    ts += __shfl_xor_sync(gmask, ts, 1); ts += __shfl_xor_sync(gmask, ts, 2); ts += __shfl_xor_sync(gmask, ts, 4);
-                    if (ts <= RP_TIGHT_MAX) { phase = 4; nPart = 0; bfi = -1; bp = 1; bend = 0; }
+                const PLInfo pi = plinfo[a];
+                if (gl == 0) { sRecTag[grp][a & 31] = La <= 4 ? a : -1; sRecStop[grp][a & 31] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff); }
+                if (!ALLMATCH && pi.n >= 0) {                                      // the pair kernel left a's partner records
+                    nPart = pi.n;
+                    int4 r0[RP_KL], r1[RP_KL];
+#pragma unroll
+                    for (int k = 0; k < RP_KL; k++) {
+                        const int j = gl + 8 * k;
+                        if (j < nPart) { r0[k] = __ldg(&PL[2 * (pi.off + j)]); r1[k] = __ldg(&PL[2 * (pi.off + j) + 1]); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < RP_KL; k++) {
+                        const int j = gl + 8 * k;
+                        if (j < nPart) {
+                            const int b = r0[k].x & QMASK;
+                            r0[k].w = (b < a && !__ldg(&isP[b])) ? 1 : 0;          // b < a and never breaking: it saw the pair
+                            sP0[grp][j] = r0[k];
+                            sP1[grp][j] = r1[k];
+                        }
+                    }
+                    phase = 5;
                 }
             }
         }
         if (__all_sync(FULL, phase == 3)) break;
         __syncwarp();
         bool stalled = false;
-        // ------------------------------------------------------------ LIST mode: build the partner list
-        if (phase == 4) {
-            while (bp > bend && bfi < La) {                                        // next filling's tight band
-                bfi++;
-                if (bfi < La) { const int2 bd = rm2(t, offa + bfi); bp = bd.x; bend = bd.y; f = rm0(t, offa + bfi); }
-            }
-            if (bfi >= La) { phase = 5; fi = 0; }
-            else {
-                const int p = bp + gl;
-                bool part = false, eflag = false;
-                int b = -1, wb = 0;
-                if (p <= bend) {
-                    const int4 c0 = __ldg(&t.SR0[p]);
-                    b = c0.w & QMASK;
-                    if (b != a && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z)) {   // cluster.py:157 for this interval pair
-                        int2 *hs = &sHash[grp][b & (PK_HASH - 1)];
-                        const int2 hv = *hs;
-                        if (hv.x != b || hv.y != a) {
-                            const int4 c1 = __ldg(&t.SR1[p]);
-                            bool settled = true;                                    // b < a and never breaking: it saw the pair
-                            if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z) && (b > a || __ldg(&isP[b]))) {
-                                wb = c1.w;
-                                const int offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
-                                const int fbp = (int)((unsigned)c0.w >> 26);
-                                int n, fl;
-                                if (La <= 4 && Lb <= 4) fl = eval_small<false>(sA0[grp], La, t.RM + 2 * offb, Lb, bfi, fbp, &n);
-                                else fl = eval_general<false>(t.RM + 2 * offa, La, t.RM + 2 * offb, Lb, bfi, fbp, &n);
-                                settled = (fl & 2) != 0;
-                                if (settled) { part = true; eflag = (La + Lb - n) <= c_umax[n]; }   // n >= 1: this very pair matches
-                            }
-                            if (settled) *hs = make_int2(b, a);
-                        }
-                    }
-                }
-                const unsigned pm = (__ballot_sync(gmask, part) >> gsh) & 0xffu;
-                if (gl == 0) tests += __popc(pm);
-                if (nPart + __popc(pm) > RP_K) { phase = 1; fi = 0; }              // too many partners: walk the bands instead
-                else {
-                    if (part) {
-                        const int j = nPart + __popc(pm & ((1u << gl) - 1u));
-                        sPb[grp][j] = b; sPw[grp][j] = wb; sPf[grp][j] = eflag ? 2 : 0;
-                    }
-                    nPart += __popc(pm);
-                    bp += 8;
-                }
-                if (gl == 0) d_steps++;
-            }
-        }
         // ------------------------------------------------------------ LIST mode: one filling's scan over the partners
-        else if (phase == 5) {
-            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; }
-            else { f = rm0(t, offa + fi); top = rm1(t, offa + fi).y; }
+        if (phase == 5) {
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; posf = sA1[grp][fi].x; }
+            else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
             lo = __ldg(&t.chrom_lo[f.x]);
-            // pass 1: where does the scan first meet each partner; did an earlier-ranked partner's own query see a first?
-            for (int j = gl; j < nPart; j += 8) {
-                int fl = sPf[grp][j], key = -1;
-                if (!(fl & 1)) {
-                    const int b = sPb[grp][j], wb = sPw[grp][j];
-                    const int offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
-                    for (int g = 0; g < Lb; g++) {
-                        const int4 i0 = rm0(t, offb + g);
-                        const int pg = rm1(t, offb + g).x;
-                        if (i0.x == f.x && pg <= top && i0.z >= f.y) key = max(key, pg);    // closed overlap with this filling
-                    }
-                    if (key >= 0 && b < a && !(fl & 12)) {
-                        bool vis = false, unres = false;
-                        for (int g = 0; g < Lb; g++) {
-                            const int4 i0 = rm0(t, offb + g);
-                            const int ubg = rm1(t, offb + g).y;
-                            const int sf = ld_relaxed(&stop[offb + g]);
-                            for (int fa = 0; fa < La; fa++) {
-                                const int4 ag = rm0(t, offa + fa);
-                                const int pa = rm1(t, offa + fa).x;
-                                if (ag.x == i0.x && pa <= ubg && ag.z >= i0.y) { if (sf < 0) unres = true; else if (sf <= pa) vis = true; }
-                            }
-                        }
-                        if (vis) fl |= 4; else if (!unres) fl |= 8;
-                        sPf[grp][j] = (unsigned char)fl;
+            // pass 1: where does the scan first meet each partner (its highest interval inside the closed band); did an
+            // earlier-ranked partner's own query see a first?  cls: 0 not met, 1 seen, 2 reach, 3 reach + edge, 4 undecided
+            int mxReach = -1, mxUn = -1, nEdge = 0;
+            int4 q0[RP_KL];
+            int keyk[RP_KL], sv[RP_KL][4];
+            bool poll[RP_KL];
+#pragma unroll
+            for (int k = 0; k < RP_KL; k++) {                                      // stage A: keys; who needs b's stops?
+                const int j = gl + 8 * k;
+                keyk[k] = -1; poll[k] = false;
+                q0[k] = make_int4(0, 0, 0, 1);
+                if (j < nPart) {
+                    q0[k] = sP0[grp][j];
+                    if (!(q0[k].w & 1)) {
+                        const int4 r1 = sP1[grp][j];
+                        keyk[k] = fi == 0 ? r1.x : fi == 1 ? r1.y : fi == 2 ? r1.z : r1.w;
+                        poll[k] = keyk[k] >= 0 && (q0[k].x & QMASK) < a && !(q0[k].w & 12);
                     }
                 }
-                sKey[grp][j] = key;
-            }
-            __syncwarp(gmask);
-            // pass 2: rank the met partners by position (descending = scan order) and build the reach / edge / undecided masks
-            unsigned long long Rm = 0, Em = 0, Um = 0;
-            for (int j = gl; j < nPart; j += 8) {
-                const int key = sKey[grp][j];
-                if (key < 0) continue;
-                int rank = 0;
-                for (int k = 0; k < nPart; k++) rank += sKey[grp][k] > key;
-                const int fl = sPf[grp][j];
-                const bool later = sPb[grp][j] > a;
-                const unsigned long long bit = 1ull << rank;
-                if (!later && !(fl & 12)) Um |= bit;
-                else if (later || (fl & 8)) { Rm |= bit; if (fl & 2) Em |= bit; }
             }
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-                Rm |= __shfl_xor_sync(gmask, Rm, o); Em |= __shfl_xor_sync(gmask, Em, o); Um |= __shfl_xor_sync(gmask, Um, o);
+            for (int k = 0; k < RP_KL; k++) {                                      // stage B: all the loads, back to back
+                if (poll[k]) {
+                    const int b = q0[k].x & QMASK;
+                    if (sRecTag[grp][b & 31] == b) {                               // replayed by this very group a moment ago
+                        const int4 c = sRecStop[grp][b & 31];
+                        sv[k][0] = c.x; sv[k][1] = c.y; sv[k][2] = c.z; sv[k][3] = c.w;
+                    } else {
+                        const int offb = (int)((unsigned)q0[k].y >> 6), Lb = (q0[k].y & 63) + 1;
+#pragma unroll
+                        for (int g = 0; g < 4; g++)
+                            sv[k][g] = (g < Lb && (((unsigned)q0[k].z >> (4 * g)) & 4u)) ? ld_relaxed(&stop[offb + g]) : 0x7fffffff;
+                    }
+                }
             }
-            const int nres = Um ? __ffsll((long long)Um) - 1 : 64;
-            const unsigned long long rmask = nres >= 64 ? ~0ull : ((1ull << nres) - 1ull);
-            int brk = -1;
-            for (unsigned long long mm = Rm & rmask; mm; mm &= mm - 1) {           // cluster.py:219-224 in scan order
-                const int l = __ffsll((long long)mm) - 1;
-                if (edges + __popcll(Em & ((2ull << l) - 1ull)) >= t.Tedge) { brk = l; break; }
+#pragma unroll
+            for (int k = 0; k < RP_KL; k++) {                                      // stage C: did b's own query see a first?
+                const int j = gl + 8 * k;
+                if (poll[k]) {
+                    bool vis = false, unres = false;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const unsigned cgg = ((unsigned)q0[k].z >> (4 * g)) & 15u;
+                        if (cgg & 4u) {
+                            if (stop_reached(sv[k][g]) <= sA1[grp][cgg & 3u].x) vis = true; else if (sv[k][g] < 0) unres = true;
+                        }
+                    }
+                    if (vis) q0[k].w |= 4; else if (!unres) q0[k].w |= 8;
+                    sP0[grp][j].w = q0[k].w;
+                }
+                if (keyk[k] >= 0) {
+                    if ((q0[k].x & QMASK) > a || (q0[k].w & 8)) { mxReach = max(mxReach, keyk[k]); nEdge += (unsigned)q0[k].x >> 31; }
+                    else if (!(q0[k].w & 4)) mxUn = max(mxUn, keyk[k]);
+                }
+                if (j < nPart) sKey[grp][j] = keyk[k];
             }
-            if (gl == 0) d_steps++;
-            if (brk < 0 && Um) { stalled = true; if (gl == 0) d_stall++; }         // an undecided partner comes first: retry later
+            __syncwarp(gmask);
+            // the break (cluster.py:223-224): the first reached partner, in scan order, at which `edges` is >= edge_threshold
+            const int need = t.Tedge - edges;
+            int brkkey = -1;
+            if (need <= 0) brkkey = gmax8(gmask, mxReach);
             else {
-                const unsigned long long cmask = brk >= 0 ? ((2ull << brk) - 1ull) : ~0ull;
-                const unsigned long long Ec = Em & cmask;
-                const int ne = __popcll(Ec);
-                if (ne && chunk_used + ne > RP_CHUNK) {                            // reserve a fresh chunk, pad the old one (ne <= RP_K <= RP_CHUNK)
-                    for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
-                    if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
-                    chunk_base = __shfl_sync(gmask, chunk_base, gsh);
-                    chunk_used = 0;
-                    if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                nEdge += __shfl_xor_sync(gmask, nEdge, 1); nEdge += __shfl_xor_sync(gmask, nEdge, 2); nEdge += __shfl_xor_sync(gmask, nEdge, 4);
+                if (nEdge >= need) {                                               // the need-th highest edge partner
+                    int thr = 0x7fffffff;
+                    for (int r = 0; r < need; r++) {
+                        int m = -1;
+                        for (int j = gl; j < nPart; j += 8) {
+                            const int key = sKey[grp][j];
+                            if (key >= 0 && key < thr) {
+                                const int4 r0 = sP0[grp][j];
+                                if (r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8))) m = max(m, key);
+                            }
+                        }
+                        thr = gmax8(gmask, m);
+                    }
+                    brkkey = thr;
                 }
-                int stopf = lo;
-                for (int j = gl; j < nPart; j += 8) {
-                    const int key = sKey[grp][j];
-                    if (key < 0) continue;
-                    int rank = 0;
-                    for (int k = 0; k < nPart; k++) rank += sKey[grp][k] > key;
-                    if (!((cmask >> rank) & 1ull)) continue;
-                    sPf[grp][j] |= 1;                                              // a's query has now seen this pair
-                    if ((Ec >> rank) & 1ull) pedges[chunk_base + chunk_used + __popcll(Ec & ((1ull << rank) - 1ull))] = make_int2(a, sPb[grp][j]);
-                    if (rank == brk) stopf = key;
+            }
+            const int unkey = gmax8(gmask, mxUn);
+            if (gl == 0) d_steps++;
+            if (unkey > brkkey) { stalled = true; if (gl == 0) d_stall++; }        // an undecided partner comes first: retry later
+            else {
+                int ne = 0;
+                for (int j0 = 0; j0 < nPart; j0 += 8) {                            // commit: everything met at or above the break
+                    const int j = j0 + gl;
+                    bool emit = false;
+                    if (j < nPart) {
+                        const int key = sKey[grp][j];
+                        if (key >= 0 && key >= brkkey) {
+                            const int4 r0 = sP0[grp][j];
+                            sP0[grp][j].w = r0.w | 1;                              // a's query has now seen this pair
+                            emit = r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8));
+                        }
+                    }
+                    const unsigned em = (__ballot_sync(gmask, emit) >> gsh) & 0xffu;
+                    if (em) {
+                        const int n = __popc(em);
+                        if (chunk_used + n > RP_CHUNK) {                           // reserve a fresh chunk, pad the old one
+                            for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+                            if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                            chunk_base = __shfl_sync(gmask, chunk_base, gsh);
+                            chunk_used = 0;
+                            if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                        }
+                        if (emit) pedges[chunk_base + chunk_used + __popc(em & ((1u << gl) - 1u))] = make_int2(a, sP0[grp][j].x & QMASK);
+                        chunk_used += n;
+                        ne += n;
+                    }
                 }
-                chunk_used += ne;
                 edges += ne;
-                if (brk >= 0) {                                                    // the owner of the break position tells the group
-                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 1));
-                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 2));
-                    stopf = max(stopf, __shfl_xor_sync(gmask, stopf, 4));
-                }
-                if (gl == 0) { sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); }
+                const int stopf = brkkey >= 0 ? brkkey : lo;
+                if (gl == 0) { st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf); ((int *)&sRecStop[grp][a & 31])[fi] = stopf; }
                 fi++;
                 if (fi == La) { tk++; phase = 0; }
             }
@@ -829,10 +925,11 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
         // ------------------------------------------------------------ WALK mode
         else {
         if (phase == 1) {
-            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; }
-            else { f = rm0(t, offa + fi); top = rm1(t, offa + fi).y; }
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; posf = sA1[grp][fi].x; }
+            else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
             lo = __ldg(&t.chrom_lo[f.x]);
             base = top;
+            wide = false;
             phase = 2;
         }
         if (phase == 2) {
@@ -840,15 +937,40 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
             unsigned Ecommit = 0;
             int b = -1;
             if (base < lo || __ldg(&t.pmaxS[base]) < f.y) stopf = lo;              // nothing at or below base overlaps the filling
+            else if (wide) {
+                // ---- nothing to do in the last step: skip ahead over candidates that are no candidates at all or whose read
+                // provably saw a first (its scan of this very interval already passed a's filling), 64 positions per step
+                int adv = 64;
+                int wq[8], we[8], ws[8];                                           // all 16 loads of the step are issued before any use
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int p = base - 8 * k - gl;
+                    wq[k] = -1; we[k] = 0; ws[k] = 0;
+                    if (p >= lo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
+                }
+#pragma unroll
+                for (int k = 7; k >= 0; k--) {
+                    const bool needs = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
+                    const unsigned nm = (__ballot_sync(gmask, needs) >> gsh) & 0xffu;
+                    if (nm) adv = 8 * k + __ffs(nm) - 1;
+                }
+                base -= adv;
+                if (adv < 64) wide = false;
+                if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                d_fsteps++;
+            }
             else {
                 const int p = base - gl;
                 int fl = 0;
+                bool cheap = true;                                                 // nothing in this step needed an evaluation
                 if (p >= lo) {
                     const int4 c0 = __ldg(&t.SR0[p]);
-                    const int4 c1 = __ldg(&t.SR1[p]);
                     b = c0.w & QMASK;
                     if (b != a && c0.y >= f.y                                      // closed overlap (start_p <= end_f by p <= ub)
-                        && difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
+                        && !(b < a && stop_reached(ld_relaxed(&stopS[p])) <= posf)) {   // b's scan of this interval passed a: seen
+                    cheap = false;
+                    const int4 c1 = __ldg(&t.SR1[p]);
+                    if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
                         const int offb = (int)((unsigned)c1.w >> 6), Lb = (c1.w & 63) + 1;
                         if (La <= 4 && Lb <= 4) {
                             // ---- lists in registers, everything unrolled; all loads of this candidate are issued together
@@ -892,7 +1014,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
                                                     const int4 af = fa < La ? sA0[grp][fa] : make_int4(-1, 0, 0, 0);
                                                     const int pa = sA1[grp][fa].x;
                                                     if (af.x == bg[g].x && pa <= bq[g].y && af.z >= bg[g].y) {
-                                                        if (sb[g] < 0) unres = true; else if (sb[g] <= pa) vis = true;
+                                                        if (stop_reached(sb[g]) <= pa) vis = true; else if (sb[g] < 0) unres = true;
                                                     }
                                                 }
                                             }
@@ -907,11 +1029,13 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
                             fl = replay_eval_general(t, stop, sStop[grp], a, offa, La, fi, f, top, p, b, offb, Lb);
                         }
                     }
+                    }
                 }
                 const unsigned U = (__ballot_sync(gmask, fl & RF_UNRES) >> gsh) & 0xffu;
                 const unsigned M = (__ballot_sync(gmask, fl & RF_REACH) >> gsh) & 0xffu;
                 const unsigned E = (__ballot_sync(gmask, fl & RF_EDGE) >> gsh) & 0xffu;
                 const unsigned Tm = (__ballot_sync(gmask, fl & RF_TESTED) >> gsh) & 0xffu;
+                wide = __all_sync(gmask, cheap);
                 const int nres = U ? __ffs(U) - 1 : 8;                             // candidates before the first undecided one
                 const unsigned rmask = (1u << nres) - 1u;
                 int brk = -1;
@@ -924,9 +1048,19 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
                 if (gl == 0) tests += __popc(Tm & cmask);
                 edges += __popc(Ecommit);
                 if (brk >= 0) stopf = base - brk;
-                else { base -= nres; stalled = nres == 0; }
+                else {
+                    base -= nres; stalled = nres == 0;
+                    if (gl == 0 && nres) { st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                }
                 if (gl == 0) { d_steps++; d_stall += stalled; }
                 d_fsteps++; d_fstall += stalled;
+                if (dbg && stalled && d_fstall == 5000 && (U & 1u) && gl == 0) {   // lane 0 is the undecided candidate
+                    if (atomicAdd(dbg + 12, 1ull) == 0) {
+                        const int wb2 = __ldg(&t.SR1[base]).w; const int ob = (int)((unsigned)wb2 >> 6);
+                        dbg[13] = a; dbg[14] = b; dbg[15] = (unsigned)ld_relaxed(&stop[ob]); dbg[16] = (unsigned)ld_relaxed(&stop[ob + 1]);
+                        dbg[17] = base; dbg[18] = top; dbg[19] = posf; dbg[20] = rm1(t, ob).x; dbg[21] = rm1(t, ob + 1).x; dbg[22] = sA1[grp][1].x; dbg[23] = fi;
+                    }
+                }
             }
             if (Ecommit) {
                 const int ne = __popc(Ecommit);
@@ -941,7 +1075,10 @@ __global__ void __launch_bounds__(RG_WARPS * 32) k_replay(Tab t, int nP, const i
                 chunk_used += ne;
             }
             if (stopf >= 0) {                                                      // publish the stop; next filling / read
-                if (gl == 0) { sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); }
+                if (gl == 0) {
+                    sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf);
+                    if (La <= 4) ((int *)&sRecStop[grp][a & 31])[fi] = stopf;
+                }
                 if (dbg && gl == 0 && d_fsteps > 2000) {
                     if (atomicMax(dbg + 4, (unsigned long long)d_fsteps) < (unsigned long long)d_fsteps) {
                         dbg[5] = a; dbg[6] = fi; dbg[7] = top - lo; dbg[8] = d_fstall; dbg[9] = top - stopf; dbg[10] = edges; dbg[11] = La;
@@ -1090,9 +1227,10 @@ struct Pipe {
     int *q_of_rid, *rid_of_q;
     int4 *SR0, *SR1, *RM, *RI;
     int *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
-    int *isP, *plist, *stop;
+    int *isP, *plist, *stop, *stopS;
     int2 *entries, *pedges;
-    unsigned long long cap_entries, cap_pedges;
+    int4 *PL; PLInfo *plinfo;
+    unsigned long long cap_entries, cap_pedges, cap_pl;
     int *parent, *ing;
     unsigned *ticket;
     void *cub_tmp; size_t cub_bytes;
@@ -1133,13 +1271,13 @@ static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const K *kin, K *kout, const int 
     return 0;
 }
 static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
-    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 32 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_pin + 32, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 48 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + 48, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 static int err_code(fslrc_ctx *ctx) {
-    int e = (int)(ctx->h_pin[32] & 0xffffffff);
+    int e = (int)(ctx->h_pin[48] & 0xffffffff);
     if (!e) return 0;
     if (e & EF_RANGE) return fail(ctx, FSLRC_ERR_RANGE, "a table value is out of range (read_id/chrom id, negative coordinate, n_alignments >= 65535 or a bad `order`)");
     if (e & EF_ZERO) return fail(ctx, FSLRC_ERR_ZERO_DIVISOR, "aln_size, qlen2 or n_alignments <= 0 on a filling (the reference raises ZeroDivisionError)");
@@ -1159,9 +1297,9 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
     cudaStream_t st = ctx->stream;
     const int A = P->A, R = P->R, TB = 256;
-    DA(P->err, 1); DA(P->cnt, 32);
+    DA(P->err, 1); DA(P->cnt, 48);
     CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(P->cnt, 0, 32 * sizeof(int64_t), st));
+    CK(cudaMemsetAsync(P->cnt, 0, 48 * sizeof(int64_t), st));
     CK(cudaMemcpyToSymbolAsync(c_umax, pr.umax, sizeof(int) * (LMAX + 1), 0, cudaMemcpyHostToDevice, st));
     long long *d_clen; unsigned char *d_cmask;
     DA(d_clen, pr.n_chrom); DA(d_cmask, pr.n_chrom);
@@ -1283,23 +1421,30 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     P->pair_blocks = std::max(1, std::min(nblk(Q, PK_GROUPS), n_sms(ctx) * 8));
     P->cap_entries = std::min<unsigned long long>(capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks + 64;
     DA(P->entries, P->cap_entries);
-    DA(P->isP, Q); DA(P->stop, D); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
+    // partner records of saturating reads (replay LIST mode): at most RP_K per read and never more than tight-band hits
+    P->cap_pl = std::min<unsigned long long>((unsigned long long)Q * RP_K, tight) + (unsigned long long)PL_CHUNK * PK_WARPS * P->pair_blocks * 2 + 64;
+    DA(P->PL, 2 * P->cap_pl); DA(P->plinfo, Q);
+    DA(P->isP, Q); DA(P->stop, D); DA(P->stopS, D); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
     if (Q > 0) CK(cudaMemsetAsync(P->isP, 0, sizeof(int) * Q, st));
     return mark(ctx, 5);
 }
 
 
 // ---- stage 6: pair kernel on one shard
-static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
+static int launch_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, int lists_only) {
     cudaStream_t st = ctx->stream;
-    if (P->Q > 0) {
-        if (P->pr.overlap > 0.0)
-            KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
-               P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
-        else
-            KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
-               P->cap_entries, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
-    }
+    if (P->pr.overlap > 0.0)
+        KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+           P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
+           (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
+    else
+        KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+           P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
+           (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
+    return 0;
+}
+static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
+    if (P->Q > 0) { int r = launch_pair(ctx, P, shard, nshard, 0); if (r) return r; }
     return mark(ctx, 6);
 }
 
@@ -1309,6 +1454,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     const int Q = P->Q, D = P->D, TB = 256;
     int *posQ;
     DA(posQ, Q);
+    if (Q > 0 && nshard > 1) { int r = launch_pair(ctx, P, shard, nshard, 1); if (r) return r; }
     if (Q > 0) {
         int r = xscan(ctx, P, P->isP, posQ, Q); if (r) return r;
         KL(k_total, 1, 1, posQ, P->isP, Q, P->cnt + 6);
@@ -1318,7 +1464,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     DA(P->plist, nP);
     if (Q > 0) KL(k_compact_flagged, nblk(Q, TB), TB, Q, P->isP, posQ, P->plist);
     // stops: a read that never breaks walks every filling's scan to the chromosome start (0 <= any position)
-    if (D > 0) CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st));
+    if (D > 0) { CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st)); CK(cudaMemsetAsync(P->stopS, 0, sizeof(int) * D, st)); }
     CK(cudaMemsetAsync(P->ticket, 0, sizeof(unsigned), st));
     { int r = mark(ctx, 7); if (r) return r; }
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
@@ -1328,20 +1474,24 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * RG_GROUPS * (replay_blocks_max + 1);
     DA(P->pedges, P->cap_pedges);
     if (nP > 0) {
-        int *rflag, *rpos, *rstart;
-        DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
-        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, rflag, P->stop);
-        int r = xscan(ctx, P, rflag, rpos, nP); if (r) return r;
+        int *sflag, *spos, *sstart, *rflag, *rpos, *rstart;
+        DA(sflag, nP); DA(spos, nP); DA(sstart, nP); DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
+        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, sflag, P->stop, P->stopS);
+        int r = xscan(ctx, P, sflag, spos, nP); if (r) return r;
+        KL(k_total, 1, 1, spos, sflag, nP, P->cnt + 15);
+        KL(k_compact_flagged, nblk(nP, TB), TB, nP, sflag, spos, sstart);
+        KL(k_run_cut, nblk(nP, TB), TB, nP, sflag, spos, sstart, P->cnt + 15, rflag);
+        r = xscan(ctx, P, rflag, rpos, nP); if (r) return r;
         KL(k_total, 1, 1, rpos, rflag, nP, P->cnt + 12);
         KL(k_compact_flagged, nblk(nP, TB), TB, nP, rflag, rpos, rstart);
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
         if (P->pr.overlap > 0.0)
-            KL(k_replay<false>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->ticket, P->pedges,
+            KL(k_replay<false>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges,
                (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
         else
-            KL(k_replay<true>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->stop, P->ticket, P->pedges,
+            KL(k_replay<true>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges,
                (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
     }
     { int r = mark(ctx, 8); if (r) return r; }
@@ -1391,6 +1541,8 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->no_clusters = h[9] == 0;
     if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld\n",
                                        (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12]);
+    if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] long stall: a %lld waits b %lld stops %d %d base %lld top %lld posf %lld bpos %lld %lld apos2 %lld fi %lld (n=%lld)\n",
+                                       (long long)h[29], (long long)h[30], (int)h[31], (int)h[32], (long long)h[33], (long long)h[34], (long long)h[35], (long long)h[36], (long long)h[37], (long long)h[38], (long long)h[39], (long long)h[28]);
     if (getenv("FSLRC_DEBUG") && h[20]) fprintf(stderr, "[fslrc] longest walk: %lld steps (stalled %lld) read %lld filling %lld/%lld band %lld walked %lld edges %lld\n",
                                        (long long)h[20], (long long)h[24], (long long)h[21], (long long)h[22], (long long)h[27], (long long)h[23], (long long)h[25], (long long)h[26]);
     for (int i = 0; i < FSLRC_N_STAGES; i++) {
