@@ -256,6 +256,46 @@ __global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const i
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = ((unsigned long long)(unsigned)it.y << 32) | (unsigned)it.z; }
 }
+// IntervalMap order without sorting by start again: data order is already sorted by start, so a STABLE partition by
+// chromosome yields (chrom, start, data order); what is missing is "end descending" inside runs of equal (chrom, start).
+// Those runs are short (PCR duplicates), and in data order their members sit in one block of equal starts: every item
+// counts, with coalesced neighbour reads, how many members of its run precede it in data order (idx) and how many must
+// precede it in the final order (rank: larger end, or equal end and earlier in data order).  The partition moves the run
+// as a block, so the item's final position is its partition position + (rank - idx).  val[d] = d | (rank - idx + 32) << 26.
+// Runs that do not fit the window raise `overflow` and the caller falls back to the two full radix sorts.
+#define TIE_WIN 48
+__global__ void k_tie_delta(int D, const int4 *__restrict__ IT0, unsigned *ckey, unsigned *val, unsigned long long *overflow, int *err) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int4 me = IT0[d];
+    if (d > 0 && IT0[d - 1].z > me.z) atomicOr(err, EF_RANGE);       // a caller-supplied `order` that does not sort by start
+    int idx = 0, rank = 0;
+    bool ovf = false;
+    for (int k = 1;; k++) {                                          // earlier in data order
+        if (d - k < 0) break;
+        const int4 o = IT0[d - k];
+        if (o.z != me.z) break;
+        if (k > TIE_WIN) { ovf = true; break; }
+        if (o.y == me.y) { idx++; rank += o.w >= me.w; }
+    }
+    for (int k = 1;; k++) {                                          // later in data order
+        if (d + k >= D) break;
+        const int4 o = IT0[d + k];
+        if (o.z != me.z) break;
+        if (k > TIE_WIN) { ovf = true; break; }
+        if (o.y == me.y) rank += o.w > me.w;
+    }
+    if (idx > 31 || rank > 31) ovf = true;
+    if (ovf) { atomicAdd(overflow, 1ull); rank = idx; }
+    ckey[d] = (unsigned)me.y;
+    val[d] = (unsigned)d | ((unsigned)(rank - idx + 32) << 26);
+}
+__global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const unsigned v = val[p];
+    s_dp[p + (int)(v >> 26) - 32] = (int)(v & 0x3ffffffu);
+}
 // SR0[p] = {start, end, T, q | fi << 26} (fi = index of the filling in its read's list); SR1[p] = the read's RI record;
 // RM[2m] = {chrom, start, end, T}, RM[2m+1] = {pos, ub (closed band, replay), lbT, ubT (tight band, pair kernel)}: one
 // 32-byte sector per filling in read-major order, written once by k_bands
@@ -1354,7 +1394,12 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     int4 *IT0; int2 *IT1; int *firstdp;
     DA(IT0, D); DA(IT1, D); DA(firstdp, R);
     if (R > 0) KL(k_fill<int>, nblk(R, TB), TB, firstdp, R, 0x7fffffff);
+    unsigned *tkey = nullptr, *tkey2 = nullptr, *tval = nullptr, *tval2 = nullptr;
     if (D > 0) KL(k_build_items, nblk(D, TB), TB, D, dfill, FR0, FR1, IT0, IT1, firstdp, P->err);
+    if (D > 0 && D < (1 << 26)) {
+        DA(tkey, D); DA(tkey2, D); DA(tval, D); DA(tval2, D);
+        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
+    }
     { int r = mark(ctx, 2); if (r) return r; }
     // ---- stage 3: query rank + per-read lists
     int *flagD, *posD, *it_q;
@@ -1381,9 +1426,14 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     }
     { int r = mark(ctx, 3); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
-    unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1, *s_dp;
-    DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D); DA(s_dp, D);
-    if (D > 0) {
+    int *s_dp; DA(s_dp, D);
+    const bool tie_ok = tkey && ctx->h_pin[41] == 0;                 // (read back with the stage-3 counters)
+    if (D > 0 && tie_ok) {                                           // one stable partition by chromosome + local tie fix
+        int r = sort_pairs<unsigned>(ctx, P, tkey, tkey2, (const int *)tval, (int *)tval2, D, 0, bits_for(pr.n_chrom)); if (r) return r;
+        KL(k_apply_delta, nblk(D, TB), TB, D, tval2, s_dp);
+    } else if (D > 0) {                                              // long runs of equal (chrom, start): two full radix sorts
+        unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1;
+        DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D);
         KL(k_end_keys, nblk(D, TB), TB, D, IT0, ek);
         int r = sort_pairs<unsigned>(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
         KL(k_chrom_start_keys, nblk(D, TB), TB, D, v1, IT0, ck);
