@@ -68,7 +68,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -174,11 +174,12 @@ def main():
 
     def step_e2e():
         if world > 1:
-            for k, t in ptab.cols.items():
-                dtab.cols[k].copy_(t[:A], non_blocking=True)
+            # every rank uploads 1/world of the rows over its own PCIe link; NVLink all-gather rebuilds the columns
+            eng.upload_sharded(ptab, dtab, rank, world)
             st = eng.run_sharded(dtab, ct, params, rank, world)
-            ptab.out_cluster[:R].copy_(dtab.out_cluster[:R], non_blocking=True)
-            ptab.out_n_reads[:R].copy_(dtab.out_n_reads[:R], non_blocking=True)
+            if rank == 0:                                     # the job's result leaves the box once
+                ptab.out_cluster[:R].copy_(dtab.out_cluster[:R], non_blocking=True)
+                ptab.out_n_reads[:R].copy_(dtab.out_n_reads[:R], non_blocking=True)
             torch.cuda.synchronize()
             return st
         return eng.run_host(ptab, ct, params)
@@ -215,34 +216,52 @@ def main():
     e2e = R * args.steps / (ms_e2e * 1e-3)
     peak, peak_kind = load_peaks()
     F, D, Q = st["n_fillings"], st["n_intervals"], st["n_query_reads"]
-    # algorithmic HBM bytes per stage (DESIGN.md §5): what one pass over the stage's data must move at least once
+    # algorithmic HBM bytes per stage (DESIGN.md §4): what one pass over the stage's data must move at least once
+    E, NP = st["relation_entries"], st["partner_records"]
     alg_bytes = {
         "keep_fillings": 12 * A + 8 * ct.n_reads + 4 * F,
         "data_order_mask": 2 * 8 * F + 16 * F + 24 * D,
         "query_rank_read_lists": 2 * 8 * D + 8 * D + 32 * Q,
-        "chrom_sort": 2 * 8 * D + 2 * 12 * D,
+        "chrom_sort": 2 * 8 * D,
         "records_bands": 28 * D + 80 * D,
-        "pair_kernel": 32 * D + 16 * D + 8 * st["relation_entries"],
-        "replay": 64 * st["saturating_reads"],
-        "union_find": 8 * st["relation_entries"] + 8 * Q,
+        "pair_kernel": 16 * D + 32 * D + 16 * Q + 8 * E + 32 * NP,
+        "replay": 32 * NP + 16 * st["saturating_reads"] + 8 * st["edges"],
+        "union_find": 8 * E + 8 * Q,
         "numbering": 12 * Q + 16 * ct.n_reads,
     }
     top = max((k for k in alg_bytes), key=lambda k: stage_ms[k])
     ach = alg_bytes[top] / (stage_ms[top] * 1e-3) / 1e9 if stage_ms[top] > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram__bytes_read+write per launch from the committed ncu capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.config, {}).get(top)
     roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes[top],
-                "ms_per_launch": stage_ms[top]}
+                "traffic": traffic, "peak_source": peak_kind, "algorithmic_bytes_per_launch": alg_bytes[top],
+                "ms_per_launch": stage_ms[top],
+                "note": "the pair kernel is instruction-issue bound (see int_issue), every other stage HBM bound"}
+    # integer-issue view of the pair kernel: 12 + 7*L1*L2 lane-ops per evaluated read pair against the
+    # measured dependent-free IADD/LOP/VIMNMX rate of this device
+    int_issue = None
+    if rank == 0 and stage_ms["pair_kernel"] > 0:
+        ipeak = eng.int_peak()
+        Lbar = D / max(Q, 1)
+        ops = st["pair_tests"] * (12 + 7 * Lbar * Lbar)
+        int_issue = {"kernel": "k_pair", "achieved_lane_ops_per_s": ops / (stage_ms["pair_kernel"] * 1e-3), "peak_lane_ops_per_s": ipeak,
+                     "frac": ops / (stage_ms["pair_kernel"] * 1e-3) / ipeak, "ops_per_pair_test": 12 + 7 * Lbar * Lbar,
+                     "peak_source": "measured in this run (fslrc_int_peak: 8 independent add/minmax/xor chains per thread)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.config, WORKLOADS[args.config]) + ("" if args.scale == 1.0 else " x%g" % args.scale),
                        "reads": R, "table_rows": A, "fillings": F, "intervals": D,
                        "l2": "inputs larger than L2 (%.2f GB of columns re-read every step)" % (32 * A / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else "table replicated, pair space sharded over %d GPUs, all-reduce + all-gather" % world},
+                       "parallelism": "1 GPU" if world == 1 else "table replicated (e2e: upload sharded, NVLink all-gather), pair space sharded by "
+                                                                  "query read over %d GPUs, all-reduce + all-gather of forests" % world},
             "pair_tests_per_s": st["pair_tests"] / (stage_ms["pair_kernel"] + stage_ms["replay"]) * 1e3 if stage_ms["pair_kernel"] > 0 else None,
             "pair_tests": st["pair_tests"], "band_pairs": st["band_pairs"], "edges": st["edges"], "clusters": st["components"],
             "saturating_reads": st["saturating_reads"],
-            "stage_ms": stage_ms, "roofline": roofline, "clocks": clocks,
+            "partner_records": st["partner_records"],
+            "stage_ms": stage_ms, "roofline": roofline, "int_issue": int_issue, "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": ptab.h2d_bytes,
                     "d2h_bytes_per_step": ptab.d2h_bytes},
             "gpu_launches": launches}

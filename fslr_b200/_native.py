@@ -32,11 +32,12 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_fillings", "n_intervals", "n_query_reads", "band_pairs", "pair_tests",
-                                          "relation_entries", "saturating_reads", "edges", "components", "clustered_reads")] + \
+                                          "relation_entries", "saturating_reads", "edges", "components", "clustered_reads",
+                                          "partner_records")] + \
                [("no_clusters", C.c_int32), ("reserved", C.c_int32), ("stage_ms", C.c_float * N_STAGES)]
 
     def as_dict(self, lib=None):
-        d = {n: int(getattr(self, n)) for n, _ in self._fields_[:10]}
+        d = {n: int(getattr(self, n)) for n, _ in self._fields_[:11]}
         d["no_clusters"] = int(self.no_clusters)
         names = [lib.fslrc_stage_name(i).decode() for i in range(N_STAGES)] if lib is not None else list(range(N_STAGES))
         d["stage_ms"] = {names[i]: float(self.stage_ms[i]) for i in range(N_STAGES)}

@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
             for (int gg = 0; gg < 3; gg++) { const int x = __shfl_sync(FULL, nrec, gg * 8); if (gg < g) before += x; }
             const unsigned long long my0 = pl_base + pl_used + before;
             pl_used += tot;
+            if (lane == 0) atomicAdd(pl_slots + 2, (unsigned long long)tot);          // (statistics: records written)
             for (int j = gl; j < nrec; j += 8) {
                 const int2 pr = sPart[grp][j];
                 const int offb = (int)((unsigned)pr.y >> 6), Lb = (pr.y & 63) + 1;
@@ -1588,6 +1589,7 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->n_fillings = P->F; s->n_intervals = P->D; s->n_query_reads = P->Q;
     s->band_pairs = h[3]; s->pair_tests = h[4]; s->relation_entries = h[13]; s->saturating_reads = P->nP;
     s->edges = h[8]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
+    s->partner_records = h[42];
     s->no_clusters = h[9] == 0;
     if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld\n",
                                        (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12]);

@@ -202,6 +202,13 @@ class Engine:
                                              C.byref(st)))
         return st.as_dict(self.lib)
 
+    def upload_sharded(self, ptab: PinnedTable, dtab: DeviceTable, rank, world, group=None):
+        """Multi-GPU ingest of HOST columns: every rank copies only its 1/world slice of the rows over its own PCIe link and
+        the slices are all-gathered over NVLink (fslr_b200.sharded.gather_columns), so the host->device time shrinks with
+        the number of GPUs instead of being paid in full by every rank."""
+        from .sharded import gather_columns
+        gather_columns({k: ptab.cols[k] for k in _COLS}, dtab.cols, dtab.n_rows, rank, world, group)
+
     def launch_count(self):
         return int(self.lib.fslrc_launch_count(self.ctx))
 

@@ -1,7 +1,8 @@
 """Exchange steps of the multi-GPU path, written against torch.distributed only so the same code
 runs over NCCL/NVLink on the GPUs and over gloo in the CPU tests.
 
-The interval table is replicated; the pair space is sharded.  Two exchanges exist:
+The interval table is replicated; the pair space is sharded by query read.  With host inputs the upload is sharded too
+(gather_columns).  Two exchanges exist on the data path:
   1. sum-all-reduce of the per-read passing-candidate counts (decides which reads are saturating);
   2. all-gather of every rank's spanning forest (<= n_query_reads - 1 edges each), then one final union-find.
 """
@@ -37,6 +38,31 @@ def exchange_forests(local_edges, group=None):
     return torch.cat(parts).contiguous(), [s // 2 for s in sizes_h]
 
 
-def shard_of_position(i, world):
-    """Rank owning sorted interval position i: tiles of 256 consecutive positions, round robin (k_pair)."""
-    return (i >> 8) % world
+def row_slice(n_rows, rank, world):
+    """Rows [lo, hi) of the table that rank `rank` uploads; chunks are equal (the last one is padded in the exchange)."""
+    chunk = (n_rows + world - 1) // world
+    lo = min(rank * chunk, n_rows)
+    return lo, min(lo + chunk, n_rows), chunk
+
+
+def gather_columns(host_cols, dev_cols, n_rows, rank, world, group=None):
+    """host_cols: name -> host tensor [>= n_rows] (pinned for the GPU path); dev_cols: name -> tensor [>= n_rows] on this
+    rank's device (CPU tensors under gloo).  Each rank moves rows row_slice(rank) of every column to its device and one
+    all-gather per column gives every rank the whole column."""
+    lo, hi, chunk = row_slice(n_rows, rank, world)
+    for k, dst in dev_cols.items():
+        src = host_cols[k]
+        if world == 1 or not dist.is_initialized():
+            dst[:n_rows].copy_(src[:n_rows], non_blocking=True)
+            continue
+        mine = torch.zeros(chunk, dtype=dst.dtype, device=dst.device)
+        if hi > lo:
+            mine[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+        full = torch.empty(chunk * world, dtype=dst.dtype, device=dst.device)
+        dist.all_gather_into_tensor(full, mine, group=group)
+        dst[:n_rows].copy_(full[:n_rows])
+
+
+def shard_of_read(q, world):
+    """Rank owning query read q (query rank): groups of 256 consecutive query ranks, round robin (k_pair)."""
+    return (q >> 8) % world

@@ -87,6 +87,7 @@ typedef struct {
     int64_t edges;                 /* edges handed to union-find */
     int64_t components;            /* clusters with >= 2 reads */
     int64_t clustered_reads;       /* reads in those clusters */
+    int64_t partner_records;       /* partner records the pair kernel left for the replay of saturating reads */
     int32_t no_clusters;           /* main.py:247-249: the reference prints "No clusters were found." and returns */
     int32_t reserved;
     float stage_ms[FSLRC_N_STAGES];/* CUDA-event time per stage, see fslrc_stage_name() */

@@ -1,5 +1,5 @@
 """world_size-2 gloo test (CPU) of the multi-GPU exchange logic: each rank evaluates the pair relation for its shard of
-sorted interval positions (tests/proto_model.py stands in for the device kernels), counts are sum-all-reduced,
+query reads (tests/proto_model.py stands in for the device kernels), counts are sum-all-reduced,
 local spanning forests are all-gathered, and the merged components must equal the oracle's clusters."""
 import os
 import sys
@@ -19,13 +19,19 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fslr_b200 import synth
-    from fslr_b200.sharded import exchange_counts, exchange_forests, shard_of_position
+    from fslr_b200.sharded import exchange_counts, exchange_forests, gather_columns, shard_of_read
     from fslr_b200.table import ClusterParams, ColumnarTable
     from tests.proto_model import Model
     t = ColumnarTable.from_synth(synth.make_config("C1", 0.12))
     p = ClusterParams.from_options(t, edge_threshold=3)
     m = Model(t, p)
-    # ---- sharded phase A: this rank evaluates only the (a, b) pairs whose canonical interval of `a` it owns
+    # ---- sharded upload: each rank holds 1/world of the rows, all-gather rebuilds the columns (Engine.upload_sharded)
+    host = {"rstart": torch.from_numpy(t.rstart.copy()), "read_id": torch.from_numpy(t.read_id.copy())}
+    devc = {k: torch.zeros(t.n_rows + 3, dtype=v.dtype) for k, v in host.items()}
+    gather_columns(host, devc, t.n_rows, rank, world)
+    for k in host:
+        assert torch.equal(devc[k][:t.n_rows], host[k])
+    # ---- sharded phase A: this rank evaluates only the (a, b) pairs of the query reads `a` it owns
     m.degub = np.zeros(m.Q, np.int64)
     m.later, m.cond = [], []
     for a in range(m.Q):
@@ -36,7 +42,7 @@ def _worker(rank, world, port, out):
                 if b == a or b in done:
                     continue
                 done.add(b)
-                if shard_of_position(int(m.pos[f]), world) != rank:
+                if shard_of_read(a, world) != rank:
                     continue
                 if m.passes(a, b)[1]:
                     m.degub[a] += 1
