@@ -23,7 +23,7 @@
 // from the order-free relation.  The remaining reads are replayed in query order by a persistent ticket kernel in
 // which a warp only ever waits for reads holding smaller tickets.
 #include <cuda_runtime.h>
-#include <cub/cub.cuh>
+#include "prims.cuh"
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -104,9 +104,6 @@ __global__ void k_fill(T *p, int64_t n, T v) {
 __global__ void k_iota(int *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
-}
-__global__ void k_total(const int *scan, const int *flag, int n, int64_t *out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) *out = n > 0 ? (int64_t)scan[n - 1] + flag[n - 1] : 0;
 }
 
 // exact threshold in the reference's double arithmetic: min{o >= 0 : fl(o/a) >= p}  (cluster.py:133-136,179,181)
@@ -252,9 +249,9 @@ __global__ void k_end_keys(int D, const int4 *__restrict__ IT0, unsigned *key) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d < D) key[d] = ~(unsigned)IT0[d].w;                        // ascending ~end == end descending
 }
-__global__ void k_chrom_start_keys(int D, const int *__restrict__ dp_in, const int4 *__restrict__ IT0, unsigned long long *key) {
+__global__ void k_gather_key(int D, const int *__restrict__ dp_in, const int4 *__restrict__ IT0, int which, unsigned *key) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = ((unsigned long long)(unsigned)it.y << 32) | (unsigned)it.z; }
+    if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = (unsigned)(which ? it.y : it.z); }      // start / chromosome of the item
 }
 // IntervalMap order without sorting by start again: data order is already sorted by start, so a STABLE partition by
 // chromosome yields (chrom, start, data order); what is missing is "end descending" inside runs of equal (chrom, start).
@@ -357,14 +354,18 @@ __global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restri
         mine = lo - p;
         mineT = tl - lb;
     }
-    typedef cub::BlockReduce<long long, 256> BR;
-    __shared__ typename BR::TempStorage tmp;
-    long long s = BR(tmp).Sum(mine);
+    __shared__ long long s_sum[2][8];                                 // one pair of global atomics per block
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { mine += __shfl_down_sync(0xffffffffu, mine, o); mineT += __shfl_down_sync(0xffffffffu, mineT, o); }
+    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = mine; s_sum[1][threadIdx.x >> 5] = mineT; }
     __syncthreads();
-    long long s2 = BR(tmp).Sum(mineT);
-    if (threadIdx.x == 0) { if (s) atomicAdd(band_pairs, (unsigned long long)s); if (s2) atomicAdd(tight_pairs, (unsigned long long)s2); }
+    if (threadIdx.x == 0) {
+        long long a = 0, b = 0;
+        for (int w = 0; w < 8; w++) { a += s_sum[0][w]; b += s_sum[1][w]; }
+        if (a) atomicAdd(band_pairs, (unsigned long long)a);
+        if (b) atomicAdd(tight_pairs, (unsigned long long)b);
+    }
 }
-struct MaxOp { __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; } };
 
 // ---------------------------------------------------------------- pair-level pieces
 struct Tab {                 // kernel-side view of the tables
@@ -1274,7 +1275,7 @@ struct Pipe {
     unsigned long long cap_entries, cap_pedges, cap_pl;
     int *parent, *ing;
     unsigned *ticket;
-    void *cub_tmp; size_t cub_bytes;
+    unsigned char *prim; size_t prim_bytes;   // scratch of the device-wide primitives
     int stage;               // next event index
     Tab tab;
 };
@@ -1283,32 +1284,65 @@ static int mark(fslrc_ctx *ctx, int stage_end) {   // record the event closing `
     CK(cudaEventRecord(ctx->ev[stage_end + 1], ctx->stream));
     return 0;
 }
-static int cub_tmp(fslrc_ctx *ctx, Pipe *P, size_t bytes) {
-    if (bytes > P->cub_bytes) {
-        void *q; size_t nb = bytes + (bytes >> 2) + 256;
+static int n_sms(fslrc_ctx *ctx) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
+    return n;
+}
+// ---- device-wide primitives (prims.cuh): look-back status words + ticket live in one reusable scratch region
+static int prim_scratch(fslrc_ctx *ctx, Pipe *P, size_t status_bytes) {
+    const size_t need = status_bytes + 256;
+    if (need > P->prim_bytes) {
+        void *q; const size_t nb = need + (need >> 1);
         CK(cudaMallocAsync(&q, nb, ctx->stream));
         ctx->allocs.push_back(q);
-        P->cub_tmp = q; P->cub_bytes = nb;
+        P->prim = (unsigned char *)q; P->prim_bytes = nb;
     }
+    CK(cudaMemsetAsync(P->prim, 0, need, ctx->stream));          // ticket (first 256 bytes) + status words
     return 0;
 }
-static int xscan(fslrc_ctx *ctx, Pipe *P, const int *in, int *out, int n) {
-    if (n <= 0) return 0;
-    size_t b = 0;
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, b, in, out, n, ctx->stream));
-    int r = cub_tmp(ctx, P, b); if (r) return r;
-    b = P->cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(P->cub_tmp, b, in, out, n, ctx->stream));
+// exclusive sum of int32; *total (device, optional) receives the grand total
+static int xscan(fslrc_ctx *ctx, Pipe *P, const int *in, int *out, int n, int64_t *total = nullptr) {
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) { if (total) CK(cudaMemsetAsync(total, 0, sizeof(int64_t), st)); return 0; }
+    const int tiles = nblk(n, prims::SC_TILE);
+    int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
+    KL(prims::k_scan_excl_i32, tiles, prims::SC_THREADS, in, out, n, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim, (long long *)total);
     return 0;
 }
-template <typename K>
-static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const K *kin, K *kout, const int *vin, int *vout, int n, int b0, int b1) {
+// per-segment inclusive prefix max (seg non-decreasing)
+static int segmax_scan(fslrc_ctx *ctx, Pipe *P, const int *seg, const int *val, int *out, int n) {
+    cudaStream_t st = ctx->stream;
     if (n <= 0) return 0;
-    size_t b = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, b, kin, kout, vin, vout, n, b0, b1, ctx->stream));
-    int r = cub_tmp(ctx, P, b); if (r) return r;
-    b = P->cub_bytes;
-    CK(cub::DeviceRadixSort::SortPairs(P->cub_tmp, b, kin, kout, vin, vout, n, b0, b1, ctx->stream));
+    const int tiles = nblk(n, prims::SC_TILE);
+    int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
+    KL(prims::k_scan_segmax, tiles, prims::SC_THREADS, seg, val, out, n, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim);
+    return 0;
+}
+// stable LSD radix sort of (key, value) pairs on key bits [b0, b1); the inputs are left untouched
+static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const unsigned *kin, unsigned *kout, const int *vin, int *vout, int n, int b0, int b1) {
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) return 0;
+    const int npass = std::max(1, (b1 - b0 + 7) / 8);
+    if (npass > 4) return fail(ctx, FSLRC_ERR_ARG, "radix sort: more than 32 key bits");
+    unsigned *hist; DA(hist, 4 * 256);
+    CK(cudaMemsetAsync(hist, 0, sizeof(unsigned) * 4 * 256, st));
+    unsigned *tk = nullptr; int *tv = nullptr;
+    if (npass > 1) { DA(tk, n); DA(tv, n); }
+    KL(prims::k_rs_hist, std::min(nblk(n, 256 * 16), n_sms(ctx) * 8), 256, kin, n, b0, b1, npass, hist);
+    KL(prims::k_rs_scan, npass, 256, hist);
+    const int tiles = nblk(n, prims::RS_TILE);
+    const unsigned *ks = kin; const int *vs = vin;
+    for (int p = 0; p < npass; p++) {
+        unsigned *kd = ((npass - 1 - p) % 2 == 0) ? kout : tk;       // the last pass lands in (kout, vout)
+        int *vd = ((npass - 1 - p) % 2 == 0) ? vout : tv;
+        int r = prim_scratch(ctx, P, sizeof(unsigned) * 256 * (size_t)tiles); if (r) return r;
+        const int nbits = std::min(8, b1 - b0 - 8 * p);
+        ctx->launches++;
+        prims::k_rs_onesweep<<<tiles, prims::RS_THREADS, sizeof(prims::RsSmem), st>>>(ks, kd, vs, vd, n, b0 + 8 * p, (1 << nbits) - 1, hist + 256 * p,
+                                                                                      (unsigned *)(P->prim + 256), (unsigned *)P->prim);
+        ks = kd; vs = vd;
+    }
     return 0;
 }
 static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
@@ -1325,11 +1359,6 @@ static int err_code(fslrc_ctx *ctx) {
     if (e & EF_TOOMANY) return fail(ctx, FSLRC_ERR_TOO_MANY_FILLINGS, "a read has more than 64 fillings");
     if (e & EF_NALN) return fail(ctx, FSLRC_ERR_NALN_NOT_CONSTANT, "n_alignments is not constant over the rows of a read");
     return fail(ctx, FSLRC_ERR_OVERFLOW, "internal edge buffer overflow");
-}
-static int n_sms(fslrc_ctx *ctx) {
-    int n = 148;
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
-    return n;
 }
 static int bits_for(int64_t n) { int b = 1; while ((1ll << b) < n && b < 32) b++; return b; }
 
@@ -1362,8 +1391,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (A > 0) {
         KL(k_first_last, nblk(A, TB), TB, A, R, tb.read_id, first, last, P->err);
         KL(k_keep, nblk(A, TB), TB, A, R, tb.read_id, first, last, tb.qstart, tb.qend, flagA, qmin, qmax);
-        int r = xscan(ctx, P, flagA, posA, A); if (r) return r;
-        KL(k_total, 1, 1, posA, flagA, A, P->cnt + 0);
+        int r = xscan(ctx, P, flagA, posA, A, P->cnt + 0); if (r) return r;
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int F = P->F = (int)ctx->h_pin[0];
@@ -1379,8 +1407,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(flagF, F); DA(posF, F);
     if (F > 0) {
         KL(k_mask_flags, nblk(F, TB), TB, F, tb.order, FR0, pr.n_chrom, d_clen, d_cmask, pr.mask_subtelomere, (long long)pr.subtel, flagF, P->err);
-        int r = xscan(ctx, P, flagF, posF, F); if (r) return r;
-        KL(k_total, 1, 1, posF, flagF, F, P->cnt + 1);
+        int r = xscan(ctx, P, flagF, posF, F, P->cnt + 1); if (r) return r;
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int D = P->D = (int)ctx->h_pin[1];
@@ -1390,7 +1417,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     } else {
         int *key, *key2, *v; DA(key, D); DA(key2, D); DA(v, D);
         if (F > 0) KL(k_compact_fillings, nblk(F, TB), TB, F, (const int *)nullptr, flagF, posF, FR0, key, v);
-        int r = sort_pairs<int>(ctx, P, key, key2, v, dfill, D, 0, 32); if (r) return r;
+        int r = sort_pairs(ctx, P, (const unsigned *)key, (unsigned *)key2, v, dfill, D, 0, 32); if (r) return r;
     }
     int4 *IT0; int2 *IT1; int *firstdp;
     DA(IT0, D); DA(IT1, D); DA(firstdp, R);
@@ -1407,8 +1434,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(flagD, D); DA(posD, D); DA(it_q, D);
     if (D > 0) {
         KL(k_is_first, nblk(D, TB), TB, D, IT0, firstdp, flagD);
-        int r = xscan(ctx, P, flagD, posD, D); if (r) return r;
-        KL(k_total, 1, 1, posD, flagD, D, P->cnt + 2);
+        int r = xscan(ctx, P, flagD, posD, D, P->cnt + 2); if (r) return r;
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int Q = P->Q = (int)ctx->h_pin[2];
@@ -1420,7 +1446,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (D > 0) {
         KL(k_item_q, nblk(D, TB), TB, D, IT0, P->q_of_rid, it_q);
         KL(k_iota, nblk(D, TB), TB, iotaD, D);
-        int r = sort_pairs<int>(ctx, P, it_q, qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
+        int r = sort_pairs(ctx, P, (const unsigned *)it_q, (unsigned *)qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
         KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
         KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RI, P->err);
         KL(k_check_naln, nblk(D, TB), TB, D, it_q, IT1, P->RI, P->err);
@@ -1430,15 +1456,18 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     int *s_dp; DA(s_dp, D);
     const bool tie_ok = tkey && ctx->h_pin[41] == 0;                 // (read back with the stage-3 counters)
     if (D > 0 && tie_ok) {                                           // one stable partition by chromosome + local tie fix
-        int r = sort_pairs<unsigned>(ctx, P, tkey, tkey2, (const int *)tval, (int *)tval2, D, 0, bits_for(pr.n_chrom)); if (r) return r;
+        int r = sort_pairs(ctx, P, tkey, tkey2, (const int *)tval, (int *)tval2, D, 0, bits_for(pr.n_chrom)); if (r) return r;
         KL(k_apply_delta, nblk(D, TB), TB, D, tval2, s_dp);
     } else if (D > 0) {                                              // long runs of equal (chrom, start): two full radix sorts
-        unsigned *ek, *ek2; unsigned long long *ck, *ck2; int *v1;
-        DA(ek, D); DA(ek2, D); DA(ck, D); DA(ck2, D); DA(v1, D);
+        // (chrom, start, end desc, data order) as three stable sorts from data order: ~end, start, chrom
+        unsigned *ek, *ek2; int *v1, *v2;
+        DA(ek, D); DA(ek2, D); DA(v1, D); DA(v2, D);
         KL(k_end_keys, nblk(D, TB), TB, D, IT0, ek);
-        int r = sort_pairs<unsigned>(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
-        KL(k_chrom_start_keys, nblk(D, TB), TB, D, v1, IT0, ck);
-        r = sort_pairs<unsigned long long>(ctx, P, ck, ck2, v1, s_dp, D, 0, 32 + bits_for(pr.n_chrom)); if (r) return r;
+        int r = sort_pairs(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
+        KL(k_gather_key, nblk(D, TB), TB, D, v1, IT0, 0, ek);
+        r = sort_pairs(ctx, P, ek, ek2, v1, v2, D, 0, 32); if (r) return r;
+        KL(k_gather_key, nblk(D, TB), TB, D, v2, IT0, 1, ek);
+        r = sort_pairs(ctx, P, ek, ek2, v2, s_dp, D, 0, bits_for(pr.n_chrom)); if (r) return r;
     }
     { int r = mark(ctx, 4); if (r) return r; }
     // ---- stage 5: records, thresholds, bands
@@ -1451,11 +1480,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         int *s_m; DA(s_m, D);
         KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
                                                s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
-        size_t b = 0;
-        CK(cub::DeviceScan::InclusiveScanByKey(nullptr, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
-        int r = cub_tmp(ctx, P, b); if (r) return r;
-        b = P->cub_bytes;
-        CK(cub::DeviceScan::InclusiveScanByKey(P->cub_tmp, b, P->s_chrom, s_end, P->pmaxS, MaxOp(), D, cub::Equality(), st));
+        int r = segmax_scan(ctx, P, P->s_chrom, s_end, P->pmaxS, D); if (r) return r;
         KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM,
            (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14));
     }
@@ -1507,8 +1532,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     DA(posQ, Q);
     if (Q > 0 && nshard > 1) { int r = launch_pair(ctx, P, shard, nshard, 1); if (r) return r; }
     if (Q > 0) {
-        int r = xscan(ctx, P, P->isP, posQ, Q); if (r) return r;
-        KL(k_total, 1, 1, posQ, P->isP, Q, P->cnt + 6);
+        int r = xscan(ctx, P, P->isP, posQ, Q, P->cnt + 6); if (r) return r;
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const int nP = P->nP = (int)ctx->h_pin[6];
@@ -1528,12 +1552,10 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
         int *sflag, *spos, *sstart, *rflag, *rpos, *rstart;
         DA(sflag, nP); DA(spos, nP); DA(sstart, nP); DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
         KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, sflag, P->stop, P->stopS);
-        int r = xscan(ctx, P, sflag, spos, nP); if (r) return r;
-        KL(k_total, 1, 1, spos, sflag, nP, P->cnt + 15);
+        int r = xscan(ctx, P, sflag, spos, nP, P->cnt + 15); if (r) return r;
         KL(k_compact_flagged, nblk(nP, TB), TB, nP, sflag, spos, sstart);
         KL(k_run_cut, nblk(nP, TB), TB, nP, sflag, spos, sstart, P->cnt + 15, rflag);
-        r = xscan(ctx, P, rflag, rpos, nP); if (r) return r;
-        KL(k_total, 1, 1, rpos, rflag, nP, P->cnt + 12);
+        r = xscan(ctx, P, rflag, rpos, nP, P->cnt + 12); if (r) return r;
         KL(k_compact_flagged, nblk(nP, TB), TB, nP, rflag, rpos, rstart);
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
@@ -1570,13 +1592,11 @@ static int pipe_number(fslrc_ctx *ctx, Pipe *P, int *out_cluster, int *out_n) {
     if (Q > 0) {
         CK(cudaMemsetAsync(csize, 0, sizeof(int) * Q, st));
         KL(k_flatten, nblk(Q, TB), TB, Q, P->parent, P->ing, isroot, csize);
-        int r = xscan(ctx, P, isroot, cidx, Q); if (r) return r;
-        KL(k_total, 1, 1, cidx, isroot, Q, P->cnt + 9);
+        int r = xscan(ctx, P, isroot, cidx, Q, P->cnt + 9); if (r) return r;
     }
     if (R > 0) {
         KL(k_single_flags, nblk(R, TB), TB, R, P->q_of_rid, P->ing, sflag);
-        int r = xscan(ctx, P, sflag, spos, R); if (r) return r;
-        KL(k_total, 1, 1, spos, sflag, R, P->cnt + 11);
+        int r = xscan(ctx, P, sflag, spos, R, P->cnt + 11); if (r) return r;
         KL(k_number, nblk(R, TB), TB, R, P->q_of_rid, P->ing, P->parent, cidx, csize, spos, P->cnt + 9, out_cluster, out_n);
     }
     return mark(ctx, 10);
@@ -1639,6 +1659,7 @@ int fslrc_create(int device, fslrc_ctx **out) {
     ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->h_pin = nullptr;
     if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaFuncSetAttribute(prims::k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prims::RsSmem));
     cudaMemPool_t pool;                                   // keep freed scratch cached between calls
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;
