@@ -482,9 +482,9 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 #define PK_GROUPS (PK_WARPS * 4)
 #define PK_HASH 64              // settled-partner filter slots per group
 #define PK_CHUNK 256            // relation-entry slots a warp reserves at a time (>= 32)
-#define RP_K 32                 // partners a saturating read may have for the replay's LIST mode
+#define RP_K 64                 // partners a saturating read may have for the replay's LIST mode
 #define PL_CHUNK 512            // partner records a warp reserves at a time (>= 4 * RP_K)
-#define RP_KL (RP_K / 8)         // partners per lane of a replay group
+#define RP_KL 4                  // partners per lane of a replay group handled in one batch (32 partners per batch)
 
 // Partner record of a saturating read a (replay LIST mode): everything the replay needs to know about partner b without
 // touching b's geometry again.  r0 = {b | edge << 31, off_b << 6 | L_b - 1, cg, 0}, r1 = {key[0..3]}:
@@ -644,7 +644,10 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
             }
             if (sat && gl == 0) { PLInfo pi; pi.off = my0; pi.n = nPart; pi.pad = 0; plinfo[q] = pi; }
         }
-        if (sat && nPart <= 0 && gl == 0) { PLInfo pi; pi.off = 0; pi.n = nPart < 0 ? -1 : 0; pi.pad = 0; plinfo[q] = pi; }
+        if (sat && nPart <= 0 && gl == 0) {
+            PLInfo pi; pi.off = 0; pi.n = nPart < 0 ? -1 : 0; pi.pad = 0; plinfo[q] = pi;
+            if (nPart < 0) atomicAdd(pl_slots + 3, 1ull);                           // (reads the replay has to WALK)
+        }
     }
     if (chunk_used < PK_CHUNK)
         for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
@@ -670,7 +673,7 @@ __global__ void k_compact_flagged(int n, const int *__restrict__ flag, const int
 // a step whose outcome depends on a stop that is not published yet commits only the candidates before it (scan order)
 // and is retried on the next iteration — nobody spins, so groups can never block one another, and a group only ever
 // depends on reads of smaller tickets (held by resident groups) or on earlier reads of its own run.
-#define RG_WARPS 4
+#define RG_WARPS 2
 #define RG_GROUPS (RG_WARPS * 4)
 #define RUN_CAP 64
 #define RUN_LONG 1
@@ -764,8 +767,10 @@ __device__ __forceinline__ int gmax8(unsigned gmask, int v) {
     v = max(v, __shfl_xor_sync(gmask, v, 1)); v = max(v, __shfl_xor_sync(gmask, v, 2)); v = max(v, __shfl_xor_sync(gmask, v, 4));
     return v;
 }
-template <bool ALLMATCH>
-__global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+// WALK = false: an instantiation without the band-walking code (half the registers, twice the resident groups) for the
+// usual case that every saturating read has partner records
+template <bool ALLMATCH, bool WALK>
+__global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
                                                            const int *__restrict__ rstart, const int *__restrict__ isP,
                                                            const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                            int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
@@ -816,23 +821,26 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, cons
                 if (La <= 4 && gl < La) { sA0[grp][gl] = rm0(t, offa + gl); sA1[grp][gl] = rm1(t, offa + gl); }
                 phase = 1;
                 const PLInfo pi = plinfo[a];
+                if (!WALK && pi.n < 0) { atomicOr(err, EF_OVERFLOW); phase = 3; }  // (cannot happen: the host picks WALK when such reads exist)
                 if (gl == 0) { sRecTag[grp][a & 31] = La <= 4 ? a : -1; sRecStop[grp][a & 31] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff); }
                 if (!ALLMATCH && pi.n >= 0) {                                      // the pair kernel left a's partner records
                     nPart = pi.n;
-                    int4 r0[RP_KL], r1[RP_KL];
+                    for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {
+                        int4 r0[RP_KL], r1[RP_KL];
 #pragma unroll
-                    for (int k = 0; k < RP_KL; k++) {
-                        const int j = gl + 8 * k;
-                        if (j < nPart) { r0[k] = __ldg(&PL[2 * (pi.off + j)]); r1[k] = __ldg(&PL[2 * (pi.off + j) + 1]); }
-                    }
+                        for (int k = 0; k < RP_KL; k++) {
+                            const int j = jb + gl + 8 * k;
+                            if (j < nPart) { r0[k] = __ldg(&PL[2 * (pi.off + j)]); r1[k] = __ldg(&PL[2 * (pi.off + j) + 1]); }
+                        }
 #pragma unroll
-                    for (int k = 0; k < RP_KL; k++) {
-                        const int j = gl + 8 * k;
-                        if (j < nPart) {
-                            const int b = r0[k].x & QMASK;
-                            r0[k].w = (b < a && !__ldg(&isP[b])) ? 1 : 0;          // b < a and never breaking: it saw the pair
-                            sP0[grp][j] = r0[k];
-                            sP1[grp][j] = r1[k];
+                        for (int k = 0; k < RP_KL; k++) {
+                            const int j = jb + gl + 8 * k;
+                            if (j < nPart) {
+                                const int b = r0[k].x & QMASK;
+                                r0[k].w = (b < a && !__ldg(&isP[b])) ? 1 : 0;      // b < a and never breaking: it saw the pair
+                                sP0[grp][j] = r0[k];
+                                sP1[grp][j] = r1[k];
+                            }
                         }
                     }
                     phase = 5;
@@ -850,12 +858,13 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, cons
             // pass 1: where does the scan first meet each partner (its highest interval inside the closed band); did an
             // earlier-ranked partner's own query see a first?  cls: 0 not met, 1 seen, 2 reach, 3 reach + edge, 4 undecided
             int mxReach = -1, mxUn = -1, nEdge = 0;
+            for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {                        // 32 partners per batch (usually one batch)
             int4 q0[RP_KL];
             int keyk[RP_KL], sv[RP_KL][4];
             bool poll[RP_KL];
 #pragma unroll
             for (int k = 0; k < RP_KL; k++) {                                      // stage A: keys; who needs b's stops?
-                const int j = gl + 8 * k;
+                const int j = jb + gl + 8 * k;
                 keyk[k] = -1; poll[k] = false;
                 q0[k] = make_int4(0, 0, 0, 1);
                 if (j < nPart) {
@@ -884,7 +893,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, cons
             }
 #pragma unroll
             for (int k = 0; k < RP_KL; k++) {                                      // stage C: did b's own query see a first?
-                const int j = gl + 8 * k;
+                const int j = jb + gl + 8 * k;
                 if (poll[k]) {
                     bool vis = false, unres = false;
 #pragma unroll
@@ -902,6 +911,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, cons
                     else if (!(q0[k].w & 4)) mxUn = max(mxUn, keyk[k]);
                 }
                 if (j < nPart) sKey[grp][j] = keyk[k];
+            }
             }
             __syncwarp(gmask);
             // the break (cluster.py:223-224): the first reached partner, in scan order, at which `edges` is >= edge_threshold
@@ -965,7 +975,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 4) k_replay(Tab t, int nP, cons
             }
         }
         // ------------------------------------------------------------ WALK mode
-        else {
+        else if (WALK) {
         if (phase == 1) {
             if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; posf = sA1[grp][fi].x; }
             else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
@@ -1543,7 +1553,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     CK(cudaMemsetAsync(P->ticket, 0, sizeof(unsigned), st));
     { int r = mark(ctx, 7); if (r) return r; }
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
-    const int replay_blocks_max = n_sms(ctx) * 8;
+    const int replay_blocks_max = n_sms(ctx) * 16;
     unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
     unsigned long long alt = 2ull * (unsigned long long)ctx->h_pin[3] + 64;
     P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * RG_GROUPS * (replay_blocks_max + 1);
@@ -1560,12 +1570,13 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
-        if (P->pr.overlap > 0.0)
-            KL(k_replay<false>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges,
-               (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
-        else
-            KL(k_replay<true>, blocks, RG_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges,
-               (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16));
+        const bool walk = !(P->pr.overlap > 0.0) || ctx->h_pin[43] != 0;   // some read without partner records?
+#define REPLAY_ARGS P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges, \
+                    (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16)
+        if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
+        else if (walk) KL((k_replay<false, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
+        else KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
+#undef REPLAY_ARGS
     }
     { int r = mark(ctx, 8); if (r) return r; }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
@@ -1611,8 +1622,8 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->edges = h[8]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
     s->partner_records = h[42];
     s->no_clusters = h[9] == 0;
-    if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld\n",
-                                       (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12]);
+    if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld, walk-mode reads %lld\n",
+                                       (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12], (long long)h[43]);
     if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] long stall: a %lld waits b %lld stops %d %d base %lld top %lld posf %lld bpos %lld %lld apos2 %lld fi %lld (n=%lld)\n",
                                        (long long)h[29], (long long)h[30], (int)h[31], (int)h[32], (long long)h[33], (long long)h[34], (long long)h[35], (long long)h[36], (long long)h[37], (long long)h[38], (long long)h[39], (long long)h[28]);
     if (getenv("FSLRC_DEBUG") && h[20]) fprintf(stderr, "[fslrc] longest walk: %lld steps (stalled %lld) read %lld filling %lld/%lld band %lld walked %lld edges %lld\n",
