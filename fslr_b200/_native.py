@@ -11,7 +11,7 @@ N_STAGES = 12
 
 SYMBOLS = ["fslrc_create", "fslrc_destroy", "fslrc_last_error", "fslrc_stage_name", "fslrc_version",
            "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_replay",
-           "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count"]
+           "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_choose_alignment_host"]
 
 ERRORS = {-1: "FSLRC_ERR_CUDA", -2: "FSLRC_ERR_ARG", -3: "FSLRC_ERR_ZERO_DIVISOR", -4: "FSLRC_ERR_TOO_MANY_FILLINGS",
           -5: "FSLRC_ERR_NALN_NOT_CONSTANT", -6: "FSLRC_ERR_OVERFLOW", -7: "FSLRC_ERR_RANGE"}
@@ -78,6 +78,7 @@ def load():
     lib.fslrc_mg_replay.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i64p]
     lib.fslrc_mg_finish.argtypes = [vp, vp, C.c_int64, vp, vp, C.POINTER(Stats)]
     lib.fslrc_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.fslrc_choose_alignment_host.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]
     lib.fslrc_launch_count.argtypes = [vp]
     lib.fslrc_launch_count.restype = C.c_longlong
     _lib = lib

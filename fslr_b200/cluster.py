@@ -177,9 +177,18 @@ def cluster_table(table, chr_lengths=None, cluster_mask="subtelomere", jaccard_c
     return _run(table, params, tie_order or TIE_ORDER, device)
 
 
-def choose_alignment(bed_file):
-    """cluster.py:237-254 — the read with the highest mean alignment_score per cluster (first on ties)."""
-    avg = bed_file.groupby("qname")["alignment_score"].mean()
-    bed_file["avg_alignment_score"] = bed_file["qname"].map(avg)
-    best = bed_file.loc[bed_file.groupby("cluster")["avg_alignment_score"].idxmax(), "qname"]
-    return bed_file[bed_file["qname"].isin(set(best))]
+def choose_alignment(bed_file, device=0):
+    """cluster.py:237-254 — the rows of the read with the highest mean alignment_score per cluster (first on ties), computed
+    on the GPU (fslrc_choose_alignment_host).  Like the reference it adds the `avg_alignment_score` column to `bed_file`."""
+    rid, _ = pd.factorize(bed_file["qname"], sort=False)
+    score = bed_file["alignment_score"].to_numpy()
+    if not np.all(np.isfinite(score)) or np.any(score != np.round(score)) or np.abs(score).max(initial=0) >= 2**31:
+        raise ValueError("alignment_score must be integer valued (collect_mapping_info.py writes the AS tag)")
+    n_reads = int(rid.max()) + 1 if rid.size else 0
+    first_row = np.full(n_reads, rid.shape[0], dtype=np.int64)
+    np.minimum.at(first_row, rid, np.arange(rid.shape[0]))
+    cid, cvals = pd.factorize(bed_file["cluster"].to_numpy()[first_row], sort=False)
+    is_rep, _ = get_engine(device).choose_alignment(rid, score.astype(np.int64), cid, len(cvals))
+    sums = np.bincount(rid, weights=score.astype(np.float64), minlength=n_reads)
+    bed_file["avg_alignment_score"] = (sums / np.maximum(np.bincount(rid, minlength=n_reads), 1))[rid]   # the column the reference adds
+    return bed_file[is_rep[rid].astype(bool)]

@@ -1252,6 +1252,50 @@ __global__ void k_number(int R, const int *__restrict__ q_of_rid, const int *__r
     else { out_cluster[r] = (int)(*ncl) + spos[r]; out_n[r] = 1; }                   // singletons after the clusters, bed order
 }
 
+// ---------------------------------------------------------------- choose_alignment (cluster.py:237-254, main.py:351-352)
+// per read: sum and count of alignment_score over its rows, first row; per cluster: the read with the highest mean
+// (IEEE double division, as pandas' groupby.mean of an integer column), first row in table order on ties (idxmax)
+__device__ __forceinline__ unsigned long long order_f64(double x) {   // monotone map double -> uint64
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__global__ void k_ca_rows(int A, int R, const int *__restrict__ rid, const int *__restrict__ score, long long *sum, int *cnt, int *first, int *err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const int r = rid[i];
+    if ((unsigned)r >= (unsigned)R) { atomicOr(err, EF_RANGE); return; }
+    atomicAdd((unsigned long long *)&sum[r], (unsigned long long)(long long)score[i]);
+    atomicAdd(&cnt[r], 1);
+    atomicMin(&first[r], i);
+}
+__global__ void k_ca_best(int R, int C, const long long *__restrict__ sum, const int *__restrict__ cnt, const int *__restrict__ cluster,
+                          unsigned long long *best, int *err) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || cnt[r] == 0) return;
+    const int c = cluster[r];
+    if ((unsigned)c >= (unsigned)C) { atomicOr(err, EF_RANGE); return; }
+    atomicMax(&best[c], order_f64(__ddiv_rn((double)sum[r], (double)cnt[r])));
+}
+__global__ void k_ca_first(int R, int C, const long long *__restrict__ sum, const int *__restrict__ cnt, const int *__restrict__ first,
+                           const int *__restrict__ cluster, const unsigned long long *__restrict__ best, int *minrow) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || cnt[r] == 0) return;
+    const int c = cluster[r];
+    if ((unsigned)c >= (unsigned)C) return;
+    if (order_f64(__ddiv_rn((double)sum[r], (double)cnt[r])) == best[c]) atomicMin(&minrow[c], first[r]);
+}
+__global__ void k_ca_flag(int R, int C, const int *__restrict__ cnt, const int *__restrict__ first, const int *__restrict__ cluster,
+                          const int *__restrict__ minrow, unsigned char *is_rep, int *rep_read) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    unsigned char f = 0;
+    if (cnt[r] > 0) {
+        const int c = cluster[r];
+        if ((unsigned)c < (unsigned)C && minrow[c] == first[r]) { f = 1; if (rep_read) rep_read[c] = r; }
+    }
+    is_rep[r] = f;
+}
+
 // ---------------------------------------------------------------- integer-issue microbenchmark (roofline denominator)
 __global__ void k_int_peak(int iters, int *out) {
     int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 5, a5 = a0 + 7, a6 = a0 + 11, a7 = a0 + 13;
@@ -1812,6 +1856,51 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, 
     cudaStreamSynchronize(st);
     delete ctx->pipe; ctx->pipe = nullptr;
     return r;
+}
+
+int fslrc_choose_alignment_host(fslrc_ctx *ctx, int64_t n_rows, int64_t n_reads, int64_t n_clusters, const int32_t *read_id,
+                                const int32_t *alignment_score, const int32_t *cluster, uint8_t *out_is_rep, int32_t *out_rep_read,
+                                void *stream) {
+    if (!ctx) return FSLRC_ERR_ARG;
+    if (n_rows < 0 || n_reads < 0 || n_clusters < 0 || n_rows > 0x7ffffff0LL || n_reads > 0x7ffffff0LL || n_clusters > 0x7ffffff0LL ||
+        (n_rows > 0 && (!read_id || !alignment_score)) || (n_reads > 0 && (!cluster || !out_is_rep)))
+        return fail(ctx, FSLRC_ERR_ARG, "choose_alignment: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    cudaStream_t st = ctx->stream;
+    const int A = (int)n_rows, R = (int)n_reads, C = (int)n_clusters, TB = 256;
+    int *d_rid, *d_sc, *d_cl, *cnt, *first, *minrow, *rep, *err; long long *sum; unsigned long long *best; unsigned char *flag;
+    DA(d_rid, A); DA(d_sc, A); DA(d_cl, R); DA(cnt, R); DA(first, R); DA(minrow, C); DA(rep, C); DA(err, 1); DA(sum, R); DA(best, C); DA(flag, R);
+    if (A > 0) {
+        CK(cudaMemcpyAsync(d_rid, read_id, sizeof(int) * A, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_sc, alignment_score, sizeof(int) * A, cudaMemcpyHostToDevice, st));
+    }
+    if (R > 0) {
+        CK(cudaMemcpyAsync(d_cl, cluster, sizeof(int) * R, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(cnt, 0, sizeof(int) * R, st));
+        CK(cudaMemsetAsync(sum, 0, sizeof(long long) * R, st));
+        KL(k_fill<int>, nblk(R, TB), TB, first, R, 0x7fffffff);
+    }
+    if (C > 0) {
+        CK(cudaMemsetAsync(best, 0, sizeof(unsigned long long) * C, st));
+        KL(k_fill<int>, nblk(C, TB), TB, minrow, C, 0x7fffffff);
+        KL(k_fill<int>, nblk(C, TB), TB, rep, C, -1);
+    }
+    CK(cudaMemsetAsync(err, 0, sizeof(int), st));
+    if (A > 0) KL(k_ca_rows, nblk(A, TB), TB, A, R, d_rid, d_sc, sum, cnt, first, err);
+    if (R > 0) {
+        KL(k_ca_best, nblk(R, TB), TB, R, C, sum, cnt, d_cl, best, err);
+        KL(k_ca_first, nblk(R, TB), TB, R, C, sum, cnt, first, d_cl, best, minrow);
+        KL(k_ca_flag, nblk(R, TB), TB, R, C, cnt, first, d_cl, minrow, flag, rep);
+        CK(cudaMemcpyAsync(out_is_rep, flag, R, cudaMemcpyDeviceToHost, st));
+    }
+    if (C > 0 && out_rep_read) CK(cudaMemcpyAsync(out_rep_read, rep, sizeof(int) * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_pin + 60, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    free_all(ctx);
+    cudaStreamSynchronize(st);
+    if ((int)(ctx->h_pin[60] & 0xffffffff)) return fail(ctx, FSLRC_ERR_RANGE, "choose_alignment: read id or cluster id out of range");
+    return 0;
 }
 
 long long fslrc_launch_count(const fslrc_ctx *ctx) { return ctx ? ctx->launches : 0; }

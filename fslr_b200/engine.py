@@ -209,6 +209,20 @@ class Engine:
         from .sharded import gather_columns
         gather_columns({k: ptab.cols[k] for k in _COLS}, dtab.cols, dtab.n_rows, rank, world, group)
 
+    def choose_alignment(self, read_id, alignment_score, cluster, n_clusters):
+        """cluster.py:237-254 on the GPU.  read_id/alignment_score: int32 per table row; cluster: int32 per read (dense ids).
+        Returns (is_rep uint8 [n_reads], rep_read int32 [n_clusters])."""
+        rid = np.ascontiguousarray(read_id, dtype=np.int32)
+        sc = np.ascontiguousarray(alignment_score, dtype=np.int32)
+        cl = np.ascontiguousarray(cluster, dtype=np.int32)
+        is_rep = np.zeros(max(cl.shape[0], 1), dtype=np.uint8)
+        rep = np.full(max(int(n_clusters), 1), -1, dtype=np.int32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._check(self.lib.fslrc_choose_alignment_host(self.ctx, rid.shape[0], cl.shape[0], int(n_clusters), rid.ctypes.data,
+                                                         sc.ctypes.data, cl.ctypes.data, is_rep.ctypes.data, rep.ctypes.data,
+                                                         C.c_void_p(stream)))
+        return is_rep[:cl.shape[0]], rep[:int(n_clusters)]
+
     def launch_count(self):
         return int(self.lib.fslrc_launch_count(self.ctx))
 

@@ -127,6 +127,15 @@ int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64
 int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges,
                     int32_t *out_cluster, int32_t *out_n_reads, fslrc_stats *stats);
 
+/* cluster.choose_alignment (cluster.py:237-254; main.py:351-352): the representative read of every cluster = the read with
+ * the highest mean alignment_score over its rows (double division of the integer sum by the row count, as pandas'
+ * groupby.mean), the read whose first row comes first in the table on ties (DataFrame.idxmax).  HOST buffers.
+ * cluster: [n_reads] cluster id per read (0..n_clusters-1; reads without rows are ignored); out_is_rep: [n_reads] 1 for the
+ * reads the reference would keep in <base>.mappings.representative.bed; out_rep_read: [n_clusters] or NULL. */
+int fslrc_choose_alignment_host(fslrc_ctx *ctx, int64_t n_rows, int64_t n_reads, int64_t n_clusters, const int32_t *read_id,
+                                const int32_t *alignment_score, const int32_t *cluster, uint8_t *out_is_rep,
+                                int32_t *out_rep_read, void *stream);
+
 /* Integer-issue microbenchmark used as the pair-kernel roofline denominator: returns the measured
  * dependent-free IADD3/LOP3/VIMNMX lane-ops per second on this device. */
 int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s);

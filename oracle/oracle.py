@@ -91,3 +91,19 @@ def fillings_start_column(table):
     np.maximum.at(last, rid, idx)
     keep = (idx != first[rid]) & (idx != last[rid])
     return np.minimum(table.rstart[keep], table.rend[keep]).astype(np.int64)
+
+
+def oracle_choose_alignment(qid, cluster_rows, score):
+    """numpy restatement of cluster.choose_alignment (cluster.py:237-254): per qname the float64 mean of alignment_score
+    (:238-239), per cluster the FIRST row holding the maximum mean (:248, DataFrame.idxmax), kept rows = all rows of the
+    selected qnames (:251).  qid: dense read id per row; cluster_rows: cluster value per row.  Returns the kept-row mask."""
+    qid = np.asarray(qid)
+    n = int(qid.max()) + 1 if qid.size else 0
+    avg = np.bincount(qid, weights=np.asarray(score, dtype=np.float64), minlength=n) / np.maximum(np.bincount(qid, minlength=n), 1)
+    row_avg = avg[qid]
+    selected = set()
+    cl = np.asarray(cluster_rows)
+    for c in np.unique(cl):
+        rows = np.nonzero(cl == c)[0]
+        selected.add(int(qid[rows[np.argmax(row_avg[rows])]]))       # argmax: first maximum, like idxmax
+    return np.isin(qid, list(selected))
