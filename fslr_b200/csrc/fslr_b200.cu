@@ -24,6 +24,8 @@
 // which a warp only ever waits for reads holding smaller tickets.
 #include <cuda_runtime.h>
 #include "prims.cuh"
+#include "tsv.cuh"
+#include <string>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -47,8 +49,11 @@ struct fslrc_ctx {
     cudaEvent_t ev[FSLRC_N_STAGES + 1];
     // pipeline state (kept between the fslrc_mg_* stages)
     struct Pipe *pipe;
+    struct TsvState *tsv;    // parsed mappings.bed kept on the device between fslrc_tsv_open and fslrc_tsv_close
     long long launches;      // kernels of this library launched since fslrc_create
 };
+
+static void tsv_free(fslrc_ctx *ctx);
 
 static const char *STAGE_NAMES[FSLRC_N_STAGES] = {
     "h2d", "keep_fillings", "data_order_mask", "query_rank_read_lists", "chrom_sort", "records_bands",
@@ -1361,7 +1366,7 @@ static int xscan(fslrc_ctx *ctx, Pipe *P, const int *in, int *out, int n, int64_
     if (n <= 0) { if (total) CK(cudaMemsetAsync(total, 0, sizeof(int64_t), st)); return 0; }
     const int tiles = nblk(n, prims::SC_TILE);
     int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
-    KL(prims::k_scan_excl_i32, tiles, prims::SC_THREADS, in, out, n, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim, (long long *)total);
+    KL(prims::k_scan_excl<int>, tiles, prims::SC_THREADS, in, out, n, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim, (long long *)total);
     return 0;
 }
 // per-segment inclusive prefix max (seg non-decreasing)
@@ -1711,7 +1716,7 @@ int fslrc_create(int device, fslrc_ctx **out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FSLRC_ERR_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) return FSLRC_ERR_CUDA;
     fslrc_ctx *ctx = new fslrc_ctx();
-    ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->h_pin = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->tsv = nullptr; ctx->h_pin = nullptr;
     if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
     cudaFuncSetAttribute(prims::k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prims::RsSmem));
@@ -1728,6 +1733,7 @@ void fslrc_destroy(fslrc_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     free_all(ctx);
+    tsv_free(ctx);
     cudaDeviceSynchronize();
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -1901,6 +1907,205 @@ int fslrc_choose_alignment_host(fslrc_ctx *ctx, int64_t n_rows, int64_t n_reads,
     cudaStreamSynchronize(st);
     if ((int)(ctx->h_pin[60] & 0xffffffff)) return fail(ctx, FSLRC_ERR_RANGE, "choose_alignment: read id or cluster id out of range");
     return 0;
+}
+
+// ---------------------------------------------------------------- mappings.bed ingest / egress on the GPU (tsv.cuh)
+}  // extern "C"
+struct TsvState {
+    std::vector<void *> allocs;
+    unsigned char *text; long long n; long long *line_start;
+    int n_lines, n_rows, n_reads, n_chrom;
+    int *read_id, *chrom, *rstart, *rend, *aln, *qstart, *qend, *naln, *score, *first_row;
+    long long *q_off; int *q_len;
+    std::vector<std::string> chrom_names;
+};
+template <typename T>
+static int palloc(fslrc_ctx *ctx, T **p, int64_t n) {                  // persistent (until fslrc_tsv_close)
+    void *q = nullptr;
+    CK(cudaMallocAsync(&q, (size_t)(n > 0 ? n : 1) * sizeof(T), ctx->stream));
+    ctx->tsv->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+#define PA(ptr, n) do { int r__ = palloc(ctx, &(ptr), (int64_t)(n)); if (r__) return r__; } while (0)
+static void tsv_free(fslrc_ctx *ctx) {
+    if (!ctx->tsv) return;
+    for (void *p : ctx->tsv->allocs) cudaFreeAsync(p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    delete ctx->tsv; ctx->tsv = nullptr;
+}
+// strings -> dense ids in order of first appearance (pandas.factorize); *n_ids receives the number of distinct strings
+static int tsv_intern(fslrc_ctx *ctx, Pipe *P, TsvState *T, const long long *off, const int *len, const unsigned long long *hash,
+                      int *id_out, int *first_row_of_id /*nullable, capacity n_rows*/, int *err, int64_t *n_ids_dev) {
+    cudaStream_t st = ctx->stream;
+    const int n = T->n_rows, TB = 256;
+    unsigned cap = 1024; while (cap < 2u * (unsigned)n && cap < (1u << 30)) cap <<= 1;
+    unsigned long long *keys; int *first, *slot, *isf, *idat;
+    DA(keys, cap); DA(first, cap); DA(slot, n); DA(isf, n); DA(idat, n);
+    CK(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * cap, st));
+    KL(k_fill<int>, nblk(cap, TB), TB, first, (int64_t)cap, 0x7fffffff);
+    KL(tsv::k_tsv_intern_insert, nblk(n, TB), TB, n, hash, keys, first, cap - 1, slot);
+    KL(tsv::k_tsv_intern_verify, nblk(n, TB), TB, n, T->text, off, len, slot, first, isf, err);
+    int r = xscan(ctx, P, isf, idat, n, n_ids_dev); if (r) return r;
+    KL(tsv::k_tsv_intern_ids, nblk(n, TB), TB, n, slot, first, idat, id_out, first_row_of_id);
+    return 0;
+}
+extern "C" {
+
+int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t hash_seed, fslrc_tsv_info *info, void *stream) {
+    if (!ctx) return FSLRC_ERR_ARG;
+    if (!text || !info || n_bytes <= 0) return fail(ctx, FSLRC_ERR_ARG, "tsv: null or empty input");
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    cudaStream_t st = ctx->stream;
+    tsv_free(ctx);
+    // ---- header (host): which field holds which column (names of collect_mapping_info.py:176-181)
+    const char *names[tsv::W_N] = {"chrom", "rstart", "rend", "qname", "n_alignments", "aln_size", "qstart", "qend", "alignment_score"};
+    tsv::Want w; for (int k = 0; k < tsv::W_N; k++) w.col[k] = -1; w.last = -1;
+    {
+        int64_t e = 0; while (e < n_bytes && text[e] != '\n') e++;
+        int f = 0; int64_t p = 0;
+        while (p <= e) {
+            int64_t q = p; while (q < e && text[q] != '\t') q++;
+            for (int k = 0; k < tsv::W_N; k++)
+                if ((int64_t)strlen(names[k]) == q - p && memcmp(names[k], text + p, q - p) == 0) { w.col[k] = f; if (f > w.last) w.last = f; }
+            f++; p = q + 1;
+        }
+        for (int k = 0; k < tsv::W_SCORE; k++) if (w.col[k] < 0) return fail(ctx, FSLRC_ERR_ARG, "tsv: header lacks column %s", names[k]);
+    }
+    TsvState *T = ctx->tsv = new TsvState();
+    Pipe Pp; memset((void *)&Pp, 0, sizeof(Pp)); Pipe *P = &Pp;       // (scratch of the scan primitive)
+    const bool pad = text[n_bytes - 1] != '\n';
+    T->n = n_bytes + (pad ? 1 : 0);
+    PA(T->text, T->n + 64);
+    CK(cudaMemcpyAsync(T->text, text, n_bytes, cudaMemcpyHostToDevice, st));
+    if (pad) CK(cudaMemsetAsync(T->text + n_bytes, '\n', 1, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // ---- lines
+    const int TB = 256;
+    const int64_t nchunks = (T->n + tsv::CHUNK - 1) / tsv::CHUNK;
+    if (nchunks > 0x7ffffff0LL) { tsv_free(ctx); return fail(ctx, FSLRC_ERR_ARG, "tsv: input too large"); }
+    int *cnt, *pre, *err;
+    DA(cnt, nchunks); DA(pre, nchunks); DA(err, 1);
+    int64_t *dcount; DA(dcount, 4);
+    CK(cudaMemsetAsync(err, 0, sizeof(int), st));
+    KL(tsv::k_tsv_count, nblk(nchunks, TB), TB, T->text, (long long)T->n, cnt);
+    { int r = xscan(ctx, P, cnt, pre, (int)nchunks, dcount); if (r) return r; }
+    CK(cudaMemcpyAsync(ctx->h_pin, dcount, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (ctx->h_pin[0] > 0x7ffffff0LL) { free_all(ctx); tsv_free(ctx); return fail(ctx, FSLRC_ERR_ARG, "tsv: too many lines"); }
+    T->n_lines = (int)ctx->h_pin[0];
+    T->n_rows = T->n_lines - 1;
+    PA(T->line_start, (int64_t)T->n_lines + 1);
+    KL(tsv::k_tsv_lines, nblk(nchunks, TB), TB, T->text, (long long)T->n, pre, T->line_start);
+    const int n = T->n_rows;
+    PA(T->read_id, n); PA(T->chrom, n); PA(T->rstart, n); PA(T->rend, n); PA(T->aln, n); PA(T->qstart, n); PA(T->qend, n); PA(T->naln, n);
+    PA(T->q_off, n); PA(T->q_len, n); PA(T->first_row, n);
+    T->score = nullptr;
+    if (w.col[tsv::W_SCORE] >= 0) PA(T->score, n);
+    T->n_reads = 0; T->n_chrom = 0;
+    if (n > 0) {
+        unsigned long long *qh, *ch; long long *coff; int *clen, *cfirst;
+        DA(qh, n); DA(ch, n); DA(coff, n); DA(clen, n); DA(cfirst, n);
+        KL(tsv::k_tsv_parse, nblk(n, TB), TB, T->text, T->line_start, n, w, (unsigned long long)hash_seed, T->rstart, T->rend, T->naln, T->aln,
+           T->qstart, T->qend, T->score, T->q_off, T->q_len, qh, coff, clen, ch, err);
+        int r = tsv_intern(ctx, P, T, T->q_off, T->q_len, qh, T->read_id, T->first_row, err, dcount + 1); if (r) return r;
+        r = tsv_intern(ctx, P, T, coff, clen, ch, T->chrom, cfirst, err, dcount + 2); if (r) return r;
+        CK(cudaMemcpyAsync(ctx->h_pin, dcount, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_pin + 8, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const int e = (int)(ctx->h_pin[8] & 0xffffffff);
+        if (e) {
+            free_all(ctx); tsv_free(ctx);
+            if (e & tsv::TE_COLLISION) return fail(ctx, FSLRC_ERR_HASH_COLLISION, "tsv: two different names share a 64-bit hash; call again with another hash_seed");
+            if (e & tsv::TE_FIELDS) return fail(ctx, FSLRC_ERR_ARG, "tsv: a line has fewer fields than the header");
+            if (e & tsv::TE_RANGE) return fail(ctx, FSLRC_ERR_RANGE, "tsv: an integer field does not fit int32");
+            return fail(ctx, FSLRC_ERR_ARG, "tsv: a numeric field is not an integer");
+        }
+        T->n_reads = (int)ctx->h_pin[1]; T->n_chrom = (int)ctx->h_pin[2];
+        // chromosome names (few): offsets of their first rows -> host strings out of the caller's text
+        std::vector<int> cf(T->n_chrom);
+        CK(cudaMemcpyAsync(cf.data(), cfirst, sizeof(int) * T->n_chrom, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        std::vector<long long> o1(1); std::vector<int> l1(1);
+        for (int c = 0; c < T->n_chrom; c++) {
+            CK(cudaMemcpyAsync(o1.data(), coff + cf[c], sizeof(long long), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(l1.data(), clen + cf[c], sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            T->chrom_names.emplace_back(text + o1[0], (size_t)l1[0]);
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[2], st));
+    free_all(ctx);
+    CK(cudaStreamSynchronize(st));
+    memset(info, 0, sizeof(*info));
+    info->n_rows = T->n_rows; info->n_reads = T->n_reads; info->n_chrom = T->n_chrom; info->has_score = T->score != nullptr;
+    info->read_id = T->read_id; info->chrom = T->chrom; info->rstart = T->rstart; info->rend = T->rend; info->aln_size = T->aln;
+    info->qstart = T->qstart; info->qend = T->qend; info->n_alignments = T->naln; info->alignment_score = T->score;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev[0 + 1], ctx->ev[2]) == cudaSuccess) info->parse_ms = ms; else cudaGetLastError();
+    return 0;
+}
+int fslrc_tsv_chrom_name(fslrc_ctx *ctx, int32_t chrom_id, char *buf, int32_t cap) {
+    if (!ctx || !ctx->tsv || !buf || chrom_id < 0 || chrom_id >= ctx->tsv->n_chrom) return FSLRC_ERR_ARG;
+    const std::string &s = ctx->tsv->chrom_names[chrom_id];
+    if ((int)s.size() + 1 > cap) return FSLRC_ERR_ARG;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
+}
+int fslrc_tsv_read_names(fslrc_ctx *ctx, int64_t *offsets, int32_t *lengths) {
+    if (!ctx || !ctx->tsv || !offsets || !lengths) return FSLRC_ERR_ARG;
+    TsvState *T = ctx->tsv;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int R = T->n_reads;
+    if (R == 0) return 0;
+    std::vector<int> fr(R);
+    CK(cudaMemcpyAsync(fr.data(), T->first_row, sizeof(int) * R, cudaMemcpyDeviceToHost, st));
+    std::vector<long long> qo(T->n_rows); std::vector<int> ql(T->n_rows);
+    CK(cudaMemcpyAsync(qo.data(), T->q_off, sizeof(long long) * T->n_rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ql.data(), T->q_len, sizeof(int) * T->n_rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int r = 0; r < R; r++) { offsets[r] = qo[fr[r]]; lengths[r] = ql[fr[r]]; }
+    return 0;
+}
+int fslrc_tsv_write_cluster_bed(fslrc_ctx *ctx, const int32_t *cluster_dev, const int32_t *n_reads_dev, char *out, int64_t cap,
+                                int64_t *n_out, void *stream) {
+    if (!ctx || !ctx->tsv || !cluster_dev || !n_reads_dev || !n_out) return FSLRC_ERR_ARG;
+    TsvState *T = ctx->tsv;
+    CK(cudaSetDevice(ctx->device));
+    ctx->stream = (cudaStream_t)stream;
+    cudaStream_t st = ctx->stream;
+    Pipe Pp; memset((void *)&Pp, 0, sizeof(Pp)); Pipe *P = &Pp;
+    const int L = T->n_lines, TB = 256;
+    long long *len, *off; int64_t *tot;
+    DA(len, L); DA(off, L); DA(tot, 1);
+    KL(tsv::k_tsv_outlen, nblk(L, TB), TB, L, T->line_start, T->read_id, cluster_dev, n_reads_dev, len);
+    {
+        const int tiles = nblk(L, prims::SC_TILE);
+        int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
+        KL(prims::k_scan_excl<long long>, tiles, prims::SC_THREADS, len, off, L, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim, (long long *)tot);
+    }
+    CK(cudaMemcpyAsync(ctx->h_pin, tot, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = ctx->h_pin[0];
+    int rc = 0;
+    if (out) {
+        if (cap < *n_out) rc = fail(ctx, FSLRC_ERR_ARG, "tsv: output buffer too small");
+        else {
+            unsigned char *d_out; DA(d_out, *n_out);
+            KL(tsv::k_tsv_emit, nblk((int64_t)L * 32, TB), TB, L, T->text, T->line_start, T->read_id, cluster_dev, n_reads_dev, off, d_out);
+            CK(cudaMemcpyAsync(out, d_out, *n_out, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    free_all(ctx);
+    CK(cudaStreamSynchronize(st));
+    return rc;
+}
+void fslrc_tsv_close(fslrc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    tsv_free(ctx);
 }
 
 long long fslrc_launch_count(const fslrc_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -63,63 +63,64 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long 
     return excl;
 }
 
-// ---------------------------------------------------------------- exclusive sum of int32
-__global__ void __launch_bounds__(SC_THREADS) k_scan_excl_i32(const int *__restrict__ in, int *__restrict__ out, int n,
-                                                              unsigned long long *status, unsigned *ticket, long long *total) {
+// ---------------------------------------------------------------- exclusive sum (int32, or int64 for byte offsets)
+template <typename T>
+__global__ void __launch_bounds__(SC_THREADS) k_scan_excl(const T *__restrict__ in, T *__restrict__ out, int n,
+                                                          unsigned long long *status, unsigned *ticket, long long *total) {
     __shared__ unsigned s_tile;
-    __shared__ int s_warp[SC_THREADS / 32];
-    __shared__ int s_excl;
+    __shared__ long long s_warp[SC_THREADS / 32];
+    __shared__ long long s_excl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = (int)s_tile;
     const int base = tile * SC_TILE + tid * SC_ITEMS;
-    int v[SC_ITEMS];
-    if (base + SC_ITEMS <= n && (((uintptr_t)(in + base)) & 15) == 0) {
+    T v[SC_ITEMS];
+    if (sizeof(T) == 4 && base + SC_ITEMS <= n && (((uintptr_t)(in + base)) & 15) == 0) {
 #pragma unroll
         for (int k = 0; k < SC_ITEMS / 4; k++) {
             const int4 q = __ldg((const int4 *)(in + base) + k);
-            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            v[4 * k] = (T)q.x; v[4 * k + 1] = (T)q.y; v[4 * k + 2] = (T)q.z; v[4 * k + 3] = (T)q.w;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < SC_ITEMS; k++) v[k] = base + k < n ? in[base + k] : 0;
+        for (int k = 0; k < SC_ITEMS; k++) v[k] = base + k < n ? in[base + k] : (T)0;
     }
-    int tsum = 0;
+    long long tsum = 0;
 #pragma unroll
     for (int k = 0; k < SC_ITEMS; k++) tsum += v[k];
-    int incl = tsum;                                                  // inclusive scan of the thread sums inside the warp
+    long long incl = tsum;                                            // inclusive scan of the thread sums inside the warp
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    int wbase = 0, tile_sum = 0;
+    long long wbase = 0, tile_sum = 0;
 #pragma unroll
-    for (int w = 0; w < SC_THREADS / 32; w++) { const int x = s_warp[w]; if (w < warp) wbase += x; tile_sum += x; }
+    for (int w = 0; w < SC_THREADS / 32; w++) { const long long x = s_warp[w]; if (w < warp) wbase += x; tile_sum += x; }
     if (warp == 0) {
-        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? ST_INC : ST_AGG) | (unsigned long long)(unsigned)tile_sum);
+        if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? ST_INC : ST_AGG) | ((unsigned long long)tile_sum & ST_MASK));
         unsigned long long excl = 0;
         if (tile > 0) {
             excl = lookback(status, tile, lane, OpAdd(), 0ull);
-            if (lane == 0) st_relaxed_u64(&status[tile], ST_INC | ((excl + (unsigned long long)(unsigned)tile_sum) & ST_MASK));
+            if (lane == 0) st_relaxed_u64(&status[tile], ST_INC | ((excl + (unsigned long long)tile_sum) & ST_MASK));
         }
         if (lane == 0) {
-            s_excl = (int)excl;
+            s_excl = (long long)excl;
             if (total && (long long)(tile + 1) * SC_TILE >= n) *total = (long long)excl + tile_sum;
         }
     }
     __syncthreads();
-    int run = s_excl + wbase + incl - tsum;
-    if (base + SC_ITEMS <= n && (((uintptr_t)(out + base)) & 15) == 0) {
+    long long run = s_excl + wbase + incl - tsum;
+    if (sizeof(T) == 4 && base + SC_ITEMS <= n && (((uintptr_t)(out + base)) & 15) == 0) {
 #pragma unroll
         for (int k = 0; k < SC_ITEMS / 4; k++) {
             int4 q;
-            q.x = run; run += v[4 * k]; q.y = run; run += v[4 * k + 1]; q.z = run; run += v[4 * k + 2]; q.w = run; run += v[4 * k + 3];
+            q.x = (int)run; run += v[4 * k]; q.y = (int)run; run += v[4 * k + 1]; q.z = (int)run; run += v[4 * k + 2]; q.w = (int)run; run += v[4 * k + 3];
             *((int4 *)(out + base) + k) = q;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < SC_ITEMS; k++) { if (base + k < n) out[base + k] = run; run += v[k]; }
+        for (int k = 0; k < SC_ITEMS; k++) { if (base + k < n) out[base + k] = (T)run; run += v[k]; }
     }
 }
 

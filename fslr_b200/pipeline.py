@@ -13,6 +13,32 @@ from . import cluster as gcluster
 from .table import ColumnarTable
 
 
+def cluster_step_fast(bed_path, chr_lengths, out_base, cluster_mask="subtelomere", jaccard_cutoffs="1,1,0.66,0.66,0.66,0.5",
+                      overlap=0.8, n_alignment_diff=0.25, qlen_diff=0.04, representative=True, device=0):
+    """The same block with the table never leaving the GPU between the file bytes and the output bytes (fslr_b200.tsv):
+    GPU TSV parse -> clustering on the device-resident columns -> GPU rendering of `<out_base>.mappings.cluster.bed`.
+    Tie order of equal starts is the GPU's stable one (ids equal the reference's whenever its unstable sort keeps ties in
+    table order, the partition always).  Returns the ClusterResult, or None for main.py:247-249's early return."""
+    from . import tsv
+    print("Making clusters", file=sys.stderr)                                    # main.py:207
+    pb = tsv.read_mappings_bed(bed_path, chr_lengths, device=device)
+    try:
+        res = pb.cluster(cluster_mask=cluster_mask, jaccard_cutoffs=jaccard_cutoffs, overlap=overlap,
+                         n_alignment_diff=n_alignment_diff, qlen_diff=qlen_diff)
+        if res.no_clusters:
+            print("No clusters were found.", file=sys.stderr)                    # main.py:247-249
+            return None
+        out = pb.cluster_bed_bytes()
+        out.tofile(f"{out_base}.mappings.cluster.bed")                           # main.py:349
+        if representative:                                                       # main.py:351-352
+            import io
+            rep = gcluster.choose_alignment(pd.read_csv(io.BytesIO(out.tobytes()), sep="\t"), device=device)
+            rep.to_csv(f"{out_base}.mappings.representative.bed", index=False, sep="\t")
+        return res
+    finally:
+        pb.close()
+
+
 def cluster_step(bed_file, chr_lengths, cluster_mask="subtelomere", jaccard_cutoffs="1,1,0.66,0.66,0.66,0.5", overlap=0.8,
                  n_alignment_diff=0.25, qlen_diff=0.04, filter_false=False, out_base=None, tie_order=None, device=0):
     """Returns the annotated DataFrame, or None when main.py:247-249 would print "No clusters were found." and return."""
@@ -49,7 +75,13 @@ def main(argv=None):
     ap.add_argument("--qlen-diff", type=float, default=0.04)
     ap.add_argument("--cluster-mask", default="subtelomere")
     ap.add_argument("--filter-false", action="store_true")
+    ap.add_argument("--fast-io", action="store_true", help="parse the TSV and render mappings.cluster.bed on the GPU")
+    ap.add_argument("--no-representative", action="store_true")
     a = ap.parse_args(argv)
+    if a.fast_io and not a.filter_false:
+        cluster_step_fast(a.bed, json.load(open(a.chr_lengths)), a.out_base, a.cluster_mask, a.jaccard_cutoffs, a.overlap,
+                          a.n_alignment_diff, a.qlen_diff, not a.no_representative)
+        return
     cluster_step(a.bed, json.load(open(a.chr_lengths)), a.cluster_mask, a.jaccard_cutoffs, a.overlap, a.n_alignment_diff,
                  a.qlen_diff, a.filter_false, a.out_base)
 

@@ -33,7 +33,8 @@ enum {
     FSLRC_ERR_NALN_NOT_CONSTANT = -5, /* n_alignments differs between rows of one read (the producer,
                                          collect_mapping_info.py:80,122,141, never emits that) */
     FSLRC_ERR_OVERFLOW = -6,        /* internal edge buffer overflow (cannot happen within the stated bounds) */
-    FSLRC_ERR_RANGE = -7            /* a value does not fit the packed device records (n_alignments >= 65536, id out of range) */
+    FSLRC_ERR_RANGE = -7,           /* a value does not fit the packed device records (n_alignments >= 65536, id out of range) */
+    FSLRC_ERR_HASH_COLLISION = -8   /* fslrc_tsv_open: two different names share a 64-bit hash (retry with another seed) */
 };
 
 typedef struct fslrc_ctx fslrc_ctx;
@@ -135,6 +136,28 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges,
 int fslrc_choose_alignment_host(fslrc_ctx *ctx, int64_t n_rows, int64_t n_reads, int64_t n_clusters, const int32_t *read_id,
                                 const int32_t *alignment_score, const int32_t *cluster, uint8_t *out_is_rep,
                                 int32_t *out_rep_read, void *stream);
+
+/* ---- `<base>.mappings.bed` ingest / egress on the GPU ----
+ * fslrc_tsv_open parses the TSV main.py:209 reads with pandas (header + the columns collect_mapping_info.py:176-181 writes;
+ * only chrom, rstart, rend, qname, n_alignments, aln_size, qstart, qend[, alignment_score] are decoded) and leaves the
+ * columnar table ON THE DEVICE: `info` holds device pointers that can go straight into fslrc_table for
+ * fslrc_cluster_device.  read_id / chrom are dense ids in order of first appearance (pandas.factorize).  The parsed table
+ * lives in the context until fslrc_tsv_close (or the next fslrc_tsv_open).
+ * fslrc_tsv_write_cluster_bed renders `<base>.mappings.cluster.bed` (main.py:349): every input line followed by the float
+ * columns `cluster` and `n_reads` (main.py:334-342), header included, into a HOST buffer (out == NULL: size query). */
+typedef struct {
+    int64_t n_rows, n_reads;
+    int32_t n_chrom, has_score;
+    const int32_t *read_id, *chrom, *rstart, *rend, *aln_size, *qstart, *qend, *n_alignments, *alignment_score;  /* device */
+    float parse_ms;                /* device time of the parse (after the upload) */
+    int32_t reserved;
+} fslrc_tsv_info;
+int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t hash_seed, fslrc_tsv_info *info, void *stream);
+int fslrc_tsv_chrom_name(fslrc_ctx *ctx, int32_t chrom_id, char *buf, int32_t cap);     /* returns the length */
+int fslrc_tsv_read_names(fslrc_ctx *ctx, int64_t *offsets, int32_t *lengths);           /* [n_reads]: where each qname sits in `text` */
+int fslrc_tsv_write_cluster_bed(fslrc_ctx *ctx, const int32_t *cluster_dev, const int32_t *n_reads_dev, char *out, int64_t cap,
+                                int64_t *n_out, void *stream);
+void fslrc_tsv_close(fslrc_ctx *ctx);
 
 /* Integer-issue microbenchmark used as the pair-kernel roofline denominator: returns the measured
  * dependent-free IADD3/LOP3/VIMNMX lane-ops per second on this device. */
