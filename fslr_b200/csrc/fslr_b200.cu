@@ -375,7 +375,8 @@ __global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restri
 // ---------------------------------------------------------------- pair-level pieces
 struct Tab {                 // kernel-side view of the tables
     const int4 *SR0, *SR1, *RM, *RI;
-    const int *pmaxS, *chrom_lo;
+    const int *pmaxS, *chrom_lo, *chrom_hi;
+    const int *sib;          // per sorted position: position of the read's next filling (cyclic) | (L - 1) << 26; WALK replay only
     int D, Q, Tedge;
 };
 // read-major filling records (see k_bands)
@@ -724,6 +725,33 @@ __global__ void k_run_cut(int nP, const int *__restrict__ sflag, const int *__re
     const int cap = (end - start) > RUN_CAP ? RUN_LONG : RUN_CAP;
     rflag[k] = ((k - start) % cap) == 0;
 }
+// sib[p]: where the next filling (cyclic) of p's read sits in sorted order, and the read's filling count
+__global__ void k_sib(int D, const int4 *__restrict__ SR0, const int4 *__restrict__ SR1, const int4 *__restrict__ RM, int *sib) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int w = SR1[p].w;
+    const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1, fi = (int)((unsigned)SR0[p].w >> 26);
+    const int nxt = off + (fi + 1 == L ? 0 : fi + 1);
+    sib[p] = (int)((unsigned)RM[2 * nxt + 1].x | ((unsigned)(L - 1) << 26));
+}
+// Did read b (owner of the interval at sorted position p, b < a) provably see a first through one of its OTHER fillings?
+// Walks b's fillings through the position-indexed sibling ring: sibling at sp saw a's filling fa iff they overlap (closed)
+// and b's scan of the sibling got down to fa's position.  A's fillings (<= 4) are in shared memory.
+__device__ __forceinline__ bool seen_via_sibling(const Tab &t, const int *stopS, int p, const int4 *A0, const int2 *A1, const int2 *Achr, int La) {
+    int sv = __ldg(&t.sib[p]);
+    const int hops = (int)((unsigned)sv >> 26);                                    // L - 1 other fillings
+    if (hops > 3) return false;
+    for (int h = 0; h < hops; h++) {
+        const int sp = sv & QMASK;
+        const int4 c = __ldg(&t.SR0[sp]);
+        const int reached = stop_reached(ld_relaxed(&stopS[sp]));
+#pragma unroll
+        for (int fa = 0; fa < 4; fa++)
+            if (fa < La && sp >= Achr[fa].x && sp < Achr[fa].y && A0[fa].y <= c.y && A0[fa].z >= c.x && reached <= A1[fa].x) return true;
+        sv = __ldg(&t.sib[sp]);
+    }
+    return false;
+}
 // one candidate b of read a's filling scan when either read has more than 4 fillings (lists stay in global memory)
 __device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
                                                 const int4 f, int top, int p, int b, int offb, int Lb) {
@@ -787,6 +815,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
     __shared__ int4 sP0[RG_GROUPS][RP_K];    // partner records: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}; flags: 1 visited by a,
     __shared__ int4 sP1[RG_GROUPS][RP_K];    //   4 b saw a first, 8 b did not;  {key[0..3]}
     __shared__ int sKey[RG_GROUPS][RP_K];    // first-visit position in the current filling's scan
+    __shared__ int2 sAchr[RG_GROUPS][4];     // [chrom_lo, chrom_hi) of a's fillings (sibling test of the WALK mode)
     __shared__ int sRecTag[RG_GROUPS][32];   // the reads this group replayed last (direct mapped by rank & 31) and their final
     __shared__ int4 sRecStop[RG_GROUPS][32]; //   stops: partners of one run mostly look each other up here, not in global memory
     const unsigned FULL = 0xffffffffu;
@@ -823,7 +852,11 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
                 ria = __ldg(&t.RI[a]);                                             // {qlen2, Lq, naln | Ln << 16, off << 6 | L - 1}
                 offa = (int)((unsigned)ria.w >> 6); La = (ria.w & 63) + 1;
                 fi = 0; edges = 0;
-                if (La <= 4 && gl < La) { sA0[grp][gl] = rm0(t, offa + gl); sA1[grp][gl] = rm1(t, offa + gl); }
+                if (La <= 4 && gl < La) {
+                    const int4 r0 = rm0(t, offa + gl);
+                    sA0[grp][gl] = r0; sA1[grp][gl] = rm1(t, offa + gl);
+                    if (WALK) sAchr[grp][gl] = make_int2(__ldg(&t.chrom_lo[r0.x]), __ldg(&t.chrom_hi[r0.x]));
+                }
                 phase = 1;
                 const PLInfo pi = plinfo[a];
                 if (!WALK && pi.n < 0) { atomicOr(err, EF_OVERFLOW); phase = 3; }  // (cannot happen: the host picks WALK when such reads exist)
@@ -1005,10 +1038,34 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
                     wq[k] = -1; we[k] = 0; ws[k] = 0;
                     if (p >= lo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
                 }
+                bool needs[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    needs[k] = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
+                if (t.sib && La <= 4) {                                            // ... or through its other filling (reads of 2 fillings:
+                    int sp[8];                                                     //     the loads of all 8 positions are batched)
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        sp[k] = -1;
+                        if (needs[k] && wq[k] < a) { const int sv = __ldg(&t.sib[base - 8 * k - gl]); if (((unsigned)sv >> 26) == 1u) sp[k] = sv & QMASK; }
+                    }
+                    int cs[8], ce[8], cv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (sp[k] >= 0) { const int4 c = __ldg(&t.SR0[sp[k]]); cs[k] = c.x; ce[k] = c.y; cv[k] = stop_reached(ld_relaxed(&stopS[sp[k]])); }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (sp[k] >= 0) {
+#pragma unroll
+                            for (int fa = 0; fa < 4; fa++)
+                                if (fa < La && sp[k] >= sAchr[grp][fa].x && sp[k] < sAchr[grp][fa].y && sA0[grp][fa].y <= ce[k] &&
+                                    sA0[grp][fa].z >= cs[k] && cv[k] <= sA1[grp][fa].x) needs[k] = false;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int k = 7; k >= 0; k--) {
-                    const bool needs = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
-                    const unsigned nm = (__ballot_sync(gmask, needs) >> gsh) & 0xffu;
+                    const unsigned nm = (__ballot_sync(gmask, needs[k]) >> gsh) & 0xffu;
                     if (nm) adv = 8 * k + __ffs(nm) - 1;
                 }
                 base -= adv;
@@ -1024,7 +1081,8 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
                     const int4 c0 = __ldg(&t.SR0[p]);
                     b = c0.w & QMASK;
                     if (b != a && c0.y >= f.y                                      // closed overlap (start_p <= end_f by p <= ub)
-                        && !(b < a && stop_reached(ld_relaxed(&stopS[p])) <= posf)) {   // b's scan of this interval passed a: seen
+                        && !(b < a && stop_reached(ld_relaxed(&stopS[p])) <= posf)     // b's scan of this interval passed a: seen
+                        && !(b < a && t.sib && La <= 4 && seen_via_sibling(t, stopS, p, sA0[grp], sA1[grp], sAchr[grp], La))) {
                     cheap = false;
                     const int4 c1 = __ldg(&t.SR1[p]);
                     if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
@@ -1548,7 +1606,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
     Tab &t = P->tab;
     t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM = P->RM; t.RI = P->RI; t.pmaxS = P->pmaxS;
-    t.chrom_lo = P->chrom_lo; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
+    t.chrom_lo = P->chrom_lo; t.chrom_hi = P->chrom_hi; t.sib = nullptr; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
     // relation entries: a read records at most edge_threshold + 7 passing partners (one step past the threshold), and every
     // entry is a distinct (filling of a, band position) hit
     const unsigned long long tight = (unsigned long long)ctx->h_pin[14];
@@ -1620,6 +1678,11 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
         const bool walk = !(P->pr.overlap > 0.0) || ctx->h_pin[43] != 0;   // some read without partner records?
+        if (walk && D > 0) {
+            int *sib; DA(sib, D);
+            KL(k_sib, nblk(D, TB), TB, D, P->SR0, P->SR1, P->RM, sib);
+            P->tab.sib = sib;
+        }
 #define REPLAY_ARGS P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges, \
                     (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16)
         if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
