@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-sample-reads", type=int, default=CPU_SAMPLE_READS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-depth", type=int, default=2, help="host-buffer calls in flight for the e2e number (1 = strictly serial)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
@@ -149,7 +150,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fslr_b200.engine import DeviceTable, Engine, PinnedTable
+    from fslr_b200.engine import DeviceTable, Engine, HostPipeline, PinnedTable
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
@@ -204,6 +205,39 @@ def main():
     clocks = sampler.stop() if sampler else {}
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
+    e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)"
+    if world == 1 and args.e2e_depth > 1:
+        # the same call, `e2e_depth` in flight: table k+1 uploads while table k computes (fslr_b200.engine.HostPipeline)
+        pipe = HostPipeline(local, args.e2e_depth)
+        ptabs = [ptab] + [PinnedTable(ct) for _ in range(args.e2e_depth - 1)]
+        for f in [pipe.submit(ptabs[i % len(ptabs)], ct, params) for i in range(args.e2e_depth)]:
+            f.result()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        e0.record(cur)
+        for s_ in pipe.streams:
+            s_.wait_event(e0)
+        futs = []
+        for i in range(args.steps):                       # a buffer set is reused only after its previous step has finished
+            if i >= len(ptabs):
+                futs[i - len(ptabs)].result()
+            futs.append(pipe.submit(ptabs[i % len(ptabs)], ct, params))
+        for f in futs:
+            f.result()
+        for s_ in pipe.streams:
+            cur.wait_stream(s_)
+        e1.record(cur)
+        torch.cuda.synchronize()
+        ms_pipe = e0.elapsed_time(e1)
+        for pt in ptabs[1:]:
+            assert np.array_equal(pt.out_cluster[:R].numpy(), ptab.out_cluster[:R].numpy()), "pipelined e2e results disagree"
+        pipe.close()
+        if ms_pipe < ms_e2e:
+            e2e_serial_ms = ms_e2e / args.steps
+            ms_e2e = ms_pipe
+            e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k); one call at a time: %.2f ms/step" % (
+                args.e2e_depth, e2e_serial_ms)
 
     # correctness guard inside the bench: both paths agree with each other
     res_a = dtab.out_cluster[:R].cpu().numpy()
@@ -263,7 +297,7 @@ def main():
             "partner_records": st["partner_records"],
             "stage_ms": stage_ms, "roofline": roofline, "int_issue": int_issue, "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": ptab.h2d_bytes,
-                    "d2h_bytes_per_step": ptab.d2h_bytes},
+                    "d2h_bytes_per_step": ptab.d2h_bytes, "mode": e2e_mode},
             "gpu_launches": launches}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:

@@ -379,11 +379,13 @@ struct Tab {                 // kernel-side view of the tables
     const int *sib;          // per sorted position: position of the read's next filling (cyclic) | (L - 1) << 26; WALK replay only
     int D, Q, Tedge;
 };
+// per-N Jaccard cutoff as the largest passing union: a kernel parameter of its own (per call, so that concurrent contexts
+// with different options never share it), staged into shared memory by the kernels that index it
+struct UmaxTab { int v[LMAX + 1]; };
 // read-major filling records (see k_bands)
 __device__ __forceinline__ int4 rm0(const Tab &t, int m) { return __ldg(&t.RM[2 * m]); }                            // {chrom, start, end, T}
 __device__ __forceinline__ int2 rm1(const Tab &t, int m) { return __ldg((const int2 *)&t.RM[2 * m + 1]); }          // {pos, ub}
 __device__ __forceinline__ int2 rm2(const Tab &t, int m) { return __ldg((const int2 *)&t.RM[2 * m + 1] + 1); }      // {lbT, ubT}
-__constant__ int c_umax[LMAX + 1];
 
 // a (query) against b, both as read-major records (RM + 2 * off, stride 2): greedy first-fit count of cluster.py:152-161
 // plus the lexicographically first matching filling pair
@@ -502,7 +504,7 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 struct PLInfo { unsigned long long off; int n; int pad; };
 
 template <bool ALLMATCH>
-__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int nshard, int lists_only, int *isP, int2 *entries,
+__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um, int shard, int nshard, int lists_only, int *isP, int2 *entries,
                                                          unsigned long long *n_slots, unsigned long long cap_entries,
                                                          int4 *PL, PLInfo *plinfo, unsigned long long *pl_slots, unsigned long long cap_pl,
                                                          unsigned long long *n_tests, unsigned long long *n_real, int *err) {
@@ -510,6 +512,9 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
     __shared__ int4 sB[PK_GROUPS][4];                                              // {lbT, ubT, pos, ub} of a's fillings
     __shared__ int2 sHash[PK_GROUPS][PK_HASH];
     __shared__ int2 sPart[PK_GROUPS][RP_K];                                        // {b | edge << 31, off_b << 6 | L_b - 1}
+    __shared__ int s_umax[LMAX + 1];
+    for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
+    __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, g = lane >> 3, grp = w * 4 + g;
     const unsigned ltmask = (1u << lane) - 1u, gmask = 0xffu << (g * 8);
@@ -572,7 +577,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, int shard, int ns
                             if (settled) {
                                 tests++;
                                 part = n > 0;                                       // the pair can be an effective candidate (cluster.py:216)
-                                pass = n > 0 && (La + Lb - n) <= c_umax[n];         // cluster.py:165-170,218-219
+                                pass = n > 0 && (La + Lb - n) <= s_umax[n];         // cluster.py:165-170,218-219
                             }
                         }
                         if (settled) *hs = make_int2(b, q);
@@ -753,7 +758,7 @@ __device__ __forceinline__ bool seen_via_sibling(const Tab &t, const int *stopS,
     return false;
 }
 // one candidate b of read a's filling scan when either read has more than 4 fillings (lists stay in global memory)
-__device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
+__device__ __noinline__ int replay_eval_general(const Tab &t, const int *umax, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
                                                 const int4 f, int top, int p, int b, int offb, int Lb) {
     for (int g = 0; g < Lb; g++) {                                                 // pair already seen earlier in this very query?
         const int4 bg = rm0(t, offb + g);
@@ -782,7 +787,7 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *stop, c
         if (vis) return RF_TESTED;
         if (unres) return RF_TESTED | RF_UNRES;
     }
-    return RF_TESTED | RF_REACH | ((La + Lb - n) <= c_umax[n] ? RF_EDGE : 0);
+    return RF_TESTED | RF_REACH | ((La + Lb - n) <= umax[n] ? RF_EDGE : 0);
 }
 // Two ways to re-run one read's query:
 //   LIST mode (the normal case): the only candidates that can ever matter to a's query are intervals of reads b that share
@@ -803,7 +808,7 @@ __device__ __forceinline__ int gmax8(unsigned gmask, int v) {
 // WALK = false: an instantiation without the band-walking code (half the registers, twice the resident groups) for the
 // usual case that every saturating read has partner records
 template <bool ALLMATCH, bool WALK>
-__global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+__global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
                                                            const int *__restrict__ rstart, const int *__restrict__ isP,
                                                            const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                            int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
@@ -816,6 +821,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
     __shared__ int4 sP1[RG_GROUPS][RP_K];    //   4 b saw a first, 8 b did not;  {key[0..3]}
     __shared__ int sKey[RG_GROUPS][RP_K];    // first-visit position in the current filling's scan
     __shared__ int2 sAchr[RG_GROUPS][4];     // [chrom_lo, chrom_hi) of a's fillings (sibling test of the WALK mode)
+    __shared__ int s_umax[LMAX + 1];
     __shared__ int sRecTag[RG_GROUPS][32];   // the reads this group replayed last (direct mapped by rank & 31) and their final
     __shared__ int4 sRecStop[RG_GROUPS][32]; //   stops: partners of one run mostly look each other up here, not in global memory
     const unsigned FULL = 0xffffffffu;
@@ -832,6 +838,8 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
     unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
     int d_fsteps = 0, d_fstall = 0;
     int chunk_used = RP_CHUNK;
+    for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
+    __syncthreads();
     for (int k = gl; k < 32; k += 8) sRecTag[grp][k] = -1;
     for (;;) {
         __syncwarp();
@@ -1136,12 +1144,12 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, int nP, cons
                                         }
                                         if (vis) { }
                                         else if (unres) fl |= RF_UNRES;
-                                        else fl |= RF_REACH | ((La + Lb - n) <= c_umax[n] ? RF_EDGE : 0);
+                                        else fl |= RF_REACH | ((La + Lb - n) <= s_umax[n] ? RF_EDGE : 0);
                                     }
                                 }
                             }
                         } else if (b > a || __ldg(&isP[b])) {
-                            fl = replay_eval_general(t, stop, sStop[grp], a, offa, La, fi, f, top, p, b, offb, Lb);
+                            fl = replay_eval_general(t, s_umax, stop, sStop[grp], a, offa, La, fi, f, top, p, b, offb, Lb);
                         }
                     }
                     }
@@ -1395,6 +1403,7 @@ struct Pipe {
     unsigned char *prim; size_t prim_bytes;   // scratch of the device-wide primitives
     int stage;               // next event index
     Tab tab;
+    UmaxTab um;
 };
 
 static int mark(fslrc_ctx *ctx, int stage_end) {   // record the event closing `stage_end`
@@ -1487,7 +1496,6 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(P->err, 1); DA(P->cnt, 48);
     CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
     CK(cudaMemsetAsync(P->cnt, 0, 48 * sizeof(int64_t), st));
-    CK(cudaMemcpyToSymbolAsync(c_umax, pr.umax, sizeof(int) * (LMAX + 1), 0, cudaMemcpyHostToDevice, st));
     long long *d_clen; unsigned char *d_cmask;
     DA(d_clen, pr.n_chrom); DA(d_cmask, pr.n_chrom);
     if (pr.n_chrom > 0) {
@@ -1607,6 +1615,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     Tab &t = P->tab;
     t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM = P->RM; t.RI = P->RI; t.pmaxS = P->pmaxS;
     t.chrom_lo = P->chrom_lo; t.chrom_hi = P->chrom_hi; t.sib = nullptr; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
+    memcpy(P->um.v, pr.umax, sizeof(P->um.v));
     // relation entries: a read records at most edge_threshold + 7 passing partners (one step past the threshold), and every
     // entry is a distinct (filling of a, band position) hit
     const unsigned long long tight = (unsigned long long)ctx->h_pin[14];
@@ -1627,11 +1636,11 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
 static int launch_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, int lists_only) {
     cudaStream_t st = ctx->stream;
     if (P->pr.overlap > 0.0)
-        KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+        KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
            P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
            (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
     else
-        KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
+        KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
            P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
            (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
     return 0;
@@ -1683,7 +1692,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
             KL(k_sib, nblk(D, TB), TB, D, P->SR0, P->SR1, P->RM, sib);
             P->tab.sib = sib;
         }
-#define REPLAY_ARGS P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges, \
+#define REPLAY_ARGS P->tab, P->um, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges, \
                     (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16)
         if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (walk) KL((k_replay<false, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);

@@ -232,6 +232,43 @@ class Engine:
         return v.value
 
 
+class HostPipeline:
+    """Host-buffer clustering of a stream of tables with the upload of one table overlapping the kernels of the previous
+    one: `depth` library contexts, each with its own CUDA stream and worker thread (the C ABI call blocks its thread, not the
+    interpreter).  This is how a service clusters sample after sample; `bench.py` uses it for the end-to-end number."""
+
+    def __init__(self, device=0, depth=2):
+        from concurrent.futures import ThreadPoolExecutor
+        self.engines = [Engine(device) for _ in range(depth)]
+        self.streams = [torch.cuda.Stream(device=self.engines[0].device) for _ in range(depth)]
+        self.pool = ThreadPoolExecutor(max_workers=depth)
+        self.depth, self._next = depth, 0
+
+    def _run(self, slot, ptab, chrom_table, params):
+        eng, stream = self.engines[slot], self.streams[slot]
+        torch.cuda.set_device(eng.device)
+        p = eng._params(chrom_table, params)
+        t = eng._table(ptab)
+        st = _native.Stats()
+        eng._check(eng.lib.fslrc_cluster_host(eng.ctx, C.byref(t), C.byref(p), ptab.out_cluster.data_ptr(),
+                                              ptab.out_n_reads.data_ptr(), C.byref(st), C.c_void_p(stream.cuda_stream)))
+        return st.as_dict(eng.lib)
+
+    def submit(self, ptab: PinnedTable, chrom_table, params):
+        """ptab must not be reused by another submit before this one's future is done (its out_* buffers receive the result)."""
+        slot = self._next
+        self._next = (self._next + 1) % self.depth
+        return self.pool.submit(self._run, slot, ptab, chrom_table, params)
+
+    def launch_count(self):
+        return sum(e.launch_count() for e in self.engines)
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        for e in self.engines:
+            e.close()
+
+
 def table_chrom_len(table):
     return table.chrom_len
 

@@ -100,3 +100,28 @@ def test_errors(engine):
     empty.n_reads = 0
     r = engine.cluster(empty, p)
     assert r.no_clusters and r.cluster.shape[0] == 0
+
+
+def test_host_pipeline_concurrent_contexts():
+    """Two library contexts in flight on one device (HostPipeline) with DIFFERENT tables and options: no state is shared
+    between calls, every result equals the oracle's."""
+    from fslr_b200 import synth
+    from fslr_b200.engine import HostPipeline, PinnedTable
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    from oracle import oracle as orc
+    jobs = []
+    for name, scale, kw in (("C2", 0.3, dict()), ("C3", 0.05, dict(jaccard_cutoffs="0.34", edge_threshold=3)),
+                            ("C5", 0.01, dict(overlap=0.5)), ("C1", 1.0, dict(jaccard_cutoffs="1,1,1"))):
+        t = ColumnarTable.from_synth(synth.make_config(name, scale))
+        p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK[name], **kw)
+        jobs.append((t, p, PinnedTable(t)))
+    pipe = HostPipeline(0, depth=2)
+    for _ in range(3):
+        futs = [pipe.submit(pt, t, p) for t, p, pt in jobs]
+        for f in futs:
+            f.result()
+        for t, p, pt in jobs:
+            ocl, onr, _ = orc.oracle_cluster(t, p)
+            assert np.array_equal(pt.out_cluster[:t.n_reads].numpy(), ocl)
+            assert np.array_equal(pt.out_n_reads[:t.n_reads].numpy(), onr)
+    pipe.close()
