@@ -206,10 +206,12 @@ def main():
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
     e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)"
+    h2d_bytes = ptab.h2d_bytes
     if world == 1 and args.e2e_depth > 1:
         # the same call, `e2e_depth` in flight: table k+1 uploads while table k computes (fslr_b200.engine.HostPipeline)
         pipe = HostPipeline(local, args.e2e_depth)
-        ptabs = [ptab] + [PinnedTable(ct) for _ in range(args.e2e_depth - 1)]
+        ptabs = [PinnedTable(ct, compact=True) for _ in range(args.e2e_depth)]
+        h2d_pipe = ptabs[0].h2d_bytes
         for f in [pipe.submit(ptabs[i % len(ptabs)], ct, params) for i in range(args.e2e_depth)]:
             f.result()
         torch.cuda.synchronize()
@@ -232,12 +234,14 @@ def main():
         ms_pipe = e0.elapsed_time(e1)
         for pt in ptabs[1:]:
             assert np.array_equal(pt.out_cluster[:R].numpy(), ptab.out_cluster[:R].numpy()), "pipelined e2e results disagree"
+        assert np.array_equal(ptabs[0].out_cluster[:R].numpy(), ptab.out_cluster[:R].numpy()), "pipelined e2e results disagree"
         pipe.close()
         if ms_pipe < ms_e2e:
             e2e_serial_ms = ms_e2e / args.steps
             ms_e2e = ms_pipe
-            e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k); one call at a time: %.2f ms/step" % (
-                args.e2e_depth, e2e_serial_ms)
+            h2d_bytes = h2d_pipe
+            e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k), chrom as uint8 and n_alignments " \
+                       "as uint16 on the wire; one call at a time with int32 columns: %.2f ms/step" % (args.e2e_depth, e2e_serial_ms)
 
     # correctness guard inside the bench: both paths agree with each other
     res_a = dtab.out_cluster[:R].cpu().numpy()
@@ -296,7 +300,7 @@ def main():
             "saturating_reads": st["saturating_reads"],
             "partner_records": st["partner_records"],
             "stage_ms": stage_ms, "roofline": roofline, "int_issue": int_issue, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": ptab.h2d_bytes,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": ptab.d2h_bytes, "mode": e2e_mode},
             "gpu_launches": launches}
     if rank == 0:

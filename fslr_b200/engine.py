@@ -54,12 +54,18 @@ class DeviceTable:
 
 
 class PinnedTable:
-    """The table's columns in pinned host memory (the e2e path copies them in every call)."""
+    """The table's columns in pinned host memory (the e2e path copies them in every call).  compact=True keeps `chrom` as
+    uint8 and `n_alignments` as uint16 when they fit (27 instead of 32 bytes per row over PCIe; widened on the device)."""
 
-    def __init__(self, table: ColumnarTable, order=None):
+    def __init__(self, table: ColumnarTable, order=None, compact=False):
         self.n_rows, self.n_reads = table.n_rows, table.n_reads
-        self.cols = {}
+        self.cols, self.narrow = {}, {}
+        if compact and self.n_rows > 0 and table.n_chrom <= 256 and int(np.max(table.n_alignments)) < 65536 and int(np.min(table.n_alignments)) >= 0:
+            self.narrow = {"chrom": torch.from_numpy(np.ascontiguousarray(table.chrom, dtype=np.uint8)).pin_memory(),
+                           "n_alignments": torch.from_numpy(np.ascontiguousarray(table.n_alignments).astype(np.uint16).view(np.int16)).pin_memory()}
         for k in _COLS:
+            if k in self.narrow:
+                continue
             t = torch.empty(max(self.n_rows, 1), dtype=torch.int32).pin_memory()
             t[:self.n_rows] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
             self.cols[k] = t
@@ -71,7 +77,8 @@ class PinnedTable:
 
     @property
     def h2d_bytes(self):
-        return 4 * self.n_rows * len(_COLS) + (4 * int(self.order.numel()) if self.order is not None else 0)
+        per_row = 4 * len(self.cols) + (3 if self.narrow else 0)
+        return per_row * self.n_rows + (4 * int(self.order.numel()) if self.order is not None else 0)
 
     @property
     def d2h_bytes(self):
@@ -134,7 +141,10 @@ class Engine:
         t = _native.Table()
         t.n_rows, t.n_reads = buf.n_rows, buf.n_reads
         for k in _COLS:
-            setattr(t, k, buf.cols[k].data_ptr())
+            setattr(t, k, buf.cols[k].data_ptr() if k in buf.cols else None)
+        narrow = getattr(buf, "narrow", None) or {}
+        t.chrom_u8 = narrow["chrom"].data_ptr() if "chrom" in narrow else None
+        t.n_alignments_u16 = narrow["n_alignments"].data_ptr() if "n_alignments" in narrow else None
         if buf.order is not None:
             t.order, t.n_order = buf.order.data_ptr(), int(buf.order.numel())
         else:

@@ -125,3 +125,19 @@ def test_host_pipeline_concurrent_contexts():
             assert np.array_equal(pt.out_cluster[:t.n_reads].numpy(), ocl)
             assert np.array_equal(pt.out_n_reads[:t.n_reads].numpy(), onr)
     pipe.close()
+
+
+def test_narrow_wire_columns_match():
+    """chrom as uint8 / n_alignments as uint16 on the wire (PinnedTable(compact=True)) give the int32 result."""
+    from fslr_b200 import synth
+    from fslr_b200.engine import PinnedTable, get_engine
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C3", 0.05))
+    p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK["C3"])
+    eng = get_engine(0)
+    wide, narrow = PinnedTable(t), PinnedTable(t, compact=True)
+    assert narrow.narrow and narrow.h2d_bytes == 27 * t.n_rows
+    eng.run_host(wide, t, p)
+    eng.run_host(narrow, t, p)
+    assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), narrow.out_cluster[:t.n_reads].numpy())
+    assert np.array_equal(wide.out_n_reads[:t.n_reads].numpy(), narrow.out_n_reads[:t.n_reads].numpy())
