@@ -240,8 +240,8 @@ def main():
             e2e_serial_ms = ms_e2e / args.steps
             ms_e2e = ms_pipe
             h2d_bytes = h2d_pipe
-            e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k), chrom as uint8 and n_alignments " \
-                       "as uint16 on the wire; one call at a time with int32 columns: %.2f ms/step" % (args.e2e_depth, e2e_serial_ms)
+            e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k), chrom as uint8, n_alignments " \
+                       "as uint16 and aln_size (= qend - qstart) derived on the device: 23 B/row on the wire; one call at a time with int32 columns: %.2f ms/step" % (args.e2e_depth, e2e_serial_ms)
 
     # correctness guard inside the bench: both paths agree with each other
     res_a = dtab.out_cluster[:R].cpu().numpy()

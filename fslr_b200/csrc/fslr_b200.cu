@@ -106,11 +106,13 @@ __global__ void k_fill(T *p, int64_t n, T v) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void k_widen(int64_t n, const unsigned char *__restrict__ c8, const unsigned short *__restrict__ n16, int *chrom, int *naln) {
+__global__ void k_widen(int64_t n, const unsigned char *__restrict__ c8, const unsigned short *__restrict__ n16, int *chrom, int *naln,
+                        int *aln, const int *__restrict__ qstart, const int *__restrict__ qend) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (c8) chrom[i] = c8[i];
     if (n16) naln[i] = n16[i];
+    if (aln) aln[i] = qend[i] - qstart[i];                             // aln_size = qend - qstart (collect_mapping_info.py:88)
 }
 __global__ void k_iota(int *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1762,11 +1764,12 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     }
 }
 
+static inline bool oc_host_path_ok(const fslrc_table *tb) { return tb->aln_size_is_qspan != 0; }   // aln_size may be omitted then
 static int check_args(fslrc_ctx *ctx, const fslrc_table *tb, const fslrc_params *pr, const void *oc, const void *on) {
     if (!ctx) return FSLRC_ERR_ARG;
     if (!tb || !pr || !oc || !on) return fail(ctx, FSLRC_ERR_ARG, "null argument");
     if (tb->n_rows < 0 || tb->n_reads < 0 || tb->n_rows > 0x7ffffff0LL || tb->n_reads > 0x7ffffff0LL) return fail(ctx, FSLRC_ERR_ARG, "table size out of range");
-    if (tb->n_rows > 0 && (!tb->read_id || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || !tb->rend || !tb->aln_size || !tb->qstart || !tb->qend ||
+    if (tb->n_rows > 0 && (!tb->read_id || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || !tb->rend || (!tb->aln_size && !oc_host_path_ok(tb)) || !tb->qstart || !tb->qend ||
                            (!tb->n_alignments && !tb->n_alignments_u16)))
         return fail(ctx, FSLRC_ERR_ARG, "null column");
     if (pr->n_chrom < 0 || pr->n_chrom > (1 << 20) || (pr->n_chrom > 0 && (!pr->chrom_len || !pr->chrom_masked))) return fail(ctx, FSLRC_ERR_ARG, "bad chromosome tables");
@@ -1857,9 +1860,12 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
         } else if (c == 7 && table->n_alignments_u16) {
             DA(d_n16, A);
             if (A > 0) CK(cudaMemcpyAsync(d_n16, table->n_alignments_u16, sizeof(unsigned short) * A, cudaMemcpyHostToDevice, st));
+        } else if (c == 4 && !table->aln_size) {
+            // derived on the device below
         } else if (A > 0) CK(cudaMemcpyAsync(cols[c], src[c], sizeof(int32_t) * A, cudaMemcpyHostToDevice, st));
     }
-    if (A > 0 && (d_c8 || d_n16)) KL(k_widen, nblk(A, 256), 256, A, d_c8, d_n16, cols[1], cols[7]);
+    if (A > 0 && (d_c8 || d_n16 || !table->aln_size))
+        KL(k_widen, nblk(A, 256), 256, A, d_c8, d_n16, cols[1], cols[7], table->aln_size ? (int *)nullptr : cols[4], cols[5], cols[6]);
     d.read_id = cols[0]; d.chrom = cols[1]; d.rstart = cols[2]; d.rend = cols[3]; d.aln_size = cols[4]; d.qstart = cols[5];
     d.qend = cols[6]; d.n_alignments = cols[7];
     int32_t *d_order = nullptr;

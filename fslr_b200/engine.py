@@ -55,7 +55,8 @@ class DeviceTable:
 
 class PinnedTable:
     """The table's columns in pinned host memory (the e2e path copies them in every call).  compact=True keeps `chrom` as
-    uint8 and `n_alignments` as uint16 when they fit (27 instead of 32 bytes per row over PCIe; widened on the device)."""
+    uint8 and `n_alignments` as uint16 when they fit, and leaves out `aln_size` when it equals qend - qstart on every row (what
+    collect_mapping_info.py:88 writes): 23 instead of 32 bytes per row over PCIe, widened / derived on the device."""
 
     def __init__(self, table: ColumnarTable, order=None, compact=False):
         self.n_rows, self.n_reads = table.n_rows, table.n_reads
@@ -63,8 +64,10 @@ class PinnedTable:
         if compact and self.n_rows > 0 and table.n_chrom <= 256 and int(np.max(table.n_alignments)) < 65536 and int(np.min(table.n_alignments)) >= 0:
             self.narrow = {"chrom": torch.from_numpy(np.ascontiguousarray(table.chrom, dtype=np.uint8)).pin_memory(),
                            "n_alignments": torch.from_numpy(np.ascontiguousarray(table.n_alignments).astype(np.uint16).view(np.int16)).pin_memory()}
+        self.aln_is_qspan = bool(compact and self.n_rows > 0 and np.array_equal(
+            np.asarray(table.aln_size, dtype=np.int64), np.asarray(table.qend, dtype=np.int64) - np.asarray(table.qstart, dtype=np.int64)))
         for k in _COLS:
-            if k in self.narrow:
+            if k in self.narrow or (k == "aln_size" and self.aln_is_qspan):
                 continue
             t = torch.empty(max(self.n_rows, 1), dtype=torch.int32).pin_memory()
             t[:self.n_rows] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
@@ -145,6 +148,7 @@ class Engine:
         narrow = getattr(buf, "narrow", None) or {}
         t.chrom_u8 = narrow["chrom"].data_ptr() if "chrom" in narrow else None
         t.n_alignments_u16 = narrow["n_alignments"].data_ptr() if "n_alignments" in narrow else None
+        t.aln_size_is_qspan = int(bool(getattr(buf, "aln_is_qspan", False)))
         if buf.order is not None:
             t.order, t.n_order = buf.order.data_ptr(), int(buf.order.numel())
         else:
