@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, g = lane >> 3, grp = w * 4 + g;
     const unsigned ltmask = (1u << lane) - 1u, gmask = 0xffu << (g * 8);
-    unsigned long long tests = 0, real = 0, chunk_base = 0, pl_base = 0;
+    unsigned long long tests = 0, real = 0, chunk_base = 0, pl_base = 0, nrec_total = 0;
     int chunk_used = PK_CHUNK, pl_used = PL_CHUNK;                                 // nothing reserved yet
     for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
     const int stride = gridDim.x * PK_GROUPS;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
             for (int gg = 0; gg < 3; gg++) { const int x = __shfl_sync(FULL, nrec, gg * 8); if (gg < g) before += x; }
             const unsigned long long my0 = pl_base + pl_used + before;
             pl_used += tot;
-            if (lane == 0) atomicAdd(pl_slots + 2, (unsigned long long)tot);          // (statistics: records written)
+            nrec_total += tot;                                                       // (statistics: records written)
             for (int j = gl; j < nrec; j += 8) {
                 const int2 pr = sPart[grp][j];
                 const int offb = (int)((unsigned)pr.y >> 6), Lb = (pr.y & 63) + 1;
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
     if (chunk_used < PK_CHUNK)
         for (int k = chunk_used + lane; k < PK_CHUNK; k += 32) entries[chunk_base + k] = make_int2(-1, -1);
     for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
-    if (lane == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
+    if (lane == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); if (nrec_total) atomicAdd(pl_slots + 2, nrec_total); }
 }
 
 // ---------------------------------------------------------------- stage 7: saturating set
@@ -1278,8 +1278,8 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
         }
         if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, e);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_edges, (unsigned long long)__popc(m));
+    const int cnt = __syncthreads_count(e);                                        // one counter update per block
+    if (threadIdx.x == 0 && cnt) atomicAdd(n_edges, (unsigned long long)cnt);
 }
 __global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing, unsigned long long *n_edges) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -1292,8 +1292,8 @@ __global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edg
             uf_union(parent, ab.x, ab.y);
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, e);
-    if ((threadIdx.x & 31) == 0 && m && n_edges) atomicAdd(n_edges, (unsigned long long)__popc(m));
+    const int cnt = __syncthreads_count(e);
+    if (threadIdx.x == 0 && cnt && n_edges) atomicAdd(n_edges, (unsigned long long)cnt);
 }
 __global__ void k_flatten(int Q, int *parent, const int *__restrict__ ing, int *isroot, int *csize) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
