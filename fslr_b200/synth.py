@@ -107,14 +107,14 @@ def _family_sizes(rng, n_reads, mean=4.0):
 
 
 def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_frac=0.0,
-               hotspot_reads=0, hotspot_fillings=2, name=""):
+               hotspot_reads=0, hotspot_fillings=2, name="", naln_range=(2, 7)):
     """Generate `n_reads` reads (`hotspot_reads` of them one giant family)."""
     rng = np.random.default_rng(seed)
     primers = list(primers)
     n_bg = n_reads - hotspot_reads
     fam_size = _family_sizes(rng, n_bg) if n_bg > 0 else np.zeros(0, dtype=np.int64)
     n_fam = fam_size.shape[0]
-    fam_naln = rng.integers(2, 7, size=n_fam)                       # U{2..6}
+    fam_naln = rng.integers(naln_range[0], naln_range[1], size=n_fam)   # U{2..6} by default
     if hotspot_reads:
         fam_size = np.concatenate([fam_size, [hotspot_reads]])
         fam_naln = np.concatenate([fam_naln, [hotspot_fillings + 2]])
@@ -179,7 +179,7 @@ def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_f
     key = rng.permutation(R).astype(np.int64)
     # table order of collect_mapping_info.py:174: n_alignments desc, qname asc, qstart asc.  Rows of a read are
     # generated in qstart order and keys are unique, so ordering the READS and expanding is the same permutation.
-    ro = np.argsort(((6 - read_naln).astype(np.int64) << 40) | key)
+    ro = np.argsort(((max(6, naln_range[1]) - read_naln).astype(np.int64) << 40) | key)
     na_s = read_naln[ro]
     new_first = np.cumsum(na_s) - na_s
     order = np.repeat(r_first[ro] - new_first, na_s) + np.arange(A)

@@ -31,3 +31,53 @@ def test_option_corners_match_oracle(name, scale, kw):
     if not res.no_clusters:
         assert np.array_equal(res.cluster, ocl)
         assert np.array_equal(res.n_reads, onr)
+
+
+def _check(t, p):
+    from fslr_b200.engine import get_engine
+    from oracle import oracle as orc
+    res = get_engine(0).cluster(t, p)
+    ocl, onr, ost = orc.oracle_cluster(t, p)
+    assert bool(ost["no_clusters"]) == res.no_clusters
+    if not res.no_clusters:
+        assert np.array_equal(res.cluster, ocl)
+        assert np.array_equal(res.n_reads, onr)
+    return res
+
+
+@pytest.mark.parametrize("T", [10, 2])
+def test_many_fillings_per_read(T):
+    """Reads with up to 12 fillings at scale: the general (> 4 fillings) paths of k_pair and the WALK replay."""
+    from fslr_b200 import synth
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_table(60_000, primers=("21q1", "17p6"), seed=77, naln_range=(2, 15), name="long"))
+    res = _check(t, ClusterParams.from_options(t, edge_threshold=T))
+    assert res.stats["saturating_reads"] > 0
+
+
+def test_rows_in_arbitrary_order():
+    """keep_fillings is defined by first/last OCCURRENCE of a qname (cluster.py:15-24): shuffle the rows of the table."""
+    from fslr_b200 import synth
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C2", 0.2))
+    perm = np.random.default_rng(11).permutation(t.n_rows)
+    for k in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments"):
+        setattr(t, k, np.ascontiguousarray(getattr(t, k)[perm]))
+    # read ids must stay dense in order of first appearance (the singleton numbering order)
+    _, first = np.unique(t.read_id, return_index=True)
+    order = np.argsort(first)
+    remap = np.empty_like(order); remap[order] = np.arange(order.size)
+    t.read_id = remap[t.read_id].astype(np.int32)
+    _check(t, ClusterParams.from_options(t))
+
+
+def test_everything_masked_and_tiny_tables():
+    from fslr_b200 import synth
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C1", 0.2))
+    p = ClusterParams.from_options(t, cluster_mask=",".join(str(c) for c in t.chrom_names))
+    res = _check(t, p)
+    assert res.no_clusters and res.stats["n_intervals"] == 0
+    for n in (16, 17, 40):
+        tt = ColumnarTable.from_synth(synth.make_table(n, seed=n))
+        _check(tt, ClusterParams.from_options(tt))
