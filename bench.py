@@ -161,7 +161,7 @@ def main():
     ct, params = make_workload(args.config, args.scale)
     R, A = ct.n_reads, ct.n_rows
     dtab = DeviceTable(ct, eng.device)
-    ptab = PinnedTable(ct)
+    ptab = PinnedTable(ct, compact=world > 1)       # (N = 1: the strictly serial e2e uses int32 columns; the pipelined one compact ones)
 
     def barrier():
         if world > 1:
@@ -205,7 +205,8 @@ def main():
     clocks = sampler.stop() if sampler else {}
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
-    e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)"
+    e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)" if world == 1 else \
+        "every rank uploads 1/%d of the rows (23 B/row on the wire), NVLink all-gather of the columns, sharded step, rank 0 downloads the result" % world
     h2d_bytes = ptab.h2d_bytes
     if world == 1 and args.e2e_depth > 1:
         # the same call, `e2e_depth` in flight: table k+1 uploads while table k computes (fslr_b200.engine.HostPipeline)

@@ -219,9 +219,20 @@ class Engine:
     def upload_sharded(self, ptab: PinnedTable, dtab: DeviceTable, rank, world, group=None):
         """Multi-GPU ingest of HOST columns: every rank copies only its 1/world slice of the rows over its own PCIe link and
         the slices are all-gathered over NVLink (fslr_b200.sharded.gather_columns), so the host->device time shrinks with
-        the number of GPUs instead of being paid in full by every rank."""
+        the number of GPUs instead of being paid in full by every rank.  Narrow columns of a compact PinnedTable travel
+        narrow (host->device and over NVLink) and are widened on the device."""
         from .sharded import gather_columns
-        gather_columns({k: ptab.cols[k] for k in _COLS}, dtab.cols, dtab.n_rows, rank, world, group)
+        n = dtab.n_rows
+        gather_columns({k: ptab.cols[k] for k in ptab.cols}, {k: dtab.cols[k] for k in ptab.cols}, n, rank, world, group)
+        if ptab.narrow:
+            if not hasattr(dtab, "_narrow"):
+                dtab._narrow = {k: torch.empty(max(n, 1), dtype=v.dtype, device=self.device) for k, v in ptab.narrow.items()}
+            gather_columns(ptab.narrow, dtab._narrow, n, rank, world, group)
+            dtab.cols["chrom"][:n].copy_(dtab._narrow["chrom"][:n])
+            dtab.cols["n_alignments"][:n].copy_(dtab._narrow["n_alignments"][:n])
+            dtab.cols["n_alignments"][:n].bitwise_and_(0xffff)
+        if getattr(ptab, "aln_is_qspan", False):
+            torch.sub(dtab.cols["qend"][:n], dtab.cols["qstart"][:n], out=dtab.cols["aln_size"][:n])
 
     def choose_alignment(self, read_id, alignment_score, cluster, n_clusters):
         """cluster.py:237-254 on the GPU.  read_id/alignment_score: int32 per table row; cluster: int32 per read (dense ids).

@@ -59,7 +59,7 @@ def gather_columns(host_cols, dev_cols, n_rows, rank, world, group=None):
         if hi > lo:
             mine[:hi - lo].copy_(src[lo:hi], non_blocking=True)
         full = torch.empty(chunk * world, dtype=dst.dtype, device=dst.device)
-        dist.all_gather_into_tensor(full, mine, group=group)
+        dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), group=group)   # bytes: any column width
         dst[:n_rows].copy_(full[:n_rows])
 
 
