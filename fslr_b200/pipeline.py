@@ -67,7 +67,7 @@ def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="fslr clustering step on B200 (drop-in for `fslr --skip-alignment`'s clustering block)")
     ap.add_argument("--bed", required=True, help="<base>.mappings.bed")
-    ap.add_argument("--chr-lengths", required=True, help="JSON {chrom: length} (BAM header lengths)")
+    ap.add_argument("--chr-lengths", required=True, help="JSON {chrom: length}, or the <base>.bwa_dodi.bam whose header holds them (main.py:225)")
     ap.add_argument("--out-base", required=True)
     ap.add_argument("--jaccard-cutoffs", default="1,1,0.66,0.66,0.66,0.5")
     ap.add_argument("--overlap", type=float, default=0.8)
@@ -78,11 +78,12 @@ def main(argv=None):
     ap.add_argument("--fast-io", action="store_true", help="parse the TSV and render mappings.cluster.bed on the GPU")
     ap.add_argument("--no-representative", action="store_true")
     a = ap.parse_args(argv)
+    lengths = gcluster.get_chromosome_lengths(a.chr_lengths) if a.chr_lengths.endswith(".bam") else json.load(open(a.chr_lengths))
     if a.fast_io and not a.filter_false:
-        cluster_step_fast(a.bed, json.load(open(a.chr_lengths)), a.out_base, a.cluster_mask, a.jaccard_cutoffs, a.overlap,
+        cluster_step_fast(a.bed, lengths, a.out_base, a.cluster_mask, a.jaccard_cutoffs, a.overlap,
                           a.n_alignment_diff, a.qlen_diff, not a.no_representative)
         return
-    cluster_step(a.bed, json.load(open(a.chr_lengths)), a.cluster_mask, a.jaccard_cutoffs, a.overlap, a.n_alignment_diff,
+    cluster_step(a.bed, lengths, a.cluster_mask, a.jaccard_cutoffs, a.overlap, a.n_alignment_diff,
                  a.qlen_diff, a.filter_false, a.out_base)
 
 

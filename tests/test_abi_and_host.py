@@ -103,3 +103,28 @@ def test_synth_tables_are_well_formed():
     assert (df["aln_size"] > 0).all() and (df["qend"] - df["qstart"] == df["aln_size"]).all()
     rid, n = t.read_ids()
     assert np.array_equal(rid, pd.factorize(df["qname"])[0]) and n == df["qname"].nunique()
+
+
+def test_get_chromosome_lengths_reads_bam_header(tmp_path):
+    """cluster.get_chromosome_lengths (cluster.py:173-175) without pysam: a BAM header split over several BGZF blocks."""
+    import struct
+    import zlib
+    from fslr_b200 import cluster
+    refs = [("chr%d" % i, 1_000_000 + 37 * i) for i in range(1, 60)] + [("L1_TALEN", 8000)]
+    text = b"@HD\tVN:1.6\tSO:unsorted\n" + b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (n.encode(), l) for n, l in refs)
+    raw = b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    for n, l in refs:
+        raw += struct.pack("<i", len(n) + 1) + n.encode() + b"\x00" + struct.pack("<i", l)
+    raw += b"\x00" * 100                                                       # (first bytes of the alignment section)
+
+    def bgzf(chunk):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        data = c.compress(chunk) + c.flush()
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(data) + 25) + data +
+                struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+    path = tmp_path / "t.bam"
+    path.write_bytes(b"".join(bgzf(raw[i:i + 300]) for i in range(0, len(raw), 300)))
+    assert cluster.get_chromosome_lengths(str(path)) == dict(refs)
+    (tmp_path / "bad.bam").write_bytes(b"not a bam file at all, not even gzip")
+    with pytest.raises(ValueError):
+        cluster.get_chromosome_lengths(str(tmp_path / "bad.bam"))
