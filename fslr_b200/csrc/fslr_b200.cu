@@ -252,11 +252,6 @@ __global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *
     if (Ln > 65535) Ln = 65535;
     RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), (int)(((unsigned)o << 6) | (unsigned)((L - 1) & 63)));
 }
-__global__ void k_check_naln(int D, const int *__restrict__ it_q, const int2 *__restrict__ IT1, const int4 *__restrict__ RI, int *err) {
-    int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D && (RI[it_q[d]].z & 0xffff) != IT1[d].y) atomicOr(err, EF_NALN);
-}
-
 // ---------------------------------------------------------------- stage 4/5: IntervalMap order + records + bands
 __global__ void k_end_keys(int D, const int4 *__restrict__ IT0, unsigned *key) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,14 +308,16 @@ __global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
                           const int4 *__restrict__ IT0, const int2 *__restrict__ IT1, const int4 *__restrict__ RI,
                           double overlap, int4 *SR0, int4 *SR1, int *s_m,
-                          int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi) {
+                          int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi, int *err) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= D) return;
     const int d = s_dp[p], m = rmidx[d], q = it_q[d];
     const int4 it = IT0[d];
     const int c = it.y, s = it.z, e = it.w;
-    const int T = thr_f64(max(IT1[d].x, 1), overlap);
+    const int2 i1 = IT1[d];
+    const int T = thr_f64(max(i1.x, 1), overlap);
     const int4 ri = RI[q];
+    if ((ri.z & 0xffff) != i1.y) atomicOr(err, EF_NALN);            // n_alignments must be constant over the rows of a read
     const int fi = m - (int)((unsigned)ri.w >> 6);                   // index of this filling in its read's list
     SR0[p] = make_int4(s, e, T, (int)((unsigned)q | ((unsigned)fi << 26)));
     SR1[p] = ri;
@@ -1582,7 +1579,6 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         int r = sort_pairs(ctx, P, (const unsigned *)it_q, (unsigned *)qs, iotaD, rm_dp, D, 0, bits_for(Q)); if (r) return r;
         KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
         KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RI, P->err);
-        KL(k_check_naln, nblk(D, TB), TB, D, it_q, IT1, P->RI, P->err);
     }
     { int r = mark(ctx, 3); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
@@ -1612,7 +1608,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
         int *s_m; DA(s_m, D);
         KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
-                                               s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi);
+                                               s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi, P->err);
         int r = segmax_scan(ctx, P, P->s_chrom, s_end, P->pmaxS, D); if (r) return r;
         KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM,
            (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14));

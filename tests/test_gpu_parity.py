@@ -94,6 +94,13 @@ def test_errors(engine):
     with pytest.raises(FslrError) as e:
         engine.cluster(bad, p)
     assert e.value.code == -3
+    mixed = ColumnarTable(**{**t.__dict__})
+    mixed.n_alignments = t.n_alignments.copy()
+    rows = np.nonzero(t.n_alignments >= 4)[0]
+    mixed.n_alignments[rows[1]] += 1                               # a filling row whose n_alignments differs from its read's
+    with pytest.raises(FslrError) as e:
+        engine.cluster(mixed, p)
+    assert e.value.code == -5
     empty = ColumnarTable(**{**t.__dict__})
     for k in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments"):
         setattr(empty, k, np.zeros(0, np.int32))
