@@ -1,0 +1,161 @@
+// Part of fslr_b200.cu (one translation unit; included after the error flags, LMAX and fslr_b200.h are defined).
+// Stages 9-10 and the rows around the path: union-find, cluster numbering, choose_alignment, integer-issue microbenchmark.
+#pragma once
+
+// ---------------------------------------------------------------- stage 9: union-find (root = smallest query rank)
+__device__ __forceinline__ int uf_find(int *parent, int x) {
+    for (;;) {
+        int p = *(volatile int *)&parent[x];
+        if (p == x) return x;
+        int gp = *(volatile int *)&parent[p];
+        if (gp != p) atomicMin(&parent[x], gp);                                      // path halving, keeps parent <= index
+        x = p;
+    }
+}
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    for (;;) {
+        a = uf_find(parent, a); b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int tmp = a; a = b; b = tmp; }                                  // hook the larger root under the smaller
+        if (atomicCAS(&parent[a], a, b) == a) return;
+    }
+}
+// entries (a, b) recorded by k_pair: a not saturating; b > a -> a tested it (edge); b < a -> edge only if b is
+// saturating and its scan stopped before reaching a (then a's query tested the pair, direction a -> b)
+__global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP, Tab t,
+                                const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    bool e = false;
+    if (k < n) {
+        const int2 ab = entries[k];
+        const int a = ab.x, b = ab.y;
+        if (a >= 0 && !isP[a]) {
+            if (b > a) e = true;
+            else if (isP[b]) {
+                const int wa = t.RI[a].w, wb = t.RI[b].w;
+                const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
+                e = true;
+                for (int f = 0; f < Lb && e; f++) {
+                    const int4 bf = rm0(t, offb + f);
+                    const int ubf = rm1(t, offb + f).y, sf = stop[offb + f];
+                    for (int g = 0; g < La; g++) {
+                        const int4 ag = rm0(t, offa + g);
+                        const int pg = rm1(t, offa + g).x;
+                        if (ag.x == bf.x && sf <= pg && pg <= ubf && ag.z >= bf.y) { e = false; break; }
+                    }
+                }
+            }
+        }
+        if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); }
+    }
+    const int cnt = __syncthreads_count(e);                                        // one counter update per block
+    if (threadIdx.x == 0 && cnt) atomicAdd(n_edges, (unsigned long long)cnt);
+}
+__global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing, unsigned long long *n_edges) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    bool e = false;
+    if (k < n) {
+        const int2 ab = edges[k];
+        if (ab.x >= 0) {                                                            // skip chunk padding
+            e = true;
+            ing[ab.x] = 1; ing[ab.y] = 1;
+            uf_union(parent, ab.x, ab.y);
+        }
+    }
+    const int cnt = __syncthreads_count(e);
+    if (threadIdx.x == 0 && cnt && n_edges) atomicAdd(n_edges, (unsigned long long)cnt);
+}
+__global__ void k_flatten(int Q, int *parent, const int *__restrict__ ing, int *isroot, int *csize) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int r = uf_find(parent, q);
+    parent[q] = r;                                                                  // safe: r is a root and stays one
+    isroot[q] = (ing[q] && r == q);
+    if (ing[q]) atomicAdd(&csize[r], 1);
+}
+// spanning forest of the local components (multi-GPU exchange)
+__global__ void k_forest(int Q, const int *__restrict__ parent, const int *__restrict__ ing, int2 *forest, unsigned long long *n) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    bool e = q < Q && ing[q] && parent[q] != q;
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    unsigned long long at = 0;
+    if ((threadIdx.x & 31) == 0 && m) at = atomicAdd(n, (unsigned long long)__popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (e) forest[at + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = make_int2(q, parent[q]);
+}
+
+// ---------------------------------------------------------------- stage 10: cluster / n_reads (main.py:251-257,334-342)
+__global__ void k_single_flags(int R, const int *__restrict__ q_of_rid, const int *__restrict__ ing, int *flag) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int q = q_of_rid[r];
+    flag[r] = !(q >= 0 && ing[q]);
+}
+__global__ void k_number(int R, const int *__restrict__ q_of_rid, const int *__restrict__ ing, const int *__restrict__ root,
+                         const int *__restrict__ cidx, const int *__restrict__ csize, const int *__restrict__ spos,
+                         const int64_t *__restrict__ ncl, int *out_cluster, int *out_n) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int q = q_of_rid[r];
+    if (q >= 0 && ing[q]) { int rt = root[q]; out_cluster[r] = cidx[rt]; out_n[r] = csize[rt]; }
+    else { out_cluster[r] = (int)(*ncl) + spos[r]; out_n[r] = 1; }                   // singletons after the clusters, bed order
+}
+
+// ---------------------------------------------------------------- choose_alignment (cluster.py:237-254, main.py:351-352)
+// per read: sum and count of alignment_score over its rows, first row; per cluster: the read with the highest mean
+// (IEEE double division, as pandas' groupby.mean of an integer column), first row in table order on ties (idxmax)
+__device__ __forceinline__ unsigned long long order_f64(double x) {   // monotone map double -> uint64
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__global__ void k_ca_rows(int A, int R, const int *__restrict__ rid, const int *__restrict__ score, long long *sum, int *cnt, int *first, int *err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    const int r = rid[i];
+    if ((unsigned)r >= (unsigned)R) { atomicOr(err, EF_RANGE); return; }
+    atomicAdd((unsigned long long *)&sum[r], (unsigned long long)(long long)score[i]);
+    atomicAdd(&cnt[r], 1);
+    atomicMin(&first[r], i);
+}
+__global__ void k_ca_best(int R, int C, const long long *__restrict__ sum, const int *__restrict__ cnt, const int *__restrict__ cluster,
+                          unsigned long long *best, int *err) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || cnt[r] == 0) return;
+    const int c = cluster[r];
+    if ((unsigned)c >= (unsigned)C) { atomicOr(err, EF_RANGE); return; }
+    atomicMax(&best[c], order_f64(__ddiv_rn((double)sum[r], (double)cnt[r])));
+}
+__global__ void k_ca_first(int R, int C, const long long *__restrict__ sum, const int *__restrict__ cnt, const int *__restrict__ first,
+                           const int *__restrict__ cluster, const unsigned long long *__restrict__ best, int *minrow) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || cnt[r] == 0) return;
+    const int c = cluster[r];
+    if ((unsigned)c >= (unsigned)C) return;
+    if (order_f64(__ddiv_rn((double)sum[r], (double)cnt[r])) == best[c]) atomicMin(&minrow[c], first[r]);
+}
+__global__ void k_ca_flag(int R, int C, const int *__restrict__ cnt, const int *__restrict__ first, const int *__restrict__ cluster,
+                          const int *__restrict__ minrow, unsigned char *is_rep, int *rep_read) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    unsigned char f = 0;
+    if (cnt[r] > 0) {
+        const int c = cluster[r];
+        if ((unsigned)c < (unsigned)C && minrow[c] == first[r]) { f = 1; if (rep_read) rep_read[c] = r; }
+    }
+    is_rep[r] = f;
+}
+
+// ---------------------------------------------------------------- integer-issue microbenchmark (roofline denominator)
+__global__ void k_int_peak(int iters, int *out) {
+    int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 5, a5 = a0 + 7, a6 = a0 + 11, a7 = a0 + 13;
+    const int k = blockIdx.x | 1;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {                                               // 8 independent chains x 2 ops: min/max + add/xor
+            a0 = max(a0 + k, a1) ^ j; a1 = min(a1 - k, a2) ^ j; a2 = max(a2 + k, a3) ^ j; a3 = min(a3 - k, a4) ^ j;
+            a4 = max(a4 + k, a5) ^ j; a5 = min(a5 - k, a6) ^ j; a6 = max(a6 + k, a7) ^ j; a7 = min(a7 - k, a0) ^ j;
+        }
+    }
+    if ((a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7) == 0x12345678) out[0] = a0;
+}

@@ -1,0 +1,281 @@
+// Part of fslr_b200.cu (one translation unit; included after the error flags, LMAX and fslr_b200.h are defined).
+// Kernels of the ingest stages 1-5: keep_fillings, data order + mask, query rank and per-read lists, IntervalMap order,
+// sorted / read-major records and bands.
+#pragma once
+
+// ---------------------------------------------------------------- small utility kernels
+template <typename T>
+__global__ void k_fill(T *p, int64_t n, T v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_widen(int64_t n, const unsigned char *__restrict__ c8, const unsigned short *__restrict__ n16, int *chrom, int *naln,
+                        int *aln, const int *__restrict__ qstart, const int *__restrict__ qend) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (c8) chrom[i] = c8[i];
+    if (n16) naln[i] = n16[i];
+    if (aln) aln[i] = qend[i] - qstart[i];                             // aln_size = qend - qstart (collect_mapping_info.py:88)
+}
+__global__ void k_iota(int *p, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+// exact threshold in the reference's double arithmetic: min{o >= 0 : fl(o/a) >= p}  (cluster.py:133-136,179,181)
+__device__ __forceinline__ int thr_f64(int a, double p) {
+    if (!(p > 0.0)) return 0;
+    double da = (double)a;
+    double x = ceil(__dmul_rn(p, da));
+    if (x >= 2147483000.0) return 2147483647;
+    long long o = (long long)x;
+    while (o > 0 && __ddiv_rn((double)(o - 1), da) >= p) --o;
+    while (__ddiv_rn((double)o, da) < p) ++o;
+    return (int)o;
+}
+
+// ---------------------------------------------------------------- stage 1: keep_fillings (cluster.py:14-31)
+__global__ void k_first_last(int A, int R, const int *__restrict__ rid, int *first, int *last, int *err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    int r = rid[i];
+    if ((unsigned)r >= (unsigned)R) { atomicOr(err, EF_RANGE); return; }
+    atomicMin(&first[r], i);
+    atomicMax(&last[r], i);
+}
+__global__ void k_keep(int A, int R, const int *__restrict__ rid, const int *__restrict__ first, const int *__restrict__ last,
+                       const int *__restrict__ qstart, const int *__restrict__ qend, int *flag, int *qmin, int *qmax) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A) return;
+    int r = rid[i];
+    int keep = 0;
+    if ((unsigned)r < (unsigned)R) {
+        keep = (i != first[r] && i != last[r]);
+        if (keep) { atomicMax(&qmax[r], qend[i]); atomicMin(&qmin[r], qstart[i]); }
+    }
+    flag[i] = keep;
+}
+// fillings in bed order as packed records: FR0[k] = {read_id, chrom, start, end}, FR1[k] = {aln_size, n_alignments}
+// (start/end = min/max of rstart, rend: cluster.py:111-112).  One coalesced pass over the kept rows.
+__global__ void k_fill_records(int A, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ rid,
+                               const int *__restrict__ chrom, const int *__restrict__ rstart, const int *__restrict__ rend,
+                               const int *__restrict__ aln, const int *__restrict__ naln, int n_chrom, int4 *FR0, int2 *FR1, int *err) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A || !flag[i]) return;
+    const int k = pos[i];
+    const int c = chrom[i], rs = rstart[i], re = rend[i];
+    if ((unsigned)c >= (unsigned)n_chrom || min(rs, re) < 0) atomicOr(err, EF_RANGE);
+    FR0[k] = make_int4(rid[i], c, min(rs, re), max(rs, re));
+    FR1[k] = make_int2(aln[i], naln[i]);
+}
+
+// ---------------------------------------------------------------- stage 2: prepare_data + mask (cluster.py:109-121, 89-106)
+__device__ __forceinline__ bool is_masked(const int4 f, int n_chrom, const long long *__restrict__ clen,
+                                          const unsigned char *__restrict__ cmasked, int sub_on, long long subtel) {
+    if ((unsigned)f.y >= (unsigned)n_chrom) return true;
+    bool masked = cmasked[f.y] != 0;                                          // cluster.py:96
+    const long long cl = clen[f.y];
+    if (sub_on && cl > 1000000 && ((long long)f.z < subtel || cl - (long long)f.w < subtel)) masked = true;   // :94,98-100
+    return masked;
+}
+// flags over the fillings taken in the order `perm` (NULL = bed order)
+__global__ void k_mask_flags(int F, const int *__restrict__ perm, const int4 *__restrict__ FR0, int n_chrom,
+                             const long long *__restrict__ clen, const unsigned char *__restrict__ cmasked, int sub_on,
+                             long long subtel, int *flag, int *err) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F) return;
+    int fk = k;
+    if (perm) { fk = perm[k]; if ((unsigned)fk >= (unsigned)F) { atomicOr(err, EF_RANGE); flag[k] = 0; return; } }
+    flag[k] = is_masked(FR0[fk], n_chrom, clen, cmasked, sub_on, subtel) ? 0 : 1;
+}
+// unmasked fillings, compacted: sort key (start) + filling index, or directly the data-order list when perm is given
+__global__ void k_compact_fillings(int F, const int *__restrict__ perm, const int *__restrict__ flag, const int *__restrict__ pos,
+                                   const int4 *__restrict__ FR0, int *key, int *val) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= F || !flag[k]) return;
+    const int fk = perm ? perm[k] : k;
+    const int u = pos[k];
+    if (key) key[u] = FR0[fk].z;
+    val[u] = fk;
+}
+// data items in data order: IT0[d] = {read_id, chrom, start, end}, IT1[d] = {aln_size, n_alignments}
+__global__ void k_build_items(int D, const int *__restrict__ dfill, const int4 *__restrict__ FR0, const int2 *__restrict__ FR1,
+                              int4 *IT0, int2 *IT1, int *firstdp, int *err) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int fk = dfill[d];
+    const int4 f0 = FR0[fk];
+    const int2 f1 = FR1[fk];
+    IT0[d] = f0; IT1[d] = f1;
+    if (f1.x <= 0 || f1.y <= 0) atomicOr(err, EF_ZERO);
+    if (f1.y >= 65535) atomicOr(err, EF_RANGE);
+    atomicMin(&firstdp[f0.x], d);
+}
+
+// ---------------------------------------------------------------- stage 3: query rank (cluster.py:189-191) + per-read lists
+__global__ void k_is_first(int D, const int4 *__restrict__ IT0, const int *__restrict__ firstdp, int *flag) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) flag[d] = (firstdp[IT0[d].x] == d);
+}
+__global__ void k_rank_reads(int R, const int *__restrict__ firstdp, const int *__restrict__ rank_at, int *q_of_rid, int *rid_of_q) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int f = firstdp[r];
+    int q = -1;
+    if (f != 0x7fffffff) { q = rank_at[f]; rid_of_q[q] = r; }
+    q_of_rid[r] = q;
+}
+__global__ void k_item_q(int D, const int4 *__restrict__ IT0, const int *__restrict__ q_of_rid, int *it_q) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) it_q[d] = q_of_rid[IT0[d].x];
+}
+// rm order: items grouped by query rank, data order inside a read
+__global__ void k_read_bounds(int D, const int *__restrict__ qs /*sorted q*/, const int *__restrict__ rm_dp, int *rmidx, int *off, int *len_end) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= D) return;
+    int q = qs[m];
+    rmidx[rm_dp[m]] = m;
+    if (m == 0 || qs[m - 1] != q) off[q] = m;
+    if (m == D - 1 || qs[m + 1] != q) len_end[q] = m + 1;
+}
+// per read: RI[q] = {qlen2, Lq, n_alignments | Ln << 16, off << 6 | (L - 1)}: the ratio thresholds of
+// cluster.py:26-29,178-183 and where the read's fillings live in read-major order
+__global__ void k_read_info(int Q, const int *__restrict__ rid_of_q, const int *__restrict__ off, const int *__restrict__ len_end,
+                            const int *__restrict__ rm_dp, const int2 *__restrict__ IT1, const int *__restrict__ qmin,
+                            const int *__restrict__ qmax, double qlen_c, double naln_c, int4 *RI, int *err) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    int r = rid_of_q[q], o = off[q], L = len_end[q] - o;
+    if (L > LMAX) { atomicOr(err, EF_TOOMANY); L = LMAX; }
+    long long ql = (long long)qmax[r] - (long long)qmin[r];
+    int na = IT1[rm_dp[o]].y;
+    if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
+    if (ql > 0x7fffffffLL) { atomicOr(err, EF_RANGE); ql = 1; }
+    int Ln = thr_f64(na, naln_c);
+    if (Ln > 65535) Ln = 65535;
+    RI[q] = make_int4((int)ql, thr_f64((int)ql, qlen_c), (na & 0xffff) | (Ln << 16), (int)(((unsigned)o << 6) | (unsigned)((L - 1) & 63)));
+}
+// ---------------------------------------------------------------- stage 4/5: IntervalMap order + records + bands
+__global__ void k_end_keys(int D, const int4 *__restrict__ IT0, unsigned *key) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) key[d] = ~(unsigned)IT0[d].w;                        // ascending ~end == end descending
+}
+__global__ void k_gather_key(int D, const int *__restrict__ dp_in, const int4 *__restrict__ IT0, int which, unsigned *key) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < D) { const int4 it = IT0[dp_in[k]]; key[k] = (unsigned)(which ? it.y : it.z); }      // start / chromosome of the item
+}
+// IntervalMap order without sorting by start again: data order is already sorted by start, so a STABLE partition by
+// chromosome yields (chrom, start, data order); what is missing is "end descending" inside runs of equal (chrom, start).
+// Those runs are short (PCR duplicates), and in data order their members sit in one block of equal starts: every item
+// counts, with coalesced neighbour reads, how many members of its run precede it in data order (idx) and how many must
+// precede it in the final order (rank: larger end, or equal end and earlier in data order).  The partition moves the run
+// as a block, so the item's final position is its partition position + (rank - idx).  val[d] = d | (rank - idx + 32) << 26.
+// Runs that do not fit the window raise `overflow` and the caller falls back to the two full radix sorts.
+#define TIE_WIN 48
+__global__ void k_tie_delta(int D, const int4 *__restrict__ IT0, unsigned *ckey, unsigned *val, unsigned long long *overflow, int *err) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int4 me = IT0[d];
+    if (d > 0 && IT0[d - 1].z > me.z) atomicOr(err, EF_RANGE);       // a caller-supplied `order` that does not sort by start
+    int idx = 0, rank = 0;
+    bool ovf = false;
+    for (int k = 1;; k++) {                                          // earlier in data order
+        if (d - k < 0) break;
+        const int4 o = IT0[d - k];
+        if (o.z != me.z) break;
+        if (k > TIE_WIN) { ovf = true; break; }
+        if (o.y == me.y) { idx++; rank += o.w >= me.w; }
+    }
+    for (int k = 1;; k++) {                                          // later in data order
+        if (d + k >= D) break;
+        const int4 o = IT0[d + k];
+        if (o.z != me.z) break;
+        if (k > TIE_WIN) { ovf = true; break; }
+        if (o.y == me.y) rank += o.w > me.w;
+    }
+    if (idx > 31 || rank > 31) ovf = true;
+    if (ovf) { atomicAdd(overflow, 1ull); rank = idx; }
+    ckey[d] = (unsigned)me.y;
+    val[d] = (unsigned)d | ((unsigned)(rank - idx + 32) << 26);
+}
+__global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const unsigned v = val[p];
+    s_dp[p + (int)(v >> 26) - 32] = (int)(v & 0x3ffffffu);
+}
+// SR0[p] = {start, end, T, q | fi << 26} (fi = index of the filling in its read's list); SR1[p] = the read's RI record;
+// RM[2m] = {chrom, start, end, T}, RM[2m+1] = {pos, ub (closed band, replay), lbT, ubT (tight band, pair kernel)}: one
+// 32-byte sector per filling in read-major order, written once by k_bands
+#define QMASK 0x3ffffff
+__global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
+                          const int4 *__restrict__ IT0, const int2 *__restrict__ IT1, const int4 *__restrict__ RI,
+                          double overlap, int4 *SR0, int4 *SR1, int *s_m,
+                          int *s_chrom, int *s_end, int *chrom_lo, int *chrom_hi, int *err) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int d = s_dp[p], m = rmidx[d], q = it_q[d];
+    const int4 it = IT0[d];
+    const int c = it.y, s = it.z, e = it.w;
+    const int2 i1 = IT1[d];
+    const int T = thr_f64(max(i1.x, 1), overlap);
+    const int4 ri = RI[q];
+    if ((ri.z & 0xffff) != i1.y) atomicOr(err, EF_NALN);            // n_alignments must be constant over the rows of a read
+    const int fi = m - (int)((unsigned)ri.w >> 6);                   // index of this filling in its read's list
+    SR0[p] = make_int4(s, e, T, (int)((unsigned)q | ((unsigned)fi << 26)));
+    SR1[p] = ri;
+    s_m[p] = m;
+    s_chrom[p] = c; s_end[p] = e;
+    const int cprev = p > 0 ? IT0[s_dp[p - 1]].y : -1;
+    const int cnext = p < D - 1 ? IT0[s_dp[p + 1]].y : -1;
+    if (cprev != c) chrom_lo[c] = p;
+    if (cnext != c) chrom_hi[c] = p + 1;
+}
+// Bands of sorted position p, and the read-major record of its filling.
+// ub(p): last sorted position on the chromosome with start <= end_p (IntervalMap upper bound), by galloping
+// from p (the band is short: ~2 log2(band) probes instead of log2(D)).  Tight band [lbT, ubT]: the positions whose
+// interval can reciprocally overlap p by >= T_p (cluster.py:157): above p, start <= end_p - T_p (inside [p, ub]); below p,
+// nothing before the first position whose prefix-max end reaches start_p + T_p.
+__global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
+                        const int *__restrict__ pmaxS, const int *__restrict__ chrom_lo, const int *__restrict__ chrom_hi,
+                        int4 *RM, unsigned long long *band_pairs, unsigned long long *tight_pairs) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    long long mine = 0, mineT = 0;
+    if (p < D) {
+        const int4 me = SR0[p];
+        const int c = s_chrom[p];
+        const int e = me.y, lim = chrom_hi[c], clo = chrom_lo[c];
+        int lo = p, step = 1;                                        // invariant: start[lo] <= e
+        while (lo + step < lim && SR0[lo + step].x <= e) { lo += step; step <<= 1; }
+        int hi = min(lo + step, lim);                                // start[hi] > e, or hi == lim
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (SR0[mid].x <= e) lo = mid; else hi = mid; }
+        const long long et = (long long)e - (long long)me.z;        // T = 0 (overlap <= 0): the closed band
+        int tl = p, th = lo + 1;                                     // start[tl] <= et or tl == p; start[th] > et or th == ub + 1
+        while (th - tl > 1) { int mid = (tl + th) >> 1; if ((long long)SR0[mid].x <= et) tl = mid; else th = mid; }
+        const long long st = (long long)me.x + (long long)me.z;
+        int lb = p;
+        if (p > clo && (long long)pmaxS[p - 1] >= st) {
+            lb = p - 1;
+            int stp = 1;                                             // invariant: pmaxS[lb] >= st
+            while (lb - stp >= clo && (long long)pmaxS[lb - stp] >= st) { lb -= stp; stp <<= 1; }
+            int l2 = max(lb - stp, clo - 1);                         // pmaxS[l2] < st, or l2 == clo - 1
+            while (lb - l2 > 1) { int mid = (l2 + lb) >> 1; if ((long long)pmaxS[mid] >= st) lb = mid; else l2 = mid; }
+        }
+        const int m = s_m[p];
+        RM[2 * m] = make_int4(c, me.x, me.y, me.z);
+        RM[2 * m + 1] = make_int4(p, lo, lb, tl);
+        mine = lo - p;
+        mineT = tl - lb;
+    }
+    __shared__ long long s_sum[2][8];                                 // one pair of global atomics per block
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { mine += __shfl_down_sync(0xffffffffu, mine, o); mineT += __shfl_down_sync(0xffffffffu, mineT, o); }
+    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = mine; s_sum[1][threadIdx.x >> 5] = mineT; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long a = 0, b = 0;
+        for (int w = 0; w < 8; w++) { a += s_sum[0][w]; b += s_sum[1][w]; }
+        if (a) atomicAdd(band_pairs, (unsigned long long)a);
+        if (b) atomicAdd(tight_pairs, (unsigned long long)b);
+    }
+}

@@ -1,0 +1,561 @@
+// Part of fslr_b200.cu (one translation unit; included after the error flags, LMAX and fslr_b200.h are defined).
+// Stages 7-8: saturating set, run cutting and the replay of saturating reads in query order (LIST and WALK modes).
+#pragma once
+
+// ---------------------------------------------------------------- stage 7: saturating set
+__global__ void k_compact_flagged(int n, const int *__restrict__ flag, const int *__restrict__ pos, int *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = i;
+}
+
+// ---------------------------------------------------------------- stage 8: replay of saturating reads in query order
+// plist holds the saturating reads in ascending query rank, cut into RUNS of reads that depend on each other (consecutive
+// ranks of one PCR family, k_run_flags).  A GROUP of 8 lanes takes the next run (ticket) and walks its reads back to back,
+// re-running each read's query exactly as cluster.py:197-224 would: per filling, the closed band is walked downwards from
+// ub, 8 sorted positions per step; pairs already seen are skipped, edges counted, and the scan breaks at edge_threshold.
+// All a later query can observe of this is one integer per filling — the position where the scan stopped — published in
+// stop[] (-1 until known).  Whether an earlier-ranked saturating read b "saw" the pair first is a function of b's stops.
+//
+// The kernel is a non-blocking state machine: the 4 groups of a warp advance one step per loop iteration in lock step;
+// a step whose outcome depends on a stop that is not published yet commits only the candidates before it (scan order)
+// and is retried on the next iteration — nobody spins, so groups can never block one another, and a group only ever
+// depends on reads of smaller tickets (held by resident groups) or on earlier reads of its own run.
+#define RG_WARPS 2
+#define RG_GROUPS (RG_WARPS * 4)
+#define RUN_CAP 64
+#define RUN_LONG 1
+#define RP_CHUNK 64             // edge slots a group reserves at a time (>= 8)
+enum { RF_TESTED = 1, RF_REACH = 2, RF_EDGE = 4, RF_UNRES = 8 };
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(int *p, int v) {
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// stop words: >= 0 final stop position of a filling's scan; < 0 while unknown: -2 - x means "every candidate at a
+// position >= x has been visited already" (progress of a long walk), STOP_UNSTARTED = nothing known yet.
+#define STOP_UNSTARTED ((int)0x80000000)
+__device__ __forceinline__ int stop_reached(int v) { return v >= 0 ? v : -2 - v; }   // lowest position known to be visited
+// streak starts: ticket k continues the previous saturating read's streak iff their first fillings reciprocally overlap
+// (same PCR family: they depend on each other).  Also marks the stops of every saturating read as unknown.
+__global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RI, const int4 *__restrict__ RM, int *flag,
+                            int *stop, int *stopS) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nP) return;
+    const int w = RI[plist[k]].w;
+    const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1;
+    for (int j = 0; j < L; j++) { stop[off + j] = STOP_UNSTARTED; stopS[RM[2 * (off + j) + 1].x] = STOP_UNSTARTED; }
+    int f = 1;
+    if (k > 0) {
+        const int4 x = RM[2 * ((unsigned)RI[plist[k - 1]].w >> 6)], y = RM[2 * off];
+        const int ov = min(x.z, y.z) - max(x.y, y.y);
+        if (x.x == y.x && max(ov, 0) >= max(x.w, y.w)) f = 0;
+    }
+    flag[k] = f;
+}
+// runs: a streak of up to RUN_CAP reads is one run (one group walks it back to back: its reads wait on each other
+// anyway); a longer streak is a giant clique whose reads mostly do NOT depend on each other — cut it into runs of RUN_LONG
+__global__ void k_run_cut(int nP, const int *__restrict__ sflag, const int *__restrict__ spos, const int *__restrict__ sstart,
+                          const int64_t *__restrict__ n_streaks, int *rflag) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nP) return;
+    const int sid = spos[k] + sflag[k] - 1;
+    const int start = sstart[sid], end = (sid + 1 < (int)*n_streaks) ? sstart[sid + 1] : nP;
+    const int cap = (end - start) > RUN_CAP ? RUN_LONG : RUN_CAP;
+    rflag[k] = ((k - start) % cap) == 0;
+}
+// sib[p]: where the next filling (cyclic) of p's read sits in sorted order, and the read's filling count
+__global__ void k_sib(int D, const int4 *__restrict__ SR0, const int4 *__restrict__ SR1, const int4 *__restrict__ RM, int *sib) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int w = SR1[p].w;
+    const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1, fi = (int)((unsigned)SR0[p].w >> 26);
+    const int nxt = off + (fi + 1 == L ? 0 : fi + 1);
+    sib[p] = (int)((unsigned)RM[2 * nxt + 1].x | ((unsigned)(L - 1) << 26));
+}
+// Did read b (owner of the interval at sorted position p, b < a) provably see a first through one of its OTHER fillings?
+// Walks b's fillings through the position-indexed sibling ring: sibling at sp saw a's filling fa iff they overlap (closed)
+// and b's scan of the sibling got down to fa's position.  A's fillings (<= 4) are in shared memory.
+__device__ __forceinline__ bool seen_via_sibling(const Tab &t, const int *stopS, int p, const int4 *A0, const int2 *A1, const int2 *Achr, int La) {
+    int sv = __ldg(&t.sib[p]);
+    const int hops = (int)((unsigned)sv >> 26);                                    // L - 1 other fillings
+    if (hops > 3) return false;
+    for (int h = 0; h < hops; h++) {
+        const int sp = sv & QMASK;
+        const int4 c = __ldg(&t.SR0[sp]);
+        const int reached = stop_reached(ld_relaxed(&stopS[sp]));
+#pragma unroll
+        for (int fa = 0; fa < 4; fa++)
+            if (fa < La && sp >= Achr[fa].x && sp < Achr[fa].y && A0[fa].y <= c.y && A0[fa].z >= c.x && reached <= A1[fa].x) return true;
+        sv = __ldg(&t.sib[sp]);
+    }
+    return false;
+}
+// one candidate b of read a's filling scan when either read has more than 4 fillings (lists stay in global memory)
+__device__ __noinline__ int replay_eval_general(const Tab &t, const int *umax, const int *stop, const int *ownStop, int a, int offa, int La, int fi,
+                                                const int4 f, int top, int p, int b, int offb, int Lb) {
+    for (int g = 0; g < Lb; g++) {                                                 // pair already seen earlier in this very query?
+        const int4 bg = rm0(t, offb + g);
+        const int pg = rm1(t, offb + g).x;
+        for (int f2 = 0; f2 < fi; f2++) {
+            const int4 af = rm0(t, offa + f2);
+            if (af.x == bg.x && ownStop[f2] <= pg && pg <= rm1(t, offa + f2).y && bg.z >= af.y) return 0;
+        }
+        if (bg.x == f.x && pg > p && pg <= top && bg.z >= f.y) return 0;
+    }
+    int ffa, ffb;
+    const int n = greedy_ab(t.RM + 2 * offa, La, t.RM + 2 * offb, Lb, &ffa, &ffb);
+    if (n == 0) return RF_TESTED;
+    if (b < a) {                                                                   // b queried first: did its scans get here?
+        bool vis = false, unres = false;
+        for (int g = 0; g < Lb; g++) {
+            const int4 bf = rm0(t, offb + g);
+            const int ubf = rm1(t, offb + g).y;
+            const int sf = ld_relaxed(&stop[offb + g]);
+            for (int fa = 0; fa < La; fa++) {
+                const int4 ag = rm0(t, offa + fa);
+                const int pa = rm1(t, offa + fa).x;
+                if (ag.x == bf.x && pa <= ubf && ag.z >= bf.y) { if (stop_reached(sf) <= pa) vis = true; else if (sf < 0) unres = true; }
+            }
+        }
+        if (vis) return RF_TESTED;
+        if (unres) return RF_TESTED | RF_UNRES;
+    }
+    return RF_TESTED | RF_REACH | ((La + Lb - n) <= umax[n] ? RF_EDGE : 0);
+}
+// Two ways to re-run one read's query:
+//   LIST mode (the normal case): the only candidates that can ever matter to a's query are intervals of reads b that share
+//     a reciprocally overlapping filling pair with a (n_i > 0, cluster.py:216) — everything else is skipped by the reference
+//     before it touches `edges` or the break.  The pair kernel already met and evaluated all of them and left one record
+//     per partner (<= RP_K): the group loads the records and replays every filling's scan over the partners only.  A
+//     partner is first met at its highest interval inside the filling's closed band (key), scan order = descending key,
+//     and the break position follows from a selection over the keys — one step per filling, however long the band is.
+//   WALK mode (reads with too many partners, e.g. a 500k-read hotspot, more than 4 fillings, or --overlap <= 0): the
+//     closed band is walked downwards 8 sorted positions per step and every candidate is evaluated; candidates whose own
+//     scan of that very interval already passed a's filling are skipped on two coalesced loads, 64 positions per step.
+static_assert(RP_K <= RP_CHUNK && 4 * RP_K <= PL_CHUNK, "chunk sizes");
+// group-wide max over the 8 lanes of a group
+__device__ __forceinline__ int gmax8(unsigned gmask, int v) {
+    v = max(v, __shfl_xor_sync(gmask, v, 1)); v = max(v, __shfl_xor_sync(gmask, v, 2)); v = max(v, __shfl_xor_sync(gmask, v, 4));
+    return v;
+}
+// WALK = false: an instantiation without the band-walking code (half the registers, twice the resident groups) for the
+// usual case that every saturating read has partner records
+template <bool ALLMATCH, bool WALK>
+__global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
+                                                           const int *__restrict__ rstart, const int *__restrict__ isP,
+                                                           const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
+                                                           int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
+                                                           unsigned long long cap_pedges, unsigned long long *n_tests, int *err,
+                                                           unsigned long long *dbg) {
+    __shared__ int4 sA0[RG_GROUPS][4];
+    __shared__ int2 sA1[RG_GROUPS][4];
+    __shared__ int sStop[RG_GROUPS][LMAX];
+    __shared__ int4 sP0[RG_GROUPS][RP_K];    // partner records: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}; flags: 1 visited by a,
+    __shared__ int4 sP1[RG_GROUPS][RP_K];    //   4 b saw a first, 8 b did not;  {key[0..3]}
+    __shared__ int sKey[RG_GROUPS][RP_K];    // first-visit position in the current filling's scan
+    __shared__ int2 sAchr[RG_GROUPS][4];     // [chrom_lo, chrom_hi) of a's fillings (sibling test of the WALK mode)
+    __shared__ int s_umax[LMAX + 1];
+    __shared__ int sRecTag[RG_GROUPS][32];   // the reads this group replayed last (direct mapped by rank & 31) and their final
+    __shared__ int4 sRecStop[RG_GROUPS][32]; //   stops: partners of one run mostly look each other up here, not in global memory
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, gsh = lane & 24, grp = w * 4 + (lane >> 3);
+    const unsigned gmask = 0xffu << gsh;
+    // group state (identical in the 8 lanes of a group)
+    int phase = 0;                      // 0 next read, 1 walk: next filling, 2 walk: scanning, 3 finished, 4 list: build, 5 list: filling
+    unsigned tk = 0, tk1 = 0;
+    int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0, posf = 0;
+    int nPart = 0;
+    bool wide = false;
+    int4 ria = make_int4(0, 0, 0, 0), f = make_int4(0, 0, 0, 0);
+    unsigned long long tests = 0, chunk_base = 0;
+    unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
+    int d_fsteps = 0, d_fstall = 0;
+    int chunk_used = RP_CHUNK;
+    for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
+    __syncthreads();
+    for (int k = gl; k < 32; k += 8) sRecTag[grp][k] = -1;
+    for (;;) {
+        __syncwarp();
+        d_iter += lane == 0;
+        if (phase == 0) {
+            if (tk == tk1) {                                                       // run finished: take the next ticket
+                unsigned run = 0;
+                if (gl == 0) run = atomicAdd(ticket, 1u);
+                run = __shfl_sync(gmask, run, gsh);
+                if (run >= (unsigned)nRuns) phase = 3;
+                else {
+                    tk = (unsigned)__ldg(&rstart[run]);
+                    tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
+                }
+            }
+            if (phase == 0) {
+                a = __ldg(&plist[tk]);
+                ria = __ldg(&t.RI[a]);                                             // {qlen2, Lq, naln | Ln << 16, off << 6 | L - 1}
+                offa = (int)((unsigned)ria.w >> 6); La = (ria.w & 63) + 1;
+                fi = 0; edges = 0;
+                if (La <= 4 && gl < La) {
+                    const int4 r0 = rm0(t, offa + gl);
+                    sA0[grp][gl] = r0; sA1[grp][gl] = rm1(t, offa + gl);
+                    if (WALK) sAchr[grp][gl] = make_int2(__ldg(&t.chrom_lo[r0.x]), __ldg(&t.chrom_hi[r0.x]));
+                }
+                phase = 1;
+                const PLInfo pi = plinfo[a];
+                if (!WALK && pi.n < 0) { atomicOr(err, EF_OVERFLOW); phase = 3; }  // (cannot happen: the host picks WALK when such reads exist)
+                if (gl == 0) { sRecTag[grp][a & 31] = La <= 4 ? a : -1; sRecStop[grp][a & 31] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff); }
+                if (!ALLMATCH && pi.n >= 0) {                                      // the pair kernel left a's partner records
+                    nPart = pi.n;
+                    for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {
+                        int4 r0[RP_KL], r1[RP_KL];
+#pragma unroll
+                        for (int k = 0; k < RP_KL; k++) {
+                            const int j = jb + gl + 8 * k;
+                            if (j < nPart) { r0[k] = __ldg(&PL[2 * (pi.off + j)]); r1[k] = __ldg(&PL[2 * (pi.off + j) + 1]); }
+                        }
+#pragma unroll
+                        for (int k = 0; k < RP_KL; k++) {
+                            const int j = jb + gl + 8 * k;
+                            if (j < nPart) {
+                                const int b = r0[k].x & QMASK;
+                                r0[k].w = (b < a && !__ldg(&isP[b])) ? 1 : 0;      // b < a and never breaking: it saw the pair
+                                sP0[grp][j] = r0[k];
+                                sP1[grp][j] = r1[k];
+                            }
+                        }
+                    }
+                    phase = 5;
+                }
+            }
+        }
+        if (__all_sync(FULL, phase == 3)) break;
+        __syncwarp();
+        bool stalled = false;
+        // ------------------------------------------------------------ LIST mode: one filling's scan over the partners
+        if (phase == 5) {
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; posf = sA1[grp][fi].x; }
+            else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
+            lo = __ldg(&t.chrom_lo[f.x]);
+            // pass 1: where does the scan first meet each partner (its highest interval inside the closed band); did an
+            // earlier-ranked partner's own query see a first?  cls: 0 not met, 1 seen, 2 reach, 3 reach + edge, 4 undecided
+            int mxReach = -1, mxUn = -1, nEdge = 0;
+            for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {                        // 32 partners per batch (usually one batch)
+            int4 q0[RP_KL];
+            int keyk[RP_KL], sv[RP_KL][4];
+            bool poll[RP_KL];
+#pragma unroll
+            for (int k = 0; k < RP_KL; k++) {                                      // stage A: keys; who needs b's stops?
+                const int j = jb + gl + 8 * k;
+                keyk[k] = -1; poll[k] = false;
+                q0[k] = make_int4(0, 0, 0, 1);
+                if (j < nPart) {
+                    q0[k] = sP0[grp][j];
+                    if (!(q0[k].w & 1)) {
+                        const int4 r1 = sP1[grp][j];
+                        keyk[k] = fi == 0 ? r1.x : fi == 1 ? r1.y : fi == 2 ? r1.z : r1.w;
+                        poll[k] = keyk[k] >= 0 && (q0[k].x & QMASK) < a && !(q0[k].w & 12);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RP_KL; k++) {                                      // stage B: all the loads, back to back
+                if (poll[k]) {
+                    const int b = q0[k].x & QMASK;
+                    if (sRecTag[grp][b & 31] == b) {                               // replayed by this very group a moment ago
+                        const int4 c = sRecStop[grp][b & 31];
+                        sv[k][0] = c.x; sv[k][1] = c.y; sv[k][2] = c.z; sv[k][3] = c.w;
+                    } else {
+                        const int offb = (int)((unsigned)q0[k].y >> 6), Lb = (q0[k].y & 63) + 1;
+#pragma unroll
+                        for (int g = 0; g < 4; g++)
+                            sv[k][g] = (g < Lb && (((unsigned)q0[k].z >> (4 * g)) & 4u)) ? ld_relaxed(&stop[offb + g]) : 0x7fffffff;
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < RP_KL; k++) {                                      // stage C: did b's own query see a first?
+                const int j = jb + gl + 8 * k;
+                if (poll[k]) {
+                    bool vis = false, unres = false;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const unsigned cgg = ((unsigned)q0[k].z >> (4 * g)) & 15u;
+                        if (cgg & 4u) {
+                            if (stop_reached(sv[k][g]) <= sA1[grp][cgg & 3u].x) vis = true; else if (sv[k][g] < 0) unres = true;
+                        }
+                    }
+                    if (vis) q0[k].w |= 4; else if (!unres) q0[k].w |= 8;
+                    sP0[grp][j].w = q0[k].w;
+                }
+                if (keyk[k] >= 0) {
+                    if ((q0[k].x & QMASK) > a || (q0[k].w & 8)) { mxReach = max(mxReach, keyk[k]); nEdge += (unsigned)q0[k].x >> 31; }
+                    else if (!(q0[k].w & 4)) mxUn = max(mxUn, keyk[k]);
+                }
+                if (j < nPart) sKey[grp][j] = keyk[k];
+            }
+            }
+            __syncwarp(gmask);
+            // the break (cluster.py:223-224): the first reached partner, in scan order, at which `edges` is >= edge_threshold
+            const int need = t.Tedge - edges;
+            int brkkey = -1;
+            if (need <= 0) brkkey = gmax8(gmask, mxReach);
+            else {
+                nEdge += __shfl_xor_sync(gmask, nEdge, 1); nEdge += __shfl_xor_sync(gmask, nEdge, 2); nEdge += __shfl_xor_sync(gmask, nEdge, 4);
+                if (nEdge >= need) {                                               // the need-th highest edge partner
+                    int thr = 0x7fffffff;
+                    for (int r = 0; r < need; r++) {
+                        int m = -1;
+                        for (int j = gl; j < nPart; j += 8) {
+                            const int key = sKey[grp][j];
+                            if (key >= 0 && key < thr) {
+                                const int4 r0 = sP0[grp][j];
+                                if (r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8))) m = max(m, key);
+                            }
+                        }
+                        thr = gmax8(gmask, m);
+                    }
+                    brkkey = thr;
+                }
+            }
+            const int unkey = gmax8(gmask, mxUn);
+            if (gl == 0) d_steps++;
+            if (unkey > brkkey) { stalled = true; if (gl == 0) d_stall++; }        // an undecided partner comes first: retry later
+            else {
+                int ne = 0;
+                for (int j0 = 0; j0 < nPart; j0 += 8) {                            // commit: everything met at or above the break
+                    const int j = j0 + gl;
+                    bool emit = false;
+                    if (j < nPart) {
+                        const int key = sKey[grp][j];
+                        if (key >= 0 && key >= brkkey) {
+                            const int4 r0 = sP0[grp][j];
+                            sP0[grp][j].w = r0.w | 1;                              // a's query has now seen this pair
+                            emit = r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8));
+                        }
+                    }
+                    const unsigned em = (__ballot_sync(gmask, emit) >> gsh) & 0xffu;
+                    if (em) {
+                        const int n = __popc(em);
+                        if (chunk_used + n > RP_CHUNK) {                           // reserve a fresh chunk, pad the old one
+                            for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+                            if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                            chunk_base = __shfl_sync(gmask, chunk_base, gsh);
+                            chunk_used = 0;
+                            if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                        }
+                        if (emit) pedges[chunk_base + chunk_used + __popc(em & ((1u << gl) - 1u))] = make_int2(a, sP0[grp][j].x & QMASK);
+                        chunk_used += n;
+                        ne += n;
+                    }
+                }
+                edges += ne;
+                const int stopf = brkkey >= 0 ? brkkey : lo;
+                if (gl == 0) { st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf); ((int *)&sRecStop[grp][a & 31])[fi] = stopf; }
+                fi++;
+                if (fi == La) { tk++; phase = 0; }
+            }
+        }
+        // ------------------------------------------------------------ WALK mode
+        else if (WALK) {
+        if (phase == 1) {
+            if (La <= 4) { f = sA0[grp][fi]; top = sA1[grp][fi].y; posf = sA1[grp][fi].x; }
+            else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
+            lo = __ldg(&t.chrom_lo[f.x]);
+            base = top;
+            wide = false;
+            phase = 2;
+        }
+        if (phase == 2) {
+            int stopf = -1;                                                        // >= 0: this filling's scan ended there
+            unsigned Ecommit = 0;
+            int b = -1;
+            if (base < lo || __ldg(&t.pmaxS[base]) < f.y) stopf = lo;              // nothing at or below base overlaps the filling
+            else if (wide) {
+                // ---- nothing to do in the last step: skip ahead over candidates that are no candidates at all or whose read
+                // provably saw a first (its scan of this very interval already passed a's filling), 64 positions per step
+                int adv = 64;
+                int wq[8], we[8], ws[8];                                           // all 16 loads of the step are issued before any use
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int p = base - 8 * k - gl;
+                    wq[k] = -1; we[k] = 0; ws[k] = 0;
+                    if (p >= lo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
+                }
+                bool needs[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    needs[k] = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
+                if (t.sib && La <= 4) {                                            // ... or through its other filling (reads of 2 fillings:
+                    int sp[8];                                                     //     the loads of all 8 positions are batched)
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        sp[k] = -1;
+                        if (needs[k] && wq[k] < a) { const int sv = __ldg(&t.sib[base - 8 * k - gl]); if (((unsigned)sv >> 26) == 1u) sp[k] = sv & QMASK; }
+                    }
+                    int cs[8], ce[8], cv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (sp[k] >= 0) { const int4 c = __ldg(&t.SR0[sp[k]]); cs[k] = c.x; ce[k] = c.y; cv[k] = stop_reached(ld_relaxed(&stopS[sp[k]])); }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        if (sp[k] >= 0) {
+#pragma unroll
+                            for (int fa = 0; fa < 4; fa++)
+                                if (fa < La && sp[k] >= sAchr[grp][fa].x && sp[k] < sAchr[grp][fa].y && sA0[grp][fa].y <= ce[k] &&
+                                    sA0[grp][fa].z >= cs[k] && cv[k] <= sA1[grp][fa].x) needs[k] = false;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 7; k >= 0; k--) {
+                    const unsigned nm = (__ballot_sync(gmask, needs[k]) >> gsh) & 0xffu;
+                    if (nm) adv = 8 * k + __ffs(nm) - 1;
+                }
+                base -= adv;
+                if (adv < 64) wide = false;
+                if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                d_fsteps++;
+            }
+            else {
+                const int p = base - gl;
+                int fl = 0;
+                bool cheap = true;                                                 // nothing in this step needed an evaluation
+                if (p >= lo) {
+                    const int4 c0 = __ldg(&t.SR0[p]);
+                    b = c0.w & QMASK;
+                    if (b != a && c0.y >= f.y                                      // closed overlap (start_p <= end_f by p <= ub)
+                        && !(b < a && stop_reached(ld_relaxed(&stopS[p])) <= posf)     // b's scan of this interval passed a: seen
+                        && !(b < a && t.sib && La <= 4 && seen_via_sibling(t, stopS, p, sA0[grp], sA1[grp], sAchr[grp], La))) {
+                    cheap = false;
+                    const int4 c1 = __ldg(&t.SR1[p]);
+                    if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {
+                        const int offb = (int)((unsigned)c1.w >> 6), Lb = (c1.w & 63) + 1;
+                        if (La <= 4 && Lb <= 4) {
+                            // ---- lists in registers, everything unrolled; all loads of this candidate are issued together
+                            const int bP = (b < a) ? __ldg(&isP[b]) : 1;           // b < a and never breaking: it saw the pair
+                            int4 bg[4]; int2 bq[4]; int sb[4];
+#pragma unroll
+                            for (int g = 0; g < 4; g++) {
+                                bg[g] = g < Lb ? rm0(t, offb + g) : make_int4(-2, 0, 0, 0x7fffffff);
+                                bq[g] = g < Lb ? rm1(t, offb + g) : make_int2(-1, -1);
+                                sb[g] = (b < a && g < Lb) ? ld_relaxed(&stop[offb + g]) : 0x7fffffff;
+                            }
+                            if (bP) {
+                                bool met = false;                                  // pair already seen earlier in this very query?
+                                unsigned m[4];
+#pragma unroll
+                                for (int fa = 0; fa < 4; fa++) {
+                                    const int4 af = fa < La ? sA0[grp][fa] : make_int4(-1, 0, 0, 0x7fffffff);
+                                    const int aub = sA1[grp][fa].y, ast = sStop[grp][fa];
+                                    unsigned r = 0;
+#pragma unroll
+                                    for (int g = 0; g < 4; g++) {
+                                        r |= (matchT<ALLMATCH>(af, bg[g]) ? 1u : 0u) << g;
+                                        met |= (fa < fi) && af.x == bg[g].x && ast <= bq[g].x && bq[g].x <= aub && bg[g].z >= af.y;
+                                    }
+                                    m[fa] = r;
+                                }
+#pragma unroll
+                                for (int g = 0; g < 4; g++) met |= bg[g].x == f.x && bq[g].x > p && bq[g].x <= top && bg[g].z >= f.y;
+                                if (!met) {
+                                    unsigned used = 0; int n = 0;
+#pragma unroll
+                                    for (int fa = 0; fa < 4; fa++) { const unsigned av = m[fa] & ~used; if (av) { used |= av & (0u - av); n++; } }
+                                    fl = RF_TESTED;
+                                    if (n > 0) {
+                                        bool vis = false, unres = false;
+                                        if (b < a) {                               // b queried first: did its scans get here?
+#pragma unroll
+                                            for (int g = 0; g < 4; g++) {
+#pragma unroll
+                                                for (int fa = 0; fa < 4; fa++) {
+                                                    const int4 af = fa < La ? sA0[grp][fa] : make_int4(-1, 0, 0, 0);
+                                                    const int pa = sA1[grp][fa].x;
+                                                    if (af.x == bg[g].x && pa <= bq[g].y && af.z >= bg[g].y) {
+                                                        if (stop_reached(sb[g]) <= pa) vis = true; else if (sb[g] < 0) unres = true;
+                                                    }
+                                                }
+                                            }
+                                        }
+                                        if (vis) { }
+                                        else if (unres) fl |= RF_UNRES;
+                                        else fl |= RF_REACH | ((La + Lb - n) <= s_umax[n] ? RF_EDGE : 0);
+                                    }
+                                }
+                            }
+                        } else if (b > a || __ldg(&isP[b])) {
+                            fl = replay_eval_general(t, s_umax, stop, sStop[grp], a, offa, La, fi, f, top, p, b, offb, Lb);
+                        }
+                    }
+                    }
+                }
+                const unsigned U = (__ballot_sync(gmask, fl & RF_UNRES) >> gsh) & 0xffu;
+                const unsigned M = (__ballot_sync(gmask, fl & RF_REACH) >> gsh) & 0xffu;
+                const unsigned E = (__ballot_sync(gmask, fl & RF_EDGE) >> gsh) & 0xffu;
+                const unsigned Tm = (__ballot_sync(gmask, fl & RF_TESTED) >> gsh) & 0xffu;
+                wide = __all_sync(gmask, cheap);
+                const int nres = U ? __ffs(U) - 1 : 8;                             // candidates before the first undecided one
+                const unsigned rmask = (1u << nres) - 1u;
+                int brk = -1;
+                for (unsigned mm = M & rmask; mm; mm &= mm - 1) {                  // cluster.py:219-224 in scan order
+                    const int l = __ffs(mm) - 1;
+                    if (edges + __popc(E & ((2u << l) - 1u)) >= t.Tedge) { brk = l; break; }
+                }
+                const unsigned cmask = brk >= 0 ? ((2u << brk) - 1u) : rmask;
+                Ecommit = E & cmask;
+                if (gl == 0) tests += __popc(Tm & cmask);
+                edges += __popc(Ecommit);
+                if (brk >= 0) stopf = base - brk;
+                else {
+                    base -= nres; stalled = nres == 0;
+                    if (gl == 0 && nres) { st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                }
+                if (gl == 0) { d_steps++; d_stall += stalled; }
+                d_fsteps++; d_fstall += stalled;
+                if (dbg && stalled && d_fstall == 5000 && (U & 1u) && gl == 0) {   // lane 0 is the undecided candidate
+                    if (atomicAdd(dbg + 12, 1ull) == 0) {
+                        const int wb2 = __ldg(&t.SR1[base]).w; const int ob = (int)((unsigned)wb2 >> 6);
+                        dbg[13] = a; dbg[14] = b; dbg[15] = (unsigned)ld_relaxed(&stop[ob]); dbg[16] = (unsigned)ld_relaxed(&stop[ob + 1]);
+                        dbg[17] = base; dbg[18] = top; dbg[19] = posf; dbg[20] = rm1(t, ob).x; dbg[21] = rm1(t, ob + 1).x; dbg[22] = sA1[grp][1].x; dbg[23] = fi;
+                    }
+                }
+            }
+            if (Ecommit) {
+                const int ne = __popc(Ecommit);
+                if (chunk_used + ne > RP_CHUNK) {                                  // reserve a fresh chunk, pad the old one
+                    for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+                    if (gl == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                    chunk_base = __shfl_sync(gmask, chunk_base, gsh);
+                    chunk_used = 0;
+                    if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                }
+                if ((Ecommit >> gl) & 1u) pedges[chunk_base + chunk_used + __popc(Ecommit & ((1u << gl) - 1u))] = make_int2(a, b);
+                chunk_used += ne;
+            }
+            if (stopf >= 0) {                                                      // publish the stop; next filling / read
+                if (gl == 0) {
+                    sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf);
+                    if (La <= 4) ((int *)&sRecStop[grp][a & 31])[fi] = stopf;
+                }
+                if (dbg && gl == 0 && d_fsteps > 2000) {
+                    if (atomicMax(dbg + 4, (unsigned long long)d_fsteps) < (unsigned long long)d_fsteps) {
+                        dbg[5] = a; dbg[6] = fi; dbg[7] = top - lo; dbg[8] = d_fstall; dbg[9] = top - stopf; dbg[10] = edges; dbg[11] = La;
+                    }
+                }
+                d_fsteps = 0; d_fstall = 0;
+                fi++;
+                if (fi == La) { tk++; phase = 0; } else phase = 1;
+            }
+        }
+        }
+        if (__all_sync(FULL, stalled || phase == 3)) { __nanosleep(100); d_sleep += lane == 0; }
+    }
+    if (chunk_used < RP_CHUNK)
+        for (int k = chunk_used + gl; k < RP_CHUNK; k += 8) pedges[chunk_base + k] = make_int2(-1, -1);
+    for (int o = 16; o; o >>= 1) tests += __shfl_down_sync(FULL, tests, o);
+    if (lane == 0 && tests) atomicAdd(n_tests, tests);
+    for (int o = 16; o; o >>= 1) { d_iter += __shfl_down_sync(FULL, d_iter, o); d_steps += __shfl_down_sync(FULL, d_steps, o);
+                                   d_stall += __shfl_down_sync(FULL, d_stall, o); d_sleep += __shfl_down_sync(FULL, d_sleep, o); }
+    if (lane == 0 && dbg) { atomicAdd(dbg, d_iter); atomicAdd(dbg + 1, d_steps); atomicAdd(dbg + 2, d_stall); atomicAdd(dbg + 3, d_sleep); }
+}
