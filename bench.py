@@ -141,6 +141,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--cpu-sample-reads", type=int, default=CPU_SAMPLE_READS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="shard", choices=["shard", "samples"],
+                    help="N > 1: 'shard' = ONE table, pair space sharded over the GPUs (strong scaling, the BASELINE config); "
+                         "'samples' = one table per GPU, no collective on the data path (weak scaling: how a run over many samples scales)")
     ap.add_argument("--e2e-depth", type=int, default=2, help="host-buffer calls in flight for the e2e number (1 = strictly serial)")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -161,19 +164,23 @@ def main():
     ct, params = make_workload(args.config, args.scale)
     R, A = ct.n_reads, ct.n_rows
     dtab = DeviceTable(ct, eng.device)
-    ptab = PinnedTable(ct, compact=world > 1)       # (N = 1: the strictly serial e2e uses int32 columns; the pipelined one compact ones)
+    ptab = PinnedTable(ct, compact=world > 1 and args.mode == "shard")       # (N = 1: the strictly serial e2e uses int32 columns; the pipelined one compact ones)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    samples = world > 1 and args.mode == "samples"
+
     def step_resident():
-        if world > 1:
+        if world > 1 and not samples:
             return eng.run_sharded(dtab, ct, params, rank, world)
         return eng.run_resident(dtab, ct, params)
 
     def step_e2e():
+        if samples:
+            return eng.run_host(ptab, ct, params)
         if world > 1:
             # every rank uploads 1/world of the rows over its own PCIe link; NVLink all-gather rebuilds the columns
             eng.upload_sharded(ptab, dtab, rank, world)
@@ -205,7 +212,7 @@ def main():
     clocks = sampler.stop() if sampler else {}
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
-    e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)" if world == 1 else \
+    e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)" if (world == 1 or samples) else \
         "every rank uploads 1/%d of the rows (23 B/row on the wire), NVLink all-gather of the columns, sharded step, rank 0 downloads the result" % world
     h2d_bytes = ptab.h2d_bytes
     if world == 1 and args.e2e_depth > 1:
@@ -251,8 +258,9 @@ def main():
 
     st = sts[-1]
     stage_ms = {k: float(np.mean([s["stage_ms"][k] for s in sts])) for k in st["stage_ms"]}
-    value = R * args.steps / (ms * 1e-3)
-    e2e = R * args.steps / (ms_e2e * 1e-3)
+    jobs = world if samples else 1                            # tables clustered per step over all ranks
+    value = jobs * R * args.steps / (ms * 1e-3)
+    e2e = jobs * R * args.steps / (ms_e2e * 1e-3)
     peak, peak_kind = load_peaks()
     F, D, Q = st["n_fillings"], st["n_intervals"], st["n_query_reads"]
     # algorithmic HBM bytes per stage: what one pass over the stage's data must move at least once
@@ -289,13 +297,14 @@ def main():
                      "frac": ops / (stage_ms["pair_kernel"] * 1e-3) / ipeak, "ops_per_pair_test": 12 + 7 * Lbar * Lbar,
                      "peak_source": "measured in this run (fslrc_int_peak: 8 independent add/minmax/xor chains per thread)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if samples else "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.config, WORKLOADS[args.config]) + ("" if args.scale == 1.0 else " x%g" % args.scale),
                        "reads": R, "table_rows": A, "fillings": F, "intervals": D,
                        "l2": "inputs larger than L2 (%.2f GB of columns re-read every step)" % (32 * A / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else "table replicated (e2e: upload sharded, NVLink all-gather), pair space sharded by "
-                                                                  "query read over %d GPUs, all-reduce + all-gather of forests" % world},
+                       "parallelism": "1 GPU" if world == 1 else ("one table per GPU on %d GPUs, no data-path collective" % world if samples else
+                                                                  "table replicated (e2e: upload sharded, NVLink all-gather), pair space sharded by "
+                                                                  "query read over %d GPUs, all-reduce + all-gather of forests" % world)},
             "pair_tests_per_s": st["pair_tests"] / (stage_ms["pair_kernel"] + stage_ms["replay"]) * 1e3 if stage_ms["pair_kernel"] > 0 else None,
             "pair_tests": st["pair_tests"], "band_pairs": st["band_pairs"], "edges": st["edges"], "clusters": st["components"],
             "saturating_reads": st["saturating_reads"],
