@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
                 const int p = band.x + ch * 8 + gl;
                 const bool v = fact && (cnt < t.Tedge || nPart >= 0) && p <= band.y;
                 if (!__any_sync(FULL, v)) break;                                    // every group of the warp is through its band
-                int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
-                if (v) c0 = __ldg(&t.SR0[p]);
+                int4 c0 = make_int4(0, 0, 0x7fffffff, -1), c1 = make_int4(0, 0, 0, 0);
+                if (v) { c0 = __ldg(&t.SR0[p]); c1 = __ldg(&t.SR1[p]); }           // both records of the position, one round trip
                 const int b = c0.w & QMASK;
                 bool pass = false, part = false, longb = false;
                 int wb = 0;
@@ -195,7 +195,6 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
                     int2 *hs = &sHash[grp][b & (PK_HASH - 1)];
                     const int2 hv = *hs;
                     if (hv.x != b || hv.y != q) {                                   // not settled earlier in this read's pass
-                        const int4 c1 = __ldg(&t.SR1[p]);
                         bool settled = true;
                         if (difflen_ok(ri.x, ri.y, ri.z, c1.x, c1.y, c1.z)) {
                             wb = c1.w;
