@@ -81,3 +81,54 @@ def test_everything_masked_and_tiny_tables():
     for n in (16, 17, 40):
         tt = ColumnarTable.from_synth(synth.make_table(n, seed=n))
         _check(tt, ClusterParams.from_options(tt))
+
+
+def test_limit_errors():
+    """Documented limits surface as error codes, never as wrong answers."""
+    from fslr_b200._native import FslrError
+    from fslr_b200.engine import get_engine
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    eng = get_engine(0)
+
+    def one_read(n_rows, naln=None, start0=10_000_000):
+        naln = n_rows if naln is None else naln
+        return ColumnarTable(read_id=np.zeros(n_rows, np.int32), chrom=np.zeros(n_rows, np.int32),
+                             rstart=(start0 + 2000 * np.arange(n_rows)).astype(np.int32),
+                             rend=(start0 + 500 + 2000 * np.arange(n_rows)).astype(np.int32), aln_size=np.full(n_rows, 500, np.int32),
+                             qstart=(500 * np.arange(n_rows)).astype(np.int32), qend=(500 * np.arange(n_rows) + 500).astype(np.int32),
+                             n_alignments=np.full(n_rows, naln, np.int32), n_reads=1, chrom_names=["chr1"],
+                             chrom_len=np.array([10**8], np.int64))
+    t = one_read(70)                                                            # 68 fillings > 64
+    with pytest.raises(FslrError) as e:
+        eng.cluster(t, ClusterParams.from_options(t))
+    assert e.value.code == -4
+    t = one_read(66)                                                            # 64 fillings: allowed, a lone read = singleton
+    r = eng.cluster(t, ClusterParams.from_options(t))
+    assert r.no_clusters
+    t = one_read(5, naln=70000)
+    with pytest.raises(FslrError) as e:
+        eng.cluster(t, ClusterParams.from_options(t))
+    assert e.value.code == -7
+    t = one_read(5, start0=-5000)
+    with pytest.raises(FslrError) as e:
+        eng.cluster(t, ClusterParams.from_options(t))
+    assert e.value.code == -7
+    t = one_read(5)
+    t.read_id = np.full(5, 3, np.int32)                                         # read id >= n_reads
+    with pytest.raises(FslrError) as e:
+        eng.cluster(t, ClusterParams.from_options(t))
+    assert e.value.code == -7
+
+
+def test_tsv_header_only_and_single_row():
+    from fslr_b200 import tsv
+    hdr = b"chrom\trstart\trend\tqname\tn_alignments\taln_size\tqstart\tqend\tstrand\tmapq\tqlen\talignment_score\n"
+    pb = tsv.read_mappings_bed(hdr, {"chr1": 1000})
+    assert pb.n_rows == 0 and pb.n_reads == 0 and pb.chrom_names == []
+    pb.close()
+    pb = tsv.read_mappings_bed(hdr + b"chr1\t10\t20\tr1\t3\t10\t0\t10\t+\t60\t30\t20", {"chr1": 1000})
+    assert (pb.n_rows, pb.n_reads, pb.chrom_names) == (1, 1, ["chr1"])
+    assert pb.column("rend").tolist() == [20] and list(pb.qnames()) == ["r1"]
+    res = pb.cluster()
+    assert res.no_clusters
+    pb.close()
