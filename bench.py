@@ -213,14 +213,19 @@ def main():
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
     e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)" if (world == 1 or samples) else \
-        "every rank uploads 1/%d of the rows (23 B/row on the wire), NVLink all-gather of the columns, sharded step, rank 0 downloads the result" % world
+        "every rank uploads 1/%d of the rows (19 B/row on the wire), NVLink all-gather of the columns, sharded step, rank 0 downloads the result" % world
     h2d_bytes = ptab.h2d_bytes
     if world == 1 and args.e2e_depth > 1:
         # the same call, `e2e_depth` in flight: table k+1 uploads while table k computes (fslr_b200.engine.HostPipeline)
         pipe = HostPipeline(local, args.e2e_depth)
         ptabs = [PinnedTable(ct, compact=True) for _ in range(args.e2e_depth)]
         h2d_pipe = ptabs[0].h2d_bytes
-        for f in [pipe.submit(ptabs[i % len(ptabs)], ct, params) for i in range(args.e2e_depth)]:
+        wf = []
+        for i in range(args.e2e_depth * max(args.warmup, 2)):        # warm-up: same submission pattern as the timed loop
+            if i >= len(ptabs):
+                wf[i - len(ptabs)].result()
+            wf.append(pipe.submit(ptabs[i % len(ptabs)], ct, params))
+        for f in wf:
             f.result()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -244,12 +249,13 @@ def main():
             assert np.array_equal(pt.out_cluster[:R].numpy(), ptab.out_cluster[:R].numpy()), "pipelined e2e results disagree"
         assert np.array_equal(ptabs[0].out_cluster[:R].numpy(), ptab.out_cluster[:R].numpy()), "pipelined e2e results disagree"
         pipe.close()
+        print("[bench] e2e: serial %.2f ms/step, %d in flight with compact columns %.2f ms/step" % (ms_e2e / args.steps, args.e2e_depth, ms_pipe / args.steps), file=sys.stderr)
         if ms_pipe < ms_e2e:
             e2e_serial_ms = ms_e2e / args.steps
             ms_e2e = ms_pipe
             h2d_bytes = h2d_pipe
             e2e_mode = "%d C-ABI calls in flight (upload of table k+1 overlaps the kernels of table k), chrom as uint8, n_alignments " \
-                       "as uint16 and aln_size (= qend - qstart) derived on the device: 23 B/row on the wire; one call at a time with int32 columns: %.2f ms/step" % (args.e2e_depth, e2e_serial_ms)
+                       "as uint16, aln_size (= qend - qstart) and read_id (run lengths) rebuilt on the device: 19 B/row on the wire; one call at a time with int32 columns: %.2f ms/step" % (args.e2e_depth, e2e_serial_ms)
 
     # throughput over resident tables with two contexts in flight (the latency-bound replay of one table beside the issue-bound
     # kernels of the next): reported beside `value`, which stays the one-table-at-a-time figure
@@ -257,7 +263,12 @@ def main():
     if world == 1 and args.e2e_depth > 1:
         pipe = HostPipeline(local, 2)
         dts = [dtab, DeviceTable(ct, eng.device)]
-        for f in [pipe.submit_resident(dts[i], ct, params) for i in range(2)]:
+        wf = []
+        for i in range(2 * max(args.warmup, 2)):
+            if i >= 2:
+                wf[i - 2].result()
+            wf.append(pipe.submit_resident(dts[i % 2], ct, params))
+        for f in wf:
             f.result()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

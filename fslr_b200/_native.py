@@ -23,7 +23,7 @@ class Table(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_reads", C.c_int64)] + \
                [(n, C.c_void_p) for n in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments")] + \
                [("order", C.c_void_p), ("n_order", C.c_int64), ("chrom_u8", C.c_void_p), ("n_alignments_u16", C.c_void_p),
-                ("aln_size_is_qspan", C.c_int64)]
+                ("rows_per_read_u8", C.c_void_p), ("aln_size_is_qspan", C.c_int64)]
 
 
 class Params(C.Structure):

@@ -483,7 +483,7 @@ static int check_args(fslrc_ctx *ctx, const fslrc_table *tb, const fslrc_params 
     if (!ctx) return FSLRC_ERR_ARG;
     if (!tb || !pr || !oc || !on) return fail(ctx, FSLRC_ERR_ARG, "null argument");
     if (tb->n_rows < 0 || tb->n_reads < 0 || tb->n_rows > 0x7ffffff0LL || tb->n_reads > 0x7ffffff0LL) return fail(ctx, FSLRC_ERR_ARG, "table size out of range");
-    if (tb->n_rows > 0 && (!tb->read_id || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || !tb->rend || (!tb->aln_size && !oc_host_path_ok(tb)) || !tb->qstart || !tb->qend ||
+    if (tb->n_rows > 0 && ((!tb->read_id && !tb->rows_per_read_u8) || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || !tb->rend || (!tb->aln_size && !oc_host_path_ok(tb)) || !tb->qstart || !tb->qend ||
                            (!tb->n_alignments && !tb->n_alignments_u16)))
         return fail(ctx, FSLRC_ERR_ARG, "null column");
     if (pr->n_chrom < 0 || pr->n_chrom > (1 << 20) || (pr->n_chrom > 0 && (!pr->chrom_len || !pr->chrom_masked))) return fail(ctx, FSLRC_ERR_ARG, "bad chromosome tables");
@@ -563,18 +563,28 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
     const int64_t A = table->n_rows, R = table->n_reads;
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], st);
     fslrc_table d = *table;
+    Pipe P; memset((void *)&P, 0, sizeof(P));
     int32_t *cols[8]; const int32_t *src[8] = {table->read_id, table->chrom, table->rstart, table->rend, table->aln_size,
                                                table->qstart, table->qend, table->n_alignments};
     unsigned char *d_c8 = nullptr; unsigned short *d_n16 = nullptr;
+    if (table->rows_per_read_u8 && A > 0) {
+        // read ids from run lengths: the rows of read r are contiguous and the reads come in id order (verified by the caller)
+        unsigned char *d_r8; int *cnt32, *first;
+        DA(cols[0], A); DA(d_r8, R); DA(cnt32, R); DA(first, R);
+        CK(cudaMemcpyAsync(d_r8, table->rows_per_read_u8, (size_t)R, cudaMemcpyHostToDevice, st));
+        KL(k_widen, nblk(R, 256), 256, R, d_r8, (const unsigned short *)nullptr, cnt32, (int *)nullptr, (int *)nullptr, (const int *)nullptr, (const int *)nullptr);
+        r = xscan(ctx, &P, cnt32, first, (int)R); if (r) return r;
+        KL(k_rid_from_runs, nblk(R, 256), 256, (int)R, (int)A, first, cnt32, cols[0]);
+    }
     for (int c = 0; c < 8; c++) {
-        DA(cols[c], A);
+        if (!(c == 0 && table->rows_per_read_u8 && A > 0)) DA(cols[c], A);
         if (c == 1 && table->chrom_u8) {
             DA(d_c8, A);
             if (A > 0) CK(cudaMemcpyAsync(d_c8, table->chrom_u8, (size_t)A, cudaMemcpyHostToDevice, st));
         } else if (c == 7 && table->n_alignments_u16) {
             DA(d_n16, A);
             if (A > 0) CK(cudaMemcpyAsync(d_n16, table->n_alignments_u16, sizeof(unsigned short) * A, cudaMemcpyHostToDevice, st));
-        } else if (c == 4 && !table->aln_size) {
+        } else if ((c == 4 && !table->aln_size) || (c == 0 && table->rows_per_read_u8)) {
             // derived on the device below
         } else if (A > 0) CK(cudaMemcpyAsync(cols[c], src[c], sizeof(int32_t) * A, cudaMemcpyHostToDevice, st));
     }
@@ -591,7 +601,6 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
     int32_t *d_oc, *d_on;
     DA(d_oc, R); DA(d_on, R);
     CK(cudaEventRecord(ctx->ev[1], st));                                   // closes stage 0 (h2d)
-    Pipe P; memset(&P, 0, sizeof(P));
     P.tb = d; P.pr = *params; P.A = (int)A; P.R = (int)R;
     r = run_device(ctx, &P, d_oc, d_on, stats);
     if (!r && R > 0) {

@@ -17,6 +17,13 @@ __global__ void k_widen(int64_t n, const unsigned char *__restrict__ c8, const u
     if (n16) naln[i] = n16[i];
     if (aln) aln[i] = qend[i] - qstart[i];                             // aln_size = qend - qstart (collect_mapping_info.py:88)
 }
+// read ids from run lengths (host calls with rows_per_read): read r owns the rows [first[r], first[r] + cnt[r])
+__global__ void k_rid_from_runs(int R, int A, const int *__restrict__ first, const int *__restrict__ cnt, int *rid) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int f = first[r], n = cnt[r];
+    for (int j = 0; j < n; j++) if (f + j < A) rid[f + j] = r;
+}
 __global__ void k_iota(int *p, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;

@@ -56,7 +56,8 @@ class DeviceTable:
 class PinnedTable:
     """The table's columns in pinned host memory (the e2e path copies them in every call).  compact=True keeps `chrom` as
     uint8 and `n_alignments` as uint16 when they fit, and leaves out `aln_size` when it equals qend - qstart on every row (what
-    collect_mapping_info.py:88 writes): 23 instead of 32 bytes per row over PCIe, widened / derived on the device."""
+    collect_mapping_info.py:88 writes), and `read_id` when the rows of every read are contiguous and in id order (run lengths
+    travel instead): 19 instead of 32 bytes per row over PCIe, widened / derived on the device."""
 
     def __init__(self, table: ColumnarTable, order=None, compact=False):
         self.n_rows, self.n_reads = table.n_rows, table.n_reads
@@ -66,8 +67,14 @@ class PinnedTable:
                            "n_alignments": torch.from_numpy(np.ascontiguousarray(table.n_alignments).astype(np.uint16).view(np.int16)).pin_memory()}
         self.aln_is_qspan = bool(compact and self.n_rows > 0 and np.array_equal(
             np.asarray(table.aln_size, dtype=np.int64), np.asarray(table.qend, dtype=np.int64) - np.asarray(table.qstart, dtype=np.int64)))
+        self.rows_per_read = None
+        if compact and self.n_rows > 0:                      # rows of a read contiguous, reads in id order: send run lengths
+            rid = np.asarray(table.read_id)
+            cnt = np.bincount(rid, minlength=self.n_reads)
+            if cnt.min(initial=1) >= 1 and cnt.max(initial=0) <= 255 and np.array_equal(rid, np.repeat(np.arange(self.n_reads, dtype=rid.dtype), cnt)):
+                self.rows_per_read = torch.from_numpy(cnt.astype(np.uint8)).pin_memory()
         for k in _COLS:
-            if k in self.narrow or (k == "aln_size" and self.aln_is_qspan):
+            if k in self.narrow or (k == "aln_size" and self.aln_is_qspan) or (k == "read_id" and self.rows_per_read is not None):
                 continue
             t = torch.empty(max(self.n_rows, 1), dtype=torch.int32).pin_memory()
             t[:self.n_rows] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
@@ -81,7 +88,8 @@ class PinnedTable:
     @property
     def h2d_bytes(self):
         per_row = 4 * len(self.cols) + (3 if self.narrow else 0)
-        return per_row * self.n_rows + (4 * int(self.order.numel()) if self.order is not None else 0)
+        return per_row * self.n_rows + (4 * int(self.order.numel()) if self.order is not None else 0) + \
+            (self.n_reads if self.rows_per_read is not None else 0)
 
     @property
     def d2h_bytes(self):
@@ -149,6 +157,8 @@ class Engine:
         t.chrom_u8 = narrow["chrom"].data_ptr() if "chrom" in narrow else None
         t.n_alignments_u16 = narrow["n_alignments"].data_ptr() if "n_alignments" in narrow else None
         t.aln_size_is_qspan = int(bool(getattr(buf, "aln_is_qspan", False)))
+        rpr = getattr(buf, "rows_per_read", None)
+        t.rows_per_read_u8 = rpr.data_ptr() if rpr is not None else None
         if buf.order is not None:
             t.order, t.n_order = buf.order.data_ptr(), int(buf.order.numel())
         else:
@@ -233,6 +243,9 @@ class Engine:
             dtab.cols["n_alignments"][:n].bitwise_and_(0xffff)
         if getattr(ptab, "aln_is_qspan", False):
             torch.sub(dtab.cols["qend"][:n], dtab.cols["qstart"][:n], out=dtab.cols["aln_size"][:n])
+        if getattr(ptab, "rows_per_read", None) is not None:   # run lengths (one byte per read, sent by every rank) -> read ids
+            cnt = ptab.rows_per_read.to(self.device, non_blocking=True).to(torch.int64)
+            dtab.cols["read_id"][:n].copy_(torch.repeat_interleave(torch.arange(cnt.numel(), device=self.device, dtype=torch.int32), cnt))
 
     def choose_alignment(self, read_id, alignment_score, cluster, n_clusters):
         """cluster.py:237-254 on the GPU.  read_id/alignment_score: int32 per table row; cluster: int32 per read (dense ids).

@@ -60,9 +60,12 @@ typedef struct {
     const int32_t *order;
     int64_t n_order;
     /* optional narrow forms of two columns for HOST-buffer calls (fslrc_cluster_host): when non-NULL they replace `chrom` /
-     * `n_alignments` on the wire (27, or 23 without aln_size, instead of 32 bytes per row over PCIe) and are widened on the device. */
+     * `n_alignments` on the wire (down to 19 instead of 32 bytes per row over PCIe) and are widened on the device. */
     const uint8_t *chrom_u8;       /* [n_rows] chromosome id < 256 */
     const uint16_t *n_alignments_u16; /* [n_rows] */
+    const uint8_t *rows_per_read_u8; /* [n_reads] number of rows of every read when the rows of a read are contiguous and the
+                                      reads appear in id order (every count in 1..255); `read_id` may then be NULL in a
+                                      host-buffer call and is rebuilt on the device */
     int64_t aln_size_is_qspan;     /* non-zero: every row has aln_size == qend - qstart (what collect_mapping_info.py:88
                                       writes); `aln_size` may then be NULL in a host-buffer call and is derived on the device */
 } fslrc_table;

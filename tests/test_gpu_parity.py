@@ -143,7 +143,7 @@ def test_narrow_wire_columns_match():
     p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK["C3"])
     eng = get_engine(0)
     wide, narrow = PinnedTable(t), PinnedTable(t, compact=True)
-    assert narrow.narrow and narrow.aln_is_qspan and narrow.h2d_bytes == 23 * t.n_rows
+    assert narrow.narrow and narrow.aln_is_qspan and narrow.rows_per_read is not None and narrow.h2d_bytes == 19 * t.n_rows + t.n_reads
     eng.run_host(wide, t, p)
     eng.run_host(narrow, t, p)
     assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), narrow.out_cluster[:t.n_reads].numpy())
