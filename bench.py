@@ -61,7 +61,7 @@ def cpu_port_run(config, n_reads):
 
 
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu):
@@ -72,7 +72,9 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: wall-clock window (time.time()) of the timed regions; samples outside it are ignored when any fall inside."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -84,6 +86,17 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
+        if t0 is not None:
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    continue
+                if t0 - 0.05 <= ts <= t1 + 0.05:
+                    inside.append(r)
+            if inside:
+                rows = inside
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -205,11 +218,11 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), sts, eng.launch_count() - l0
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local) if rank == 0 else None      # runs across warm-up and every timed region; samples are filtered
+    for _ in range(args.warmup):                              # to the timed window below
         step_resident()
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_first = time.time()
     ms, sts, launches = timed(step_resident, args.steps)
-    clocks = sampler.stop() if sampler else {}
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
     e2e_mode = "one blocking C-ABI call per step (pinned host columns in, host results out)" if (world == 1 or samples) else \
@@ -292,6 +305,8 @@ def main():
         pipe.close()
         del dts
         resident_pipelined = {"depth": 2, "ms_per_step": msp, "value": R / (msp * 1e-3), "unit": UNIT}
+
+    clocks = sampler.stop(t_first, time.time()) if sampler else {}
 
     # correctness guard inside the bench: both paths agree with each other
     res_a = dtab.out_cluster[:R].cpu().numpy()
