@@ -177,9 +177,70 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
     for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
     __syncthreads();
     for (int k = gl; k < 32; k += 8) sRecTag[grp][k] = -1;
+    int wit = 0;
     for (;;) {
         __syncwarp();
         d_iter += lane == 0;
+        wit++;
+        if (WALK) {
+            // ---- every group of this warp that still has work is skipping through a long band (the tail of a giant clique):
+            // serve one of them with all 32 lanes, 256 positions per step (a lone 8-lane walker is instruction-latency bound)
+            const unsigned actm = __ballot_sync(FULL, phase != 3), widem = __ballot_sync(FULL, phase == 2 && wide);
+            if (actm != 0 && widem == actm) {
+                const unsigned gm = ((actm >> 0) & 1u) | (((actm >> 8) & 1u) << 1) | (((actm >> 16) & 1u) << 2) | (((actm >> 24) & 1u) << 3);
+                const int sel = __fns(gm, 0, (wit % __popc(gm)) + 1);              // round robin over the walking groups
+                const int src = sel * 8, wgrp = w * 4 + sel;
+                const int wa = __shfl_sync(FULL, a, src), wlo = __shfl_sync(FULL, lo, src), wbase = __shfl_sync(FULL, base, src);
+                const int wposf = __shfl_sync(FULL, posf, src), wLa = __shfl_sync(FULL, La, src), wfy = __shfl_sync(FULL, f.y, src);
+                if (!(wbase < wlo || __ldg(&t.pmaxS[wbase]) < wfy)) {
+                    int wq[8], we[8], ws[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const int p = wbase - 32 * k - lane;
+                        wq[k] = -1; we[k] = 0; ws[k] = 0;
+                        if (p >= wlo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
+                    }
+                    bool needs[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        needs[k] = wq[k] >= 0 && wq[k] != wa && we[k] >= wfy && !(wq[k] < wa && stop_reached(ws[k]) <= wposf);
+                    if (t.sib && wLa <= 4) {
+                        int sp[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            sp[k] = -1;
+                            if (needs[k] && wq[k] < wa) { const int sv = __ldg(&t.sib[wbase - 32 * k - lane]); if (((unsigned)sv >> 26) == 1u) sp[k] = sv & QMASK; }
+                        }
+                        int cs[8], ce[8], cv[8];
+#pragma unroll
+                        for (int k = 0; k < 8; k++)
+                            if (sp[k] >= 0) { const int4 c = __ldg(&t.SR0[sp[k]]); cs[k] = c.x; ce[k] = c.y; cv[k] = stop_reached(ld_relaxed(&stopS[sp[k]])); }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            if (sp[k] >= 0) {
+#pragma unroll
+                                for (int fa = 0; fa < 4; fa++)
+                                    if (fa < wLa && sp[k] >= sAchr[wgrp][fa].x && sp[k] < sAchr[wgrp][fa].y && sA0[wgrp][fa].y <= ce[k] &&
+                                        sA0[wgrp][fa].z >= cs[k] && cv[k] <= sA1[wgrp][fa].x) needs[k] = false;
+                            }
+                        }
+                    }
+                    int adv = 256;
+#pragma unroll
+                    for (int k = 7; k >= 0; k--) {
+                        const unsigned nm = __ballot_sync(FULL, needs[k]);
+                        if (nm) adv = 32 * k + __ffs(nm) - 1;
+                    }
+                    if ((lane >> 3) == sel) {
+                        base -= adv;
+                        if (adv < 256) wide = false;
+                        if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                        d_fsteps++;
+                    }
+                    continue;
+                }
+            }
+        }
         if (phase == 0) {
             if (tk == tk1) {                                                       // run finished: take the next ticket
                 unsigned run = 0;
