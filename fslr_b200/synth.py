@@ -107,9 +107,14 @@ def _family_sizes(rng, n_reads, mean=4.0):
 
 
 def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_frac=0.0,
-               hotspot_reads=0, hotspot_fillings=2, name="", naln_range=(2, 7)):
-    """Generate `n_reads` reads (`hotspot_reads` of them one giant family)."""
+               hotspot_reads=0, hotspot_fillings=2, name="", naln_range=(2, 7), genome_scale=1.0):
+    """Generate `n_reads` reads (`hotspot_reads` of them one giant family).  `genome_scale` < 1 shortens every nuclear
+    chromosome and the subtelomere window by that factor: n_reads * genome_scale reads on such a genome have the filling
+    density (chance overlaps per filling) of the full-size table — the density-preserving sample bench.py times on the CPU."""
     rng = np.random.default_rng(seed)
+    CHROM_LEN = globals()["CHROM_LEN"].copy()
+    CHROM_LEN[:N_NUCLEAR] = (CHROM_LEN[:N_NUCLEAR] * genome_scale).astype(np.int64)
+    SUBTEL = max(8000, int(globals()["SUBTEL"] * genome_scale))
     primers = list(primers)
     n_bg = n_reads - hotspot_reads
     fam_size = _family_sizes(rng, n_bg) if n_bg > 0 else np.zeros(0, dtype=np.int64)
@@ -196,7 +201,8 @@ def make_table(n_reads, primers=("21q1",), seed=SEED_BASE, subtel_frac=0.0, l1_f
         qlen=qlen[order].astype(np.int32),
         alignment_score=(aln[order] * 9 // 5).astype(np.int32),
         primer=fam_primer[read_fam[row_read]][order].astype(np.int8),
-        primers=primers, name=name, read_id=read_id, n_reads=R)
+        primers=primers, name=name, read_id=read_id, n_reads=R,
+        chr_lengths={n: int(l) for n, l in zip(CHROM_NAMES, CHROM_LEN)})
 
 
 # name -> (generator kwargs, clustering parameters handed to main.py's options)
@@ -212,9 +218,9 @@ CONFIG_MASK = {"C1": "subtelomere", "C2": "subtelomere", "C3": "subtelomere,L1_T
 C3_CUTOFF_SWEEP = ["1,1,0.66,0.66,0.66,0.5", "1,1,1,1,1,1", "1,0.5,0.5,0.5,0.5,0.5", "0.5", "0.34"]
 
 
-def make_config(name, scale=1.0):
-    """Table for a named config; `scale` < 1 shrinks the read counts proportionally (tests)."""
-    kw = dict(CONFIGS[name])
+def make_config(name, scale=1.0, genome_scale=1.0):
+    """Table for a named config; `scale` < 1 shrinks the read counts proportionally (tests); `genome_scale`: see make_table."""
+    kw = dict(CONFIGS[name], genome_scale=genome_scale)
     kw["n_reads"] = max(16, int(round(kw["n_reads"] * scale)))
     if "hotspot_reads" in kw:
         kw["hotspot_reads"] = int(round(kw["hotspot_reads"] * scale))
