@@ -12,7 +12,8 @@ N_STAGES = 12
 SYMBOLS = ["fslrc_create", "fslrc_destroy", "fslrc_last_error", "fslrc_stage_name", "fslrc_version",
            "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_replay",
            "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_choose_alignment_host",
-           "fslrc_tsv_open", "fslrc_tsv_chrom_name", "fslrc_tsv_read_names", "fslrc_tsv_write_cluster_bed", "fslrc_tsv_close"]
+           "fslrc_tsv_open", "fslrc_tsv_chrom_name", "fslrc_tsv_read_names", "fslrc_tsv_write_cluster_bed", "fslrc_tsv_close",
+           "fslrc_bam_open", "fslrc_bam_write_mappings_bed", "fslrc_bam_read_names", "fslrc_bam_close"]
 
 ERRORS = {-1: "FSLRC_ERR_CUDA", -2: "FSLRC_ERR_ARG", -3: "FSLRC_ERR_ZERO_DIVISOR", -4: "FSLRC_ERR_TOO_MANY_FILLINGS",
           -5: "FSLRC_ERR_NALN_NOT_CONSTANT", -6: "FSLRC_ERR_OVERFLOW", -7: "FSLRC_ERR_RANGE", -8: "FSLRC_ERR_HASH_COLLISION"}
@@ -51,6 +52,16 @@ class TsvInfo(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_reads", C.c_int64), ("n_chrom", C.c_int32), ("has_score", C.c_int32)] + \
                [(n, C.c_void_p) for n in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments",
                                           "alignment_score")] + [("parse_ms", C.c_float), ("reserved", C.c_int32)]
+
+
+BAM_COLUMNS = ("read_id", "chrom", "rstart", "rend", "n_alignments", "aln_size", "qstart", "qend", "strand", "mapq", "qlen",
+               "alignment_score", "short_anchor", "inferred_by_primer", "overlaps_region")
+
+
+class BamInfo(C.Structure):
+    _fields_ = [("n_records", C.c_int64), ("n_mapped", C.c_int64), ("n_reads", C.c_int64), ("n_rows", C.c_int64),
+                ("n_chrom", C.c_int32), ("overlaps_as_float", C.c_int32)] + [(n, C.c_void_p) for n in BAM_COLUMNS] + \
+               [("parse_ms", C.c_float), ("reserved", C.c_int32)]
 
 
 class FslrError(RuntimeError):
@@ -94,6 +105,12 @@ def load():
     lib.fslrc_tsv_write_cluster_bed.argtypes = [vp, vp, vp, vp, C.c_int64, i64p, vp]
     lib.fslrc_tsv_close.argtypes = [vp]
     lib.fslrc_tsv_close.restype = None
+    lib.fslrc_bam_open.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_char_p, vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_uint64,
+                                   C.POINTER(BamInfo), vp]
+    lib.fslrc_bam_write_mappings_bed.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_int64, i64p, vp]
+    lib.fslrc_bam_read_names.argtypes = [vp, vp, vp]
+    lib.fslrc_bam_close.argtypes = [vp]
+    lib.fslrc_bam_close.restype = None
     lib.fslrc_launch_count.argtypes = [vp]
     lib.fslrc_launch_count.restype = C.c_longlong
     _lib = lib

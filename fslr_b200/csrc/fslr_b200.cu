@@ -50,10 +50,12 @@ struct fslrc_ctx {
     // pipeline state (kept between the fslrc_mg_* stages)
     struct Pipe *pipe;
     struct TsvState *tsv;    // parsed mappings.bed kept on the device between fslrc_tsv_open and fslrc_tsv_close
+    struct BamState *bam;    // table produced from a BAM file, kept on the device between fslrc_bam_open and fslrc_bam_close
     long long launches;      // kernels of this library launched since fslrc_create
 };
 
 static void tsv_free(fslrc_ctx *ctx);
+static void bam_free(fslrc_ctx *ctx);
 
 static const char *STAGE_NAMES[FSLRC_N_STAGES] = {
     "h2d", "keep_fillings", "data_order_mask", "query_rank_read_lists", "chrom_sort", "records_bands",
@@ -104,6 +106,7 @@ static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 #include "kernels_pair.cuh"
 #include "kernels_replay.cuh"
 #include "kernels_graph.cuh"
+#include "bam.cuh"
 
 // ================================================================ host pipeline
 struct Pipe {
@@ -512,7 +515,7 @@ int fslrc_create(int device, fslrc_ctx **out) {
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); return FSLRC_ERR_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) return FSLRC_ERR_CUDA;
     fslrc_ctx *ctx = new fslrc_ctx();
-    ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->tsv = nullptr; ctx->h_pin = nullptr;
+    ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->tsv = nullptr; ctx->bam = nullptr; ctx->h_pin = nullptr;
     if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
     cudaFuncSetAttribute(prims::k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prims::RsSmem));
@@ -530,6 +533,7 @@ void fslrc_destroy(fslrc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     free_all(ctx);
     tsv_free(ctx);
+    bam_free(ctx);
     cudaDeviceSynchronize();
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -751,17 +755,18 @@ static void tsv_free(fslrc_ctx *ctx) {
     delete ctx->tsv; ctx->tsv = nullptr;
 }
 // strings -> dense ids in order of first appearance (pandas.factorize); *n_ids receives the number of distinct strings
-static int tsv_intern(fslrc_ctx *ctx, Pipe *P, TsvState *T, const long long *off, const int *len, const unsigned long long *hash,
-                      int *id_out, int *first_row_of_id /*nullable, capacity n_rows*/, int *err, int64_t *n_ids_dev) {
+static int tsv_intern(fslrc_ctx *ctx, Pipe *P, const unsigned char *text, int n, const long long *off, const int *len,
+                      const unsigned long long *hash, int *id_out, int *first_row_of_id /*nullable, capacity n*/, int *err,
+                      int64_t *n_ids_dev) {
     cudaStream_t st = ctx->stream;
-    const int n = T->n_rows, TB = 256;
+    const int TB = 256;
     unsigned cap = 1024; while (cap < 2u * (unsigned)n && cap < (1u << 30)) cap <<= 1;
     unsigned long long *keys; int *first, *slot, *isf, *idat;
     DA(keys, cap); DA(first, cap); DA(slot, n); DA(isf, n); DA(idat, n);
     CK(cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * cap, st));
     KL(k_fill<int>, nblk(cap, TB), TB, first, (int64_t)cap, 0x7fffffff);
     KL(tsv::k_tsv_intern_insert, nblk(n, TB), TB, n, hash, keys, first, cap - 1, slot);
-    KL(tsv::k_tsv_intern_verify, nblk(n, TB), TB, n, T->text, off, len, slot, first, isf, err);
+    KL(tsv::k_tsv_intern_verify, nblk(n, TB), TB, n, text, off, len, slot, first, isf, err);
     int r = xscan(ctx, P, isf, idat, n, n_ids_dev); if (r) return r;
     KL(tsv::k_tsv_intern_ids, nblk(n, TB), TB, n, slot, first, idat, id_out, first_row_of_id);
     return 0;
@@ -825,8 +830,8 @@ int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t h
         DA(qh, n); DA(ch, n); DA(coff, n); DA(clen, n); DA(cfirst, n);
         KL(tsv::k_tsv_parse, nblk(n, TB), TB, T->text, T->line_start, n, w, (unsigned long long)hash_seed, T->rstart, T->rend, T->naln, T->aln,
            T->qstart, T->qend, T->score, T->q_off, T->q_len, qh, coff, clen, ch, err);
-        int r = tsv_intern(ctx, P, T, T->q_off, T->q_len, qh, T->read_id, T->first_row, err, dcount + 1); if (r) return r;
-        r = tsv_intern(ctx, P, T, coff, clen, ch, T->chrom, cfirst, err, dcount + 2); if (r) return r;
+        int r = tsv_intern(ctx, P, T->text, n, T->q_off, T->q_len, qh, T->read_id, T->first_row, err, dcount + 1); if (r) return r;
+        r = tsv_intern(ctx, P, T->text, n, coff, clen, ch, T->chrom, cfirst, err, dcount + 2); if (r) return r;
         CK(cudaMemcpyAsync(ctx->h_pin, dcount, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_pin + 8, err, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -923,6 +928,8 @@ void fslrc_tsv_close(fslrc_ctx *ctx) {
     cudaSetDevice(ctx->device);
     tsv_free(ctx);
 }
+
+#include "bam_abi.inl"
 
 long long fslrc_launch_count(const fslrc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

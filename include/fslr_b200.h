@@ -168,6 +168,38 @@ int fslrc_tsv_write_cluster_bed(fslrc_ctx *ctx, const int32_t *cluster_dev, cons
                                 int64_t *n_out, void *stream);
 void fslrc_tsv_close(fslrc_ctx *ctx);
 
+/* ---- The producer of `<base>.mappings.bed`: replaces collect_mapping_info.mapping_info
+ * (/root/reference/fslr/collect_mapping_info.py:19-181; called from main.py:181-183).  `bam` is the UNCOMPRESSED BAM stream
+ * (BGZF blocks inflated by the caller) in host memory; `first_record` is the offset of the first alignment record (after the
+ * header text and the reference list).  Record boundaries are walked on the host, everything else runs on the device:
+ * CIGAR / aux parsing, grouping by read name, the primary record, the missing-bread rule for single-alignment reads, the two
+ * sorts, short_anchor<50bp, region overlaps.  The table stays on the device (rows in the order of :174) until
+ * fslrc_bam_close; `read_id` numbers the reads in order of first appearance in that order, so the columns feed
+ * fslrc_cluster_device directly.  Inputs the reference stops on (no primary record, primary without sequence, no AS tag,
+ * record without CIGAR, read name without two primer tokens, unknown primer) return FSLRC_ERR_ARG with a message. */
+typedef struct {
+    int64_t n_records;             /* alignment records in the file */
+    int64_t n_mapped;              /* of those, without flag 0x4 */
+    int64_t n_reads;               /* distinct read names among them */
+    int64_t n_rows;                /* table rows: mapped records + inferred primer rows */
+    int32_t n_chrom;               /* chrom ids: [0, n_ref) references, n_ref + k = primer k (inferred rows, :124,143) */
+    int32_t overlaps_as_float;     /* regions given and an inferred row exists: pandas holds overlaps_region as float (NaN there) */
+    const int32_t *read_id, *chrom, *rstart, *rend, *n_alignments, *aln_size, *qstart, *qend, *strand /* 1 = '-' */,
+                  *mapq, *qlen, *alignment_score, *short_anchor, *inferred_by_primer, *overlaps_region /* -1 = absent */;  /* device */
+    float parse_ms;
+    int32_t reserved;
+} fslrc_bam_info;
+int fslrc_bam_open(fslrc_ctx *ctx, const uint8_t *bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
+                   const char *primer_names /* n_primers NUL-terminated strings back to back */, const int32_t *primer_seq_len, int32_t n_primers,
+                   const int32_t *region_chrom, const int32_t *region_start, const int32_t *region_end, int32_t n_regions /* -1: no regions file */,
+                   uint64_t hash_seed, fslrc_bam_info *info, void *stream);
+/* Renders the TSV of :176-181.  chrom_names: n_chrom NUL-terminated strings back to back (references, then primers).
+ * With out == NULL only *n_out is computed. */
+int fslrc_bam_write_mappings_bed(fslrc_ctx *ctx, const char *chrom_names, const char *fslr_version, char *out, int64_t cap,
+                                 int64_t *n_out, void *stream);
+int fslrc_bam_read_names(fslrc_ctx *ctx, int64_t *offsets, int32_t *lengths);   /* [n_reads], by read_id: where each qname sits in `bam` */
+void fslrc_bam_close(fslrc_ctx *ctx);
+
 /* Integer-issue microbenchmark used as the pair-kernel roofline denominator: returns the measured
  * dependent-free IADD3/LOP3/VIMNMX lane-ops per second on this device. */
 int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s);

@@ -109,3 +109,29 @@ def reference_sort_order(starts):
     int64 column with numpy's default (unstable) quicksort; same array + same numpy → same order."""
     df = pd.DataFrame({"start": np.asarray(starts, dtype=np.int64)})
     return df.sort_values("start").index.to_numpy()
+
+
+FSLR_VERSION_FOR_TESTS = "0.0.test"
+
+
+def run_reference_mapping_info(bam_path, out_path, regions_path=None, primers=None):
+    """Runs the UNMODIFIED collect_mapping_info.mapping_info (collect_mapping_info.py:19-181) on a BAM file through the
+    stub pysam; `importlib.metadata.version("fslr")` (no installed distribution here) is answered with a constant.
+    Returns None, or the SystemExit / exception the reference ended with (its `quit()` calls, KeyError on a missing tag)."""
+    if not reference_available():
+        raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
+    for p in (_STUBS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import contextlib
+    import io
+    from fslr import collect_mapping_info as cmi
+    cmi.version = lambda name: FSLR_VERSION_FOR_TESTS
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            cmi.mapping_info(bam_path, out_path, regions_path, primers or {})
+    except SystemExit as e:
+        return e
+    except Exception as e:          # noqa: BLE001 - the reference's own failure mode is the thing recorded
+        return e
+    return None

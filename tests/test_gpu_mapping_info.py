@@ -1,0 +1,90 @@
+"""GPU parity of the table-producer row through the C ABI (fslrc_bam_*): the TSV rendered on the
+device must equal, byte for byte, the file the unmodified reference wrote (tests/golden/bam_cases) and, on larger random
+inputs, the oracle restatement; inputs the reference stops on must raise."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES_DIR = os.path.join(ROOT, "tests", "golden", "bam_cases")
+CASES = json.load(open(os.path.join(CASES_DIR, "cases.json")))
+
+
+def _first_diff(got, want):
+    g, w = got.split(b"\n"), want.split(b"\n")
+    for i, (a, b) in enumerate(zip(g, w)):
+        if a != b:
+            return "line %d:\n got %r\nwant %r" % (i, a[:260], b[:260])
+    return "line counts %d / %d" % (len(g), len(w))
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if not CASES[n]["reference_error"]))
+def test_fixture_tsv_is_byte_identical(name):
+    from fslr_b200 import mapping_info as mi
+    c = CASES[name]
+    reg = os.path.join(CASES_DIR, name + ".regions.bed") if c["regions"] else None
+    t = mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), reg, c["primers"])
+    try:
+        got = t.mappings_bed_bytes(c["fslr_version"]).tobytes()
+        want = open(os.path.join(CASES_DIR, name + ".mappings.bed"), "rb").read()
+        assert got == want, _first_diff(got, want)
+        df = t.to_dataframe()
+        assert len(df) == t.n_rows and df["qname"].nunique() == t.n_reads
+        rid = t.column("read_id")
+        assert rid[0] == 0 and (np.diff(rid) >= 0).all() and (np.diff(rid) <= 1).all()      # numbered in output order
+    finally:
+        t.close()
+
+
+@pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["reference_error"]))
+def test_inputs_the_reference_stops_on_raise(name):
+    from fslr_b200 import _native, mapping_info as mi
+    with pytest.raises(_native.FslrError):
+        mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), None, CASES[name]["primers"])
+
+
+@pytest.mark.parametrize("seed,kw", [(21, dict(n_reads=4000)), (22, dict(n_reads=3000, name_style="prefix", p_single=0.6)),
+                                     (23, dict(n_reads=2500, with_seq_on_supp=True, max_aln=12))])
+def test_random_bam_against_oracle(tmp_path, seed, kw):
+    from fslr_b200 import mapping_info as mi, synth_bam as sb
+    from oracle import mapping_info_oracle as mo
+    refs, recs, primers = sb.make_alignments(seed=seed, **kw)
+    bam = str(tmp_path / "t.bam")
+    sb.write_bam(bam, refs, [sb.encode_record(*r) for r in recs])
+    reg = str(tmp_path / "r.bed")
+    open(reg, "w").write("chr1\t1000\t90000000\nchr21\t5\t20000000\nL1_TALEN\t100\t4000\nchr9\t1\t2\n")
+    want = mo.mapping_tsv(mo.mapping_rows(bam, mo.read_regions(reg), primers, "9.9"), True).encode()
+    t = mi.mapping_info(bam, str(tmp_path / "out.bed"), reg, primers, fslr_version="9.9")
+    try:
+        got = open(str(tmp_path / "out.bed"), "rb").read()
+        assert got == want, _first_diff(got, want)
+    finally:
+        t.close()
+
+
+def test_bam_table_feeds_the_clustering_step(tmp_path):
+    """BAM -> device table -> clusters equals BAM -> mappings.bed file -> GPU parse -> clusters."""
+    from fslr_b200 import mapping_info as mi, synth_bam as sb, tsv
+    refs, recs, primers = sb.make_alignments(3000, seed=31, refs=[("chr1", 3_000_000), ("chr2", 2_500_000), ("chr21", 2_000_000)],
+                                             p_single=0.1)
+    bam = str(tmp_path / "t.bam")
+    sb.write_bam(bam, refs, [sb.encode_record(*r) for r in recs])
+    t = mi.mapping_info(bam, str(tmp_path / "m.bed"), None, primers, fslr_version="9.9")
+    lens = dict(refs)
+    try:
+        a = t.cluster(cluster_mask="subtelomere")
+        names_a = t.qnames()
+    finally:
+        t.close()
+    p = tsv.read_mappings_bed(str(tmp_path / "m.bed"), lens)
+    try:
+        b = p.cluster(cluster_mask="subtelomere")
+        names_b = p.qnames()
+    finally:
+        p.close()
+    assert list(names_a) == list(names_b)
+    assert np.array_equal(a.cluster, b.cluster) and np.array_equal(a.n_reads, b.n_reads)

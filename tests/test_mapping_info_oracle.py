@@ -1,0 +1,53 @@
+"""CPU tests of the table-producer row: the oracle restatement of collect_mapping_info.mapping_info
+against the fixtures the unmodified reference produced (tests/golden/make_bam_golden.py), and the host-side BGZF /
+header readers of fslr_b200.mapping_info."""
+import gzip
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mapping_info_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES_DIR = os.path.join(ROOT, "tests", "golden", "bam_cases")
+CASES = json.load(open(os.path.join(CASES_DIR, "cases.json")))
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_fixture(name):
+    c = CASES[name]
+    bam = os.path.join(CASES_DIR, name + ".bam")
+    regions = mo.read_regions(os.path.join(CASES_DIR, name + ".regions.bed")) if c["regions"] else None
+    if c["reference_error"]:
+        with pytest.raises((mo.MappingInfoError, KeyError)):                # err_empty: the reference's KeyError on an empty frame
+            rows = mo.mapping_rows(bam, regions, c["primers"], c["fslr_version"])
+            if not rows:
+                raise KeyError("empty table")
+        return
+    rows = mo.mapping_rows(bam, regions, c["primers"], c["fslr_version"])
+    want = open(os.path.join(CASES_DIR, name + ".mappings.bed")).read()
+    assert mo.mapping_tsv(rows, c["regions"]) == want
+
+
+def test_bgzf_inflate_and_header():
+    from fslr_b200 import mapping_info as mi, synth_bam as sb
+    refs, recs, _ = sb.make_alignments(60, seed=11)
+    b = sb.bam_bytes(refs, [sb.encode_record(*r) for r in recs], block=777)       # many small blocks, one EOF block
+    u = mi.inflate_bgzf(b, threads=4)
+    assert bytes(u) == gzip.decompress(b)
+    got, first = mi.parse_bam_header(u)
+    assert got == list(refs)
+    assert int(np.frombuffer(u[first:first + 4].tobytes(), dtype="<i4")[0]) >= 32     # block_size of the first record
+    with pytest.raises(ValueError):
+        mi.inflate_bgzf(b"not a bam file at all, not even gzip")
+    with pytest.raises(ValueError):
+        mi.inflate_bgzf(b[:len(b) // 2])
+
+
+def test_reference_end_of_an_alignment_without_reference_bases():
+    """htslib's bam_endpos counts a zero reference span as 1 (pysam reference_end); the stub, the oracle and the kernel agree."""
+    rows = mo.mapping_rows(os.path.join(CASES_DIR, "edge.bam"), None, CASES["edge"]["primers"])
+    r = [x for x in rows if x["qname"].startswith("cccc") and not x["inferred_by_primer"]][0]
+    assert (r["rstart"], r["rend"]) == (78, 78)
