@@ -39,6 +39,22 @@ def cluster_step_fast(bed_path, chr_lengths, out_base, cluster_mask="subtelomere
         pb.close()
 
 
+def bam_to_clusters(bam_path, primers, out_base, regions_path=None, fslr_version=None, device=0, **cluster_options):
+    """main.py:181-183 + main.py:190-352 without the table ever being parsed on the host: `<base>.bwa_dodi.bam` ->
+    `<out_base>.mappings.bed` (fslr_b200.mapping_info, the GPU stand-in for collect_mapping_info.mapping_info) ->
+    `<out_base>.mappings.cluster.bed` (+ representative).  The chromosome lengths come from the same BAM header
+    (cluster.py:173-175).  primers: {name: sequence} as main.py:69 builds it from primers.csv."""
+    from . import mapping_info as mi
+    t = mi.read_bam_table(bam_path, regions_path, primers, device=device)
+    try:
+        bed = t.mappings_bed_bytes(fslr_version)
+        lengths = {n: int(l) for n, l in zip(t.chrom_names, t.chrom_len) if l > 0}
+    finally:
+        t.close()
+    bed.tofile(f"{out_base}.mappings.bed")                                       # collect_mapping_info.py:181
+    return cluster_step_fast(bed.tobytes(), lengths, out_base, device=device, **cluster_options)
+
+
 def cluster_step(bed_file, chr_lengths, cluster_mask="subtelomere", jaccard_cutoffs="1,1,0.66,0.66,0.66,0.5", overlap=0.8,
                  n_alignment_diff=0.25, qlen_diff=0.04, filter_false=False, out_base=None, tie_order=None, device=0):
     """Returns the annotated DataFrame, or None when main.py:247-249 would print "No clusters were found." and return."""
@@ -66,8 +82,12 @@ def cluster_step(bed_file, chr_lengths, cluster_mask="subtelomere", jaccard_cuto
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="fslr clustering step on B200 (drop-in for `fslr --skip-alignment`'s clustering block)")
-    ap.add_argument("--bed", required=True, help="<base>.mappings.bed")
-    ap.add_argument("--chr-lengths", required=True, help="JSON {chrom: length}, or the <base>.bwa_dodi.bam whose header holds them (main.py:225)")
+    ap.add_argument("--bed", help="<base>.mappings.bed")
+    ap.add_argument("--bam", help="<base>.bwa_dodi.bam: build mappings.bed on the GPU first (needs --primers-csv and --primers)")
+    ap.add_argument("--primers-csv", help="primers.csv of the fslr installation (columns primer_name, primer_seq; main.py:59)")
+    ap.add_argument("--primers", help="comma-separated primer names (main.py:23)")
+    ap.add_argument("--regions", help="regions BED for the overlaps_region column (collect_mapping_info.py:28-36)")
+    ap.add_argument("--chr-lengths", help="JSON {chrom: length}, or the <base>.bwa_dodi.bam whose header holds them (main.py:225)")
     ap.add_argument("--out-base", required=True)
     ap.add_argument("--jaccard-cutoffs", default="1,1,0.66,0.66,0.66,0.5")
     ap.add_argument("--overlap", type=float, default=0.8)
@@ -78,6 +98,16 @@ def main(argv=None):
     ap.add_argument("--fast-io", action="store_true", help="parse the TSV and render mappings.cluster.bed on the GPU")
     ap.add_argument("--no-representative", action="store_true")
     a = ap.parse_args(argv)
+    if a.bam:
+        d = pd.read_csv(a.primers_csv)
+        want = set(a.primers.split(","))
+        primers = {k: v for k, v in zip(d["primer_name"], d["primer_seq"]) if k in want}       # main.py:69
+        bam_to_clusters(a.bam, primers, a.out_base, a.regions, cluster_mask=a.cluster_mask, jaccard_cutoffs=a.jaccard_cutoffs,
+                        overlap=a.overlap, n_alignment_diff=a.n_alignment_diff, qlen_diff=a.qlen_diff,
+                        representative=not a.no_representative)
+        return
+    if not a.bed or not a.chr_lengths:
+        ap.error("--bed and --chr-lengths are required without --bam")
     lengths = gcluster.get_chromosome_lengths(a.chr_lengths) if a.chr_lengths.endswith(".bam") else json.load(open(a.chr_lengths))
     if a.fast_io and not a.filter_false:
         cluster_step_fast(a.bed, lengths, a.out_base, a.cluster_mask, a.jaccard_cutoffs, a.overlap,

@@ -88,3 +88,22 @@ def test_bam_table_feeds_the_clustering_step(tmp_path):
         p.close()
     assert list(names_a) == list(names_b)
     assert np.array_equal(a.cluster, b.cluster) and np.array_equal(a.n_reads, b.n_reads)
+
+
+def test_bam_to_clusters_writes_the_three_files(tmp_path):
+    import pandas as pd
+    from fslr_b200 import pipeline, synth_bam as sb
+    refs, recs, primers = sb.make_alignments(1500, seed=41, refs=[("chr1", 3_000_000), ("chr2", 2_500_000)], p_single=0.1)
+    bam = str(tmp_path / "t.bam")
+    sb.write_bam(bam, refs, [sb.encode_record(*r) for r in recs])
+    base = str(tmp_path / "s")
+    res = pipeline.bam_to_clusters(bam, primers, base, fslr_version="9.9")
+    bed = pd.read_csv(base + ".mappings.bed", sep="\t")
+    if res is None:
+        return
+    cl = pd.read_csv(base + ".mappings.cluster.bed", sep="\t")
+    assert list(cl.columns) == list(bed.columns) + ["cluster", "n_reads"] and len(cl) == len(bed)
+    assert cl["cluster"].dtype == float and (cl.groupby("qname")["cluster"].nunique() == 1).all()
+    per_read = cl.drop_duplicates("qname")
+    assert (per_read.groupby("cluster").size() == per_read.groupby("cluster")["n_reads"].first()).all()
+    assert os.path.exists(base + ".mappings.representative.bed")
