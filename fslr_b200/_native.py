@@ -13,7 +13,7 @@ SYMBOLS = ["fslrc_create", "fslrc_destroy", "fslrc_last_error", "fslrc_stage_nam
            "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_replay",
            "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_choose_alignment_host",
            "fslrc_tsv_open", "fslrc_tsv_chrom_name", "fslrc_tsv_read_names", "fslrc_tsv_write_cluster_bed", "fslrc_tsv_close",
-           "fslrc_bam_open", "fslrc_bam_write_mappings_bed", "fslrc_bam_read_names", "fslrc_bam_close"]
+           "fslrc_bam_open", "fslrc_bam_open_bgzf", "fslrc_bam_read_stream", "fslrc_bam_write_mappings_bed", "fslrc_bam_read_names", "fslrc_bam_close"]
 
 ERRORS = {-1: "FSLRC_ERR_CUDA", -2: "FSLRC_ERR_ARG", -3: "FSLRC_ERR_ZERO_DIVISOR", -4: "FSLRC_ERR_TOO_MANY_FILLINGS",
           -5: "FSLRC_ERR_NALN_NOT_CONSTANT", -6: "FSLRC_ERR_OVERFLOW", -7: "FSLRC_ERR_RANGE", -8: "FSLRC_ERR_HASH_COLLISION"}
@@ -107,6 +107,8 @@ def load():
     lib.fslrc_tsv_close.restype = None
     lib.fslrc_bam_open.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_char_p, vp, C.c_int32, vp, vp, vp, C.c_int32, C.c_uint64,
                                    C.POINTER(BamInfo), vp]
+    lib.fslrc_bam_open_bgzf.argtypes = lib.fslrc_bam_open.argtypes
+    lib.fslrc_bam_read_stream.argtypes = [vp, vp, C.c_int64, i64p]
     lib.fslrc_bam_write_mappings_bed.argtypes = [vp, C.c_char_p, C.c_char_p, vp, C.c_int64, i64p, vp]
     lib.fslrc_bam_read_names.argtypes = [vp, vp, vp]
     lib.fslrc_bam_close.argtypes = [vp]

@@ -359,3 +359,4 @@ __global__ void k_bam_emit(int N, Emit E, const unsigned char *__restrict__ text
 }
 
 }  // namespace bam
+

@@ -107,6 +107,7 @@ static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 #include "kernels_replay.cuh"
 #include "kernels_graph.cuh"
 #include "bam.cuh"
+#include "bam_chain.cuh"
 
 // ================================================================ host pipeline
 struct Pipe {

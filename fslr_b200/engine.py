@@ -116,6 +116,14 @@ class Engine:
         if rc != 0:
             raise _native.FslrError(rc, "fslrc_create failed")
 
+    def pinned_bytes(self, n):
+        """A pinned uint8 staging buffer of at least n bytes, kept and reused (pinning hundreds of MB costs more than the
+        copy it speeds up).  The returned view is valid until the next call."""
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < n:
+            self._pinned = buf = torch.empty(max(int(n * 1.25), 1 << 20), dtype=torch.uint8).pin_memory()
+        return buf[:max(n, 1)]
+
     def close(self):
         if getattr(self, "ctx", None):
             self.lib.fslrc_destroy(self.ctx)

@@ -2,8 +2,8 @@
 
 `mapping_info(f, outf, regions_path, primers)` has the signature and the output file of
 /root/reference/fslr/collect_mapping_info.py:19-181 (called from main.py:181-183) without pysam: the BGZF blocks are
-inflated on the host (zlib, one task per block on a thread pool — zlib releases the GIL), the uncompressed record stream
-goes to the device once, and everything else — CIGAR and aux parsing, grouping by read name, the primary record, the
+inflated on the DEVICE (fslr_b200/csrc/inflate.cuh: one warp per block, so only the compressed bytes cross PCIe; a host
+zlib thread pool is the `device_inflate=False` alternative), the record boundaries are found there too, and everything else — CIGAR and aux parsing, grouping by read name, the primary record, the
 strand flip of the query interval, the inferred primer rows of single-alignment reads, both sorts, short_anchor<50bp,
 region overlaps, the TSV text with the decoded sequence — runs there (fslr_b200/csrc/bam.cuh).  The table stays on the
 device, so `BamTable.cluster()` runs the clustering step on it without going through the file at all.
@@ -29,7 +29,7 @@ OUT_COLUMNS = ["chrom", "rstart", "rend", "qname", "n_alignments", "aln_size", "
 def inflate_bgzf(path_or_bytes, threads=8):
     """The uncompressed stream of a BGZF file as a uint8 array.  Block sizes come from the `BC` extra field and the ISIZE
     trailer, so every block inflates independently into its final place."""
-    raw = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray, memoryview)) else open(path_or_bytes, "rb").read()
+    raw = path_or_bytes if isinstance(path_or_bytes, (bytes, bytearray, memoryview, np.ndarray)) else open(path_or_bytes, "rb").read()
     mv = memoryview(raw)
     blocks, p, total = [], 0, 0
     while p < len(mv):
@@ -62,6 +62,49 @@ def inflate_bgzf(path_or_bytes, threads=8):
         for b in blocks:
             work(b)
     return out
+
+
+def bgzf_header_prefix(raw, want=None):
+    """Inflate BGZF blocks from the start of `raw` (file bytes) until the BAM header — magic, text, reference list — is
+    complete.  Returns (references, offset of the first alignment record in the inflated stream)."""
+    mv = memoryview(raw)
+    buf = bytearray()
+    p = 0
+
+    def more():
+        nonlocal p
+        if len(mv) - p < 18 or bytes(mv[p:p + 4]) != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a BGZF/BAM file (block header at byte %d)" % p)
+        xlen = struct.unpack_from("<H", mv, p + 10)[0]
+        q, bsize = p + 12, None
+        while q < p + 12 + xlen:
+            slen = struct.unpack_from("<H", mv, q + 2)[0]
+            if mv[q] == 66 and mv[q + 1] == 67 and slen == 2:
+                bsize = struct.unpack_from("<H", mv, q + 4)[0] + 1
+            q += 4 + slen
+        if bsize is None or p + bsize > len(mv):
+            raise ValueError("truncated BGZF block at byte %d" % p)
+        buf.extend(zlib.decompress(mv[p + 12 + xlen:p + bsize - 8], -15))
+        p += bsize
+
+    def need(n):
+        while len(buf) < n:
+            more()
+
+    need(12)
+    if bytes(buf[:4]) != b"BAM\x01":
+        raise ValueError("bad BAM magic")
+    l_text = struct.unpack_from("<i", buf, 4)[0]
+    need(12 + l_text)
+    n_ref = struct.unpack_from("<i", buf, 8 + l_text)[0]
+    q, refs = 12 + l_text, []
+    for _ in range(n_ref):
+        need(q + 4)
+        l = struct.unpack_from("<i", buf, q)[0]
+        need(q + 8 + l)
+        refs.append((bytes(buf[q + 4:q + 4 + l - 1]).decode(), struct.unpack_from("<i", buf, q + 4 + l)[0]))
+        q += 8 + l
+    return refs, q
 
 
 def parse_bam_header(buf):
@@ -131,13 +174,22 @@ class BamTable:
         """Host copy of one column (int32)."""
         return self.columns[name].cpu().numpy()
 
+    def _stream(self):
+        """The inflated BAM stream on the host (fetched from the device when the file was inflated there)."""
+        if self._data is None:
+            n = C.c_int64()
+            self.engine._check(self.engine.lib.fslrc_bam_read_stream(self.engine.ctx, None, 0, C.byref(n)))
+            self._data = np.empty(n.value, dtype=np.uint8)
+            self.engine._check(self.engine.lib.fslrc_bam_read_stream(self.engine.ctx, self._data.ctypes.data, n.value, C.byref(n)))
+        return self._data
+
     def qnames(self):
         """qname of every read id (reads numbered in output order)."""
         if self._names is None:
             off = np.zeros(max(self.n_reads, 1), dtype=np.int64)
             ln = np.zeros(max(self.n_reads, 1), dtype=np.int32)
             self.engine._check(self.engine.lib.fslrc_bam_read_names(self.engine.ctx, off.ctypes.data, ln.ctypes.data))
-            buf = self._data.tobytes()
+            buf = self._stream().tobytes()
             self._names = np.array([buf[o:o + l].decode() for o, l in zip(off[:self.n_reads], ln[:self.n_reads])], dtype=object)
         return self._names
 
@@ -165,7 +217,7 @@ class BamTable:
         stream = C.c_void_p(torch.cuda.current_stream(self.engine.device).cuda_stream)
         n = C.c_int64()
         self.engine._check(lib.fslrc_bam_write_mappings_bed(ctx, names, ver, None, 0, C.byref(n), stream))
-        out = torch.empty(max(n.value, 1), dtype=torch.uint8).pin_memory()
+        out = self.engine.pinned_bytes(n.value)       # reused staging buffer: the result is valid until the next rendering call
         self.engine._check(lib.fslrc_bam_write_mappings_bed(ctx, names, ver, out.data_ptr(), n.value, C.byref(n), stream))
         return out[:n.value].numpy()
 
@@ -185,13 +237,24 @@ class BamTable:
             self.engine = None
 
 
-def read_bam_table(bam, regions_path=None, primers=None, device=0, hash_seed=0, threads=8):
-    """Build the mappings table on the GPU.  bam: path, BGZF bytes, or an already inflated uint8 array.
+def read_bam_table(bam, regions_path=None, primers=None, device=0, hash_seed=0, threads=8, device_inflate=True):
+    """Build the mappings table on the GPU.  bam: path or BGZF bytes (inflated on the device when device_inflate, else with
+    zlib on `threads` host threads), or an already inflated uint8 array.
     primers: {name: sequence} (main.py hands the parsed primer file); only the sequence lengths are used (:133,151)."""
     eng = get_engine(device)
-    data = bam if isinstance(bam, np.ndarray) else inflate_bgzf(bam, threads)
-    data = np.ascontiguousarray(data, dtype=np.uint8)
-    refs, first = parse_bam_header(data)
+    inflated = isinstance(bam, np.ndarray)
+    if inflated:
+        data = np.ascontiguousarray(bam, dtype=np.uint8)
+        refs, first = parse_bam_header(data)
+    else:
+        raw = bam if isinstance(bam, (bytes, bytearray, memoryview)) else np.fromfile(bam, dtype=np.uint8)
+        if device_inflate:
+            data = raw if isinstance(raw, np.ndarray) else np.frombuffer(raw, dtype=np.uint8)
+            refs, first = bgzf_header_prefix(data)
+        else:
+            data = inflate_bgzf(raw, threads)
+            refs, first = parse_bam_header(data)
+            inflated = True
     primers = dict(primers or {})
     pnames = list(primers)
     if any(not n or "\x00" in n for n in pnames):
@@ -209,13 +272,14 @@ def read_bam_table(bam, regions_path=None, primers=None, device=0, hash_seed=0, 
     info = _native.BamInfo()
     stream = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
     names = b"".join(n.encode() + b"\x00" for n in pnames)
+    fn = eng.lib.fslrc_bam_open if inflated else eng.lib.fslrc_bam_open_bgzf
     for attempt in range(4):                                             # a 64-bit hash collision between two names: reseed
-        code = eng.lib.fslrc_bam_open(eng.ctx, data.ctypes.data, data.shape[0], first, len(refs), names, plen.ctypes.data, len(pnames),
-                                      rc.ctypes.data, rs.ctypes.data, re_.ctypes.data, n_regions, hash_seed + attempt, C.byref(info), stream)
+        code = fn(eng.ctx, data.ctypes.data, data.shape[0], first, len(refs), names, plen.ctypes.data, len(pnames),
+                  rc.ctypes.data, rs.ctypes.data, re_.ctypes.data, n_regions, hash_seed + attempt, C.byref(info), stream)
         if code != _native.ERR_HASH_COLLISION:
             break
     eng._check(code)
-    return BamTable(eng, data, info, refs, pnames, n_regions >= 0)
+    return BamTable(eng, data if inflated else None, info, refs, pnames, n_regions >= 0)
 
 
 def mapping_info(f, outf, regions_path, primers, fslr_version=None, device=0):

@@ -72,7 +72,7 @@ class ParsedBed:
         n = C.c_int64()
         self.engine._check(lib.fslrc_tsv_write_cluster_bed(ctx, self.out_cluster.data_ptr(), self.out_n_reads.data_ptr(), None, 0,
                                                           C.byref(n), stream))
-        out = torch.empty(max(n.value, 1), dtype=torch.uint8).pin_memory()
+        out = self.engine.pinned_bytes(n.value)       # reused staging buffer: the result is valid until the next rendering call
         self.engine._check(lib.fslrc_tsv_write_cluster_bed(ctx, self.out_cluster.data_ptr(), self.out_n_reads.data_ptr(), out.data_ptr(),
                                                           n.value, C.byref(n), stream))
         return out[:n.value].numpy()

@@ -193,6 +193,15 @@ int fslrc_bam_open(fslrc_ctx *ctx, const uint8_t *bam, int64_t n_bytes, int64_t 
                    const char *primer_names /* n_primers NUL-terminated strings back to back */, const int32_t *primer_seq_len, int32_t n_primers,
                    const int32_t *region_chrom, const int32_t *region_start, const int32_t *region_end, int32_t n_regions /* -1: no regions file */,
                    uint64_t hash_seed, fslrc_bam_info *info, void *stream);
+/* The same from the COMPRESSED file bytes: BGZF blocks are inflated on the device (one warp per block) and the record
+ * boundaries are found there as well, so only the compressed bytes cross PCIe.  first_record / n_ref come from the caller's
+ * parse of the BAM header (the first blocks).  info->reserved is 1 when the device's record-boundary guess failed its chain
+ * check and the host walk ran instead (same result).  CRC32 trailers are not verified; ISIZE is. */
+int fslrc_bam_open_bgzf(fslrc_ctx *ctx, const uint8_t *file, int64_t n_bytes, int64_t first_record, int32_t n_ref,
+                        const char *primer_names, const int32_t *primer_seq_len, int32_t n_primers,
+                        const int32_t *region_chrom, const int32_t *region_start, const int32_t *region_end, int32_t n_regions,
+                        uint64_t hash_seed, fslrc_bam_info *info, void *stream);
+int fslrc_bam_read_stream(fslrc_ctx *ctx, uint8_t *out, int64_t cap, int64_t *n);   /* the inflated stream (read names live there) */
 /* Renders the TSV of :176-181.  chrom_names: n_chrom NUL-terminated strings back to back (references, then primers).
  * With out == NULL only *n_out is computed. */
 int fslrc_bam_write_mappings_bed(fslrc_ctx *ctx, const char *chrom_names, const char *fslr_version, char *out, int64_t cap,

@@ -22,12 +22,13 @@ def _first_diff(got, want):
     return "line counts %d / %d" % (len(g), len(w))
 
 
+@pytest.mark.parametrize("device_inflate", [True, False])
 @pytest.mark.parametrize("name", sorted(n for n in CASES if not CASES[n]["reference_error"]))
-def test_fixture_tsv_is_byte_identical(name):
+def test_fixture_tsv_is_byte_identical(name, device_inflate):
     from fslr_b200 import mapping_info as mi
     c = CASES[name]
     reg = os.path.join(CASES_DIR, name + ".regions.bed") if c["regions"] else None
-    t = mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), reg, c["primers"])
+    t = mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), reg, c["primers"], device_inflate=device_inflate)
     try:
         got = t.mappings_bed_bytes(c["fslr_version"]).tobytes()
         want = open(os.path.join(CASES_DIR, name + ".mappings.bed"), "rb").read()
@@ -43,8 +44,9 @@ def test_fixture_tsv_is_byte_identical(name):
 @pytest.mark.parametrize("name", sorted(n for n in CASES if CASES[n]["reference_error"]))
 def test_inputs_the_reference_stops_on_raise(name):
     from fslr_b200 import _native, mapping_info as mi
-    with pytest.raises(_native.FslrError):
-        mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), None, CASES[name]["primers"])
+    for device_inflate in (True, False):
+        with pytest.raises(_native.FslrError):
+            mi.read_bam_table(os.path.join(CASES_DIR, name + ".bam"), None, CASES[name]["primers"], device_inflate=device_inflate)
 
 
 @pytest.mark.parametrize("seed,kw", [(21, dict(n_reads=4000)), (22, dict(n_reads=3000, name_style="prefix", p_single=0.6)),
@@ -107,3 +109,37 @@ def test_bam_to_clusters_writes_the_three_files(tmp_path):
     per_read = cl.drop_duplicates("qname")
     assert (per_read.groupby("cluster").size() == per_read.groupby("cluster")["n_reads"].first()).all()
     assert os.path.exists(base + ".mappings.representative.bed")
+
+
+@pytest.mark.parametrize("level,block,force_host_walk", [(0, 60000, False), (1, 5000, False), (9, 65280, False), (6, 60000, True)])
+def test_device_inflate_and_record_finder(tmp_path, monkeypatch, level, block, force_host_walk):
+    """Stored / fast / best DEFLATE blocks of several sizes through the device decoder and the device record-boundary
+    finder give the table the host-inflated path gives; the host-walk fallback of a failed chain check is forced once."""
+    from fslr_b200 import mapping_info as mi, synth_bam as sb
+    refs, recs, primers = sb.make_alignments(2500, seed=50 + level, p_unmapped=0.2)
+    raw = sb.bam_bytes(refs, [sb.encode_record(*r) for r in recs], block=block, level=level)
+    a = mi.read_bam_table(raw, None, primers, device_inflate=False)
+    want = a.mappings_bed_bytes("9.9").tobytes()
+    names = list(a.qnames())
+    a.close()
+    if force_host_walk:
+        monkeypatch.setenv("FSLRC_BAM_FORCE_HOST_WALK", "1")
+    b = mi.read_bam_table(raw, None, primers, device_inflate=True)
+    try:
+        assert int(b.info.reserved) == int(force_host_walk)
+        assert (b.n_records, b.n_mapped) == (len(recs), sum(1 for r in recs if not r[1] & 4))
+        got = b.mappings_bed_bytes("9.9").tobytes()
+        assert got == want, _first_diff(got, want)
+        assert list(b.qnames()) == names
+    finally:
+        b.close()
+
+
+def test_corrupt_bgzf_payload_is_reported():
+    from fslr_b200 import _native, mapping_info as mi, synth_bam as sb
+    refs, recs, primers = sb.make_alignments(200, seed=60)
+    raw = bytearray(sb.bam_bytes(refs, [sb.encode_record(*r) for r in recs], level=6))
+    for k in range(len(raw) // 2, len(raw) // 2 + 40):
+        raw[k] ^= 0x5a
+    with pytest.raises((_native.FslrError, ValueError)):
+        mi.read_bam_table(bytes(raw), None, primers, device_inflate=True)
