@@ -25,6 +25,12 @@ struct Bits {                      // LSB-first bit reader over [in, in + n)
 };
 FSLR_HD void bits_init(Bits &b, const unsigned char *in, long long n) { b.in = in; b.n = n; b.pos = 0; b.buf = 0; b.cnt = 0; b.err = 0; }
 FSLR_HD void bits_fill(Bits &b) {
+    if (b.cnt <= 32 && b.pos + 4 <= b.n) {               // four independent byte loads: one memory latency, not four
+        const unsigned char *p = b.in + b.pos;
+        const unsigned v = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+        b.buf |= (unsigned long long)v << b.cnt; b.cnt += 32; b.pos += 4;
+        return;
+    }
     while (b.cnt <= 56 && b.pos < b.n) { b.buf |= (unsigned long long)b.in[b.pos++] << b.cnt; b.cnt += 8; }
 }
 FSLR_HD unsigned bits_get(Bits &b, int need) {          // need <= 16
@@ -36,7 +42,7 @@ FSLR_HD unsigned bits_get(Bits &b, int need) {          // need <= 16
 
 // canonical Huffman code: count[l] codes of length l, symbols ordered by (length, symbol value)
 struct Huff {
-    unsigned short count[16];
+    unsigned short *count;         // [16]
     unsigned short *symbol;
 };
 // returns 0 for a complete code, >0 for an incomplete one, <0 for an over-subscribed one
@@ -69,10 +75,31 @@ FSLR_HD int huff_decode(Bits &b, const Huff &h) {
     return -1;
 }
 
+constexpr int LBITS = 10, DBITS = 8;   // codes up to this many bits decode with one table lookup
 struct Work {                      // per-decoder scratch (shared memory on the device)
-    unsigned short lsym[288], dsym[32];
+    unsigned short lsym[288], dsym[32], lcount[16], dcount[16];
+    unsigned short ltab[1 << LBITS], dtab[1 << DBITS];   // (symbol << 4) | code length, 0 = longer code: walk the lengths
     unsigned char len[320];
 };
+// the table entry of the bit pattern `idx` (as it would sit in the low bits of the bit buffer)
+FSLR_HD unsigned short tab_entry(const Huff &h, unsigned idx, int K) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= K; l++) {
+        code |= (int)(idx & 1u); idx >>= 1;
+        const int c = h.count[l];
+        if (code - c < first) return (unsigned short)((h.symbol[index + (code - first)] << 4) | l);
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return 0;
+}
+FSLR_HD int huff_decode(Bits &b, const Huff &h);
+FSLR_HD int decode_fast(Bits &b, const Huff &h, const unsigned short *tab, int K) {
+    if (b.cnt < 15) bits_fill(b);
+    const unsigned e = tab[(unsigned)b.buf & ((1u << K) - 1u)];
+    const int l = (int)(e & 15u);
+    if (l && l <= b.cnt) { b.buf >>= l; b.cnt -= l; return (int)(e >> 4); }
+    return huff_decode(b, h);
+}
 
 // length codes 257..285 and distance codes 0..29 (RFC 1951 3.2.5) in closed form; s = symbol - 257 for lengths
 FSLR_HD int extra_len(int s) { return s < 8 || s == 28 ? 0 : (s - 4) >> 2; }
@@ -143,7 +170,7 @@ FSLR_HD int inflate_stream(const unsigned char *in, long long n_in, unsigned cha
             continue;
         }
         if (type == 3) return INF_BADBLOCK;
-        Huff hl, hd; hl.symbol = w.lsym; hd.symbol = w.dsym;
+        Huff hl, hd; hl.symbol = w.lsym; hd.symbol = w.dsym; hl.count = w.lcount; hd.count = w.dcount;
 #if INF_WARP
         if (lane == 0) {
 #endif
@@ -163,7 +190,7 @@ FSLR_HD int inflate_stream(const unsigned char *in, long long n_in, unsigned cha
             else {
                 for (int i = 0; i < 19; i++) w.len[i] = 0;
                 for (int i = 0; i < ncode; i++) w.len[order[i]] = (unsigned char)bits_get(b, 3);
-                Huff hc; unsigned short csym[19]; hc.symbol = csym;
+                Huff hc; unsigned short csym[19], ccount[16]; hc.symbol = csym; hc.count = ccount;
                 if (huff_build(hc, w.len, 19) != 0) rc = INF_BADCODE;    // the code-length code must be complete
                 int idx = 0;
                 while (!rc && idx < nlen + ndist) {
@@ -196,6 +223,16 @@ FSLR_HD int inflate_stream(const unsigned char *in, long long n_in, unsigned cha
         rc = __shfl_sync(0xffffffffu, rc, 0);
 #endif
         if (rc) return rc;
+        // ---- one-lookup tables for the short codes, filled by the whole warp
+#if INF_WARP
+        __syncwarp();
+        for (int i = lane; i < (1 << LBITS); i += INF_LANES) w.ltab[i] = tab_entry(hl, (unsigned)i, LBITS);
+        for (int i = lane; i < (1 << DBITS); i += INF_LANES) w.dtab[i] = tab_entry(hd, (unsigned)i, DBITS);
+        __syncwarp();
+#else
+        for (int i = 0; i < (1 << LBITS); i++) w.ltab[i] = tab_entry(hl, (unsigned)i, LBITS);
+        for (int i = 0; i < (1 << DBITS); i++) w.dtab[i] = tab_entry(hd, (unsigned)i, DBITS);
+#endif
         // ---- symbols of the block
 #if INF_WARP
         // lane 0 decodes; literals go straight to memory, every match is broadcast and copied by the warp
@@ -203,14 +240,14 @@ FSLR_HD int inflate_stream(const unsigned char *in, long long n_in, unsigned cha
             int mlen = 0, mdist = 0, done = 0;
             if (lane == 0) {
                 for (;;) {
-                    const int sym = huff_decode(b, hl);
+                    const int sym = decode_fast(b, hl, w.ltab, LBITS);
                     if (sym < 0) { rc = b.err ? b.err : INF_BADCODE; break; }
                     if (sym < 256) { if (op >= n_out) { rc = INF_OVERRUN; break; } out[op++] = (unsigned char)sym; continue; }
                     if (sym == 256) { done = 1; break; }
                     const int s = sym - 257;
                     if (s >= 29) { rc = INF_BADCODE; break; }
                     mlen = base_len(s) + (int)bits_get(b, extra_len(s));
-                    const int ds = huff_decode(b, hd);
+                    const int ds = decode_fast(b, hd, w.dtab, DBITS);
                     if (ds < 0 || ds >= 30) { rc = b.err ? b.err : INF_BADCODE; break; }
                     mdist = base_dist(ds) + (int)bits_get(b, extra_dist(ds));
                     if (b.err) { rc = b.err; break; }
@@ -232,14 +269,14 @@ FSLR_HD int inflate_stream(const unsigned char *in, long long n_in, unsigned cha
         }
 #else
         for (;;) {
-            const int sym = huff_decode(b, hl);
+            const int sym = decode_fast(b, hl, w.ltab, LBITS);
             if (sym < 0) return b.err ? b.err : INF_BADCODE;
             if (sym < 256) { if (op >= n_out) return INF_OVERRUN; out[op++] = (unsigned char)sym; continue; }
             if (sym == 256) break;
             const int s = sym - 257;
             if (s >= 29) return INF_BADCODE;
             const int mlen = base_len(s) + (int)bits_get(b, extra_len(s));
-            const int ds = huff_decode(b, hd);
+            const int ds = decode_fast(b, hd, w.dtab, DBITS);
             if (ds < 0 || ds >= 30) return b.err ? b.err : INF_BADCODE;
             const int mdist = base_dist(ds) + (int)bits_get(b, extra_dist(ds));
             if (b.err) return b.err;
