@@ -11,7 +11,7 @@ N_STAGES = 12
 
 SYMBOLS = ["fslrc_create", "fslrc_destroy", "fslrc_last_error", "fslrc_stage_name", "fslrc_version",
            "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_replay",
-           "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_choose_alignment_host",
+           "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_set_blocking_sync", "fslrc_choose_alignment_host",
            "fslrc_tsv_open", "fslrc_tsv_chrom_name", "fslrc_tsv_read_names", "fslrc_tsv_write_cluster_bed", "fslrc_tsv_close",
            "fslrc_bam_open", "fslrc_bam_open_bgzf", "fslrc_bam_read_stream", "fslrc_bam_write_mappings_bed", "fslrc_bam_read_names", "fslrc_bam_close"]
 
@@ -113,6 +113,7 @@ def load():
     lib.fslrc_bam_read_names.argtypes = [vp, vp, vp]
     lib.fslrc_bam_close.argtypes = [vp]
     lib.fslrc_bam_close.restype = None
+    lib.fslrc_set_blocking_sync.argtypes = [vp, C.c_int]
     lib.fslrc_launch_count.argtypes = [vp]
     lib.fslrc_launch_count.restype = C.c_longlong
     _lib = lib

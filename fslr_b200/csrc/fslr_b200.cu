@@ -50,6 +50,8 @@ struct fslrc_ctx {
     // pipeline state (kept between the fslrc_mg_* stages)
     struct Pipe *pipe;
     struct TsvState *tsv;    // parsed mappings.bed kept on the device between fslrc_tsv_open and fslrc_tsv_close
+    cudaEvent_t ev_block;    // cudaEventBlockingSync event: waits that put the thread to sleep (fslrc_set_blocking_sync)
+    int blocking;
     struct BamState *bam;    // table produced from a BAM file, kept on the device between fslrc_bam_open and fslrc_bam_close
     long long launches;      // kernels of this library launched since fslrc_create
 };
@@ -198,10 +200,17 @@ static int sort_pairs(fslrc_ctx *ctx, Pipe *P, const unsigned *kin, unsigned *ko
     }
     return 0;
 }
+// wait for the context's stream: spinning (lowest latency) or, for contexts driven from several host threads at once
+// (engine.HostPipeline), sleeping on a blocking-sync event so that a waiting thread leaves its core to the others
+static cudaError_t ctx_sync(fslrc_ctx *ctx) {
+    if (!ctx->blocking) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_block);
+}
 static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
     CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 48 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_pin + 48, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(ctx_sync(ctx));
     return 0;
 }
 static int err_code(fslrc_ctx *ctx) {
@@ -519,6 +528,8 @@ int fslrc_create(int device, fslrc_ctx **out) {
     ctx->device = device; ctx->launches = 0; ctx->err[0] = 0; ctx->stream = nullptr; ctx->pipe = nullptr; ctx->tsv = nullptr; ctx->bam = nullptr; ctx->h_pin = nullptr;
     if (cudaMallocHost((void **)&ctx->h_pin, 64 * sizeof(int64_t)) != cudaSuccess) { delete ctx; return FSLRC_ERR_CUDA; }
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    ctx->blocking = 0;
     cudaFuncSetAttribute(prims::k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prims::RsSmem));
     cudaMemPool_t pool;                                   // keep freed scratch cached between calls
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -537,6 +548,7 @@ void fslrc_destroy(fslrc_ctx *ctx) {
     bam_free(ctx);
     cudaDeviceSynchronize();
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaEventDestroy(ctx->ev_block);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx->pipe;
     delete ctx;
@@ -555,7 +567,7 @@ int fslrc_cluster_device(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_p
     if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, &P, stats);
     free_all(ctx);
-    cudaStreamSynchronize(ctx->stream);
+    ctx_sync(ctx);
     return r;
 }
 
@@ -616,7 +628,7 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
     if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, &P, stats);
     free_all(ctx);
-    cudaStreamSynchronize(st);
+    ctx_sync(ctx);
     return r;
 }
 
@@ -931,6 +943,12 @@ void fslrc_tsv_close(fslrc_ctx *ctx) {
 }
 
 #include "bam_abi.inl"
+
+int fslrc_set_blocking_sync(fslrc_ctx *ctx, int on) {
+    if (!ctx) return FSLRC_ERR_ARG;
+    ctx->blocking = on != 0;
+    return 0;
+}
 
 long long fslrc_launch_count(const fslrc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 

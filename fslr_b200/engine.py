@@ -283,9 +283,14 @@ class HostPipeline:
     one: `depth` library contexts, each with its own CUDA stream and worker thread (the C ABI call blocks its thread, not the
     interpreter).  This is how a service clusters sample after sample; `bench.py` uses it for the end-to-end number."""
 
-    def __init__(self, device=0, depth=2):
+    def __init__(self, device=0, depth=2, blocking_sync=None):
+        import os
         from concurrent.futures import ThreadPoolExecutor
         self.engines = [Engine(device) for _ in range(depth)]
+        if blocking_sync is None:
+            blocking_sync = os.environ.get("FSLR_B200_BLOCKING_SYNC", "0") == "1"
+        for e in self.engines:                            # worker threads sleep in their waits instead of spinning
+            e.lib.fslrc_set_blocking_sync(e.ctx, int(bool(blocking_sync)))
         self.streams = [torch.cuda.Stream(device=self.engines[0].device) for _ in range(depth)]
         self.pool = ThreadPoolExecutor(max_workers=depth)
         self.depth, self._next = depth, 0

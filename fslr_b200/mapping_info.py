@@ -247,7 +247,18 @@ def read_bam_table(bam, regions_path=None, primers=None, device=0, hash_seed=0, 
         data = np.ascontiguousarray(bam, dtype=np.uint8)
         refs, first = parse_bam_header(data)
     else:
-        raw = bam if isinstance(bam, (bytes, bytearray, memoryview)) else np.fromfile(bam, dtype=np.uint8)
+        if isinstance(bam, (bytes, bytearray, memoryview)):
+            raw = bam
+        elif device_inflate:                                              # straight into the reused pinned staging buffer
+            import os
+            if os.path.getsize(bam) == 0:
+                raise ValueError("%s: empty file" % bam)
+            raw = eng.pinned_bytes(os.path.getsize(bam)).numpy()
+            with open(bam, "rb") as f:
+                if f.readinto(memoryview(raw)) != raw.shape[0]:
+                    raise IOError("short read of %s" % bam)
+        else:
+            raw = np.fromfile(bam, dtype=np.uint8)
         if device_inflate:
             data = raw if isinstance(raw, np.ndarray) else np.frombuffer(raw, dtype=np.uint8)
             refs, first = bgzf_header_prefix(data)

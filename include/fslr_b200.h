@@ -209,6 +209,10 @@ int fslrc_bam_write_mappings_bed(fslrc_ctx *ctx, const char *chrom_names, const 
 int fslrc_bam_read_names(fslrc_ctx *ctx, int64_t *offsets, int32_t *lengths);   /* [n_reads], by read_id: where each qname sits in `bam` */
 void fslrc_bam_close(fslrc_ctx *ctx);
 
+/* on != 0: the waits inside fslrc_cluster_host / fslrc_cluster_device put the calling thread to sleep (blocking-sync event)
+ * instead of spinning — for contexts driven concurrently from several host threads (one context per thread). */
+int fslrc_set_blocking_sync(fslrc_ctx *ctx, int on);
+
 /* Integer-issue microbenchmark used as the pair-kernel roofline denominator: returns the measured
  * dependent-free IADD3/LOP3/VIMNMX lane-ops per second on this device. */
 int fslrc_int_peak(fslrc_ctx *ctx, double *lane_ops_per_s);

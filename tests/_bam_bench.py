@@ -41,12 +41,12 @@ out.update({"host_inflate": {"inflate_s": t1 - t0, "open_s": t2 - t1, "open_devi
                              "reads_per_s_from_bgzf": n_reads / (t3 - t0)}, "bed_MB": bed.shape[0] / 1e6})
 want = bed.tobytes()
 for rep in range(2):
-    t0 = time.perf_counter(); raw = open(path, "rb").read(); t1 = time.perf_counter()
-    t = mi.read_bam_table(raw, None, primers, device_inflate=True); t2 = time.perf_counter()
+    t0 = time.perf_counter(); t1 = t0
+    t = mi.read_bam_table(path, None, primers, device_inflate=True); t2 = time.perf_counter()
     bed = t.mappings_bed_bytes("9.9"); t3 = time.perf_counter()
     kernels_ms, fb = t.parse_ms, int(t.info.reserved)
     t.close()
-out.update({"device_inflate": {"read_file_s": t1 - t0, "open_s": t2 - t1, "open_device_ms": kernels_ms, "render_s": t3 - t2,
+out.update({"device_inflate": {"read_file_and_open_s": t2 - t0, "open_device_ms": kernels_ms, "render_s": t3 - t2,
                                "host_walk_fallback": fb, "reads_per_s_from_bgzf": n_reads / (t3 - t0), "same_bytes": bool(bed.tobytes() == want)}})
 if copies == 1:
     out["identical_to_oracle"] = bool(bed.tobytes() == txt.encode())
