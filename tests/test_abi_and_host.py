@@ -32,6 +32,12 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_native.Table) == 8 * 2 + 8 * 8 + 8 + 8 + 8 * 3 + 8
     assert ctypes.sizeof(_native.Stats) == 8 * 11 + 4 + 4 + 4 * _native.N_STAGES
     assert _native.Params.umax.offset == 24 and _native.Params.edge_threshold.offset == 24 + 4 * 65 + 4
+    assert ctypes.sizeof(_native.BamInfo) == 8 * 4 + 4 * 2 + 8 * 15 + 4 + 4
+    # the field order of the pointer block of fslrc_bam_info is the one the header declares
+    hdr = open(os.path.join(ROOT, "include", "fslr_b200.h")).read()
+    block = hdr[hdr.index("int32_t overlaps_as_float;"):hdr.index("} fslrc_bam_info;")]
+    names = re.findall(r"\*(\w+)", re.sub(r"/\*.*?\*/", "", block, flags=re.S))
+    assert tuple(n.replace("n_alignments", "n_alignments") for n in names) == _native.BAM_COLUMNS
 
 
 def test_no_cpu_fallback():
