@@ -51,3 +51,25 @@ def test_reference_end_of_an_alignment_without_reference_bases():
     rows = mo.mapping_rows(os.path.join(CASES_DIR, "edge.bam"), None, CASES["edge"]["primers"])
     r = [x for x in rows if x["qname"].startswith("cccc") and not x["inferred_by_primer"]][0]
     assert (r["rstart"], r["rend"]) == (78, 78)
+
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104])
+def test_oracle_against_the_reference_itself_on_random_bams(tmp_path, seed):
+    """Only where /root/reference exists (the build container): fresh random BAMs through the unmodified
+    collect_mapping_info.mapping_info and through the restatement must give the same file."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference not present")
+    from fslr_b200 import synth_bam as sb
+    kw = [dict(), dict(name_style="prefix", with_seq_on_supp=True), dict(p_single=0.7, p_false=0.5), dict(max_aln=12, p_two_primary=0.3)][seed % 4]
+    refs, recs, primers = sb.make_alignments(150, seed=seed, **kw)
+    bam = str(tmp_path / "t.bam")
+    sb.write_bam(bam, refs, [sb.encode_record(*r) for r in recs])
+    reg = None
+    if seed % 2:
+        reg = str(tmp_path / "r.bed")
+        open(reg, "w").write("chr1\t1000\t90000000\nchr21\t5\t20000000\nL1_TALEN\t100\t4000\n")
+    out = str(tmp_path / "ref.bed")
+    assert rh.run_reference_mapping_info(bam, out, reg, primers) is None
+    rows = mo.mapping_rows(bam, mo.read_regions(reg) if reg else None, primers, rh.FSLR_VERSION_FOR_TESTS)
+    assert mo.mapping_tsv(rows, bool(reg)) == open(out).read()
