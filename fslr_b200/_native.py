@@ -7,10 +7,10 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libfslr_b200.so")
 MAX_FILLINGS = 64
-N_STAGES = 12
+N_STAGES = 14
 
 SYMBOLS = ["fslrc_create", "fslrc_destroy", "fslrc_last_error", "fslrc_stage_name", "fslrc_version",
-           "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_replay",
+           "fslrc_cluster_device", "fslrc_cluster_host", "fslrc_mg_prepare", "fslrc_mg_pair", "fslrc_mg_partners", "fslrc_mg_replay",
            "fslrc_mg_finish", "fslrc_int_peak", "fslrc_launch_count", "fslrc_set_blocking_sync", "fslrc_choose_alignment_host",
            "fslrc_tsv_open", "fslrc_tsv_chrom_name", "fslrc_tsv_read_names", "fslrc_tsv_write_cluster_bed", "fslrc_tsv_close",
            "fslrc_bam_open", "fslrc_bam_open_bgzf", "fslrc_bam_read_stream", "fslrc_bam_write_mappings_bed", "fslrc_bam_read_names", "fslrc_bam_close"]
@@ -95,7 +95,8 @@ def load():
         f.argtypes = [vp, C.POINTER(Table), C.POINTER(Params), vp, vp, C.POINTER(Stats), vp]
     lib.fslrc_mg_prepare.argtypes = [vp, C.POINTER(Table), C.POINTER(Params), vp]
     lib.fslrc_mg_pair.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i64p]
-    lib.fslrc_mg_replay.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i64p]
+    lib.fslrc_mg_partners.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), i64p]
+    lib.fslrc_mg_replay.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, C.POINTER(vp), i64p]
     lib.fslrc_mg_finish.argtypes = [vp, vp, C.c_int64, vp, vp, C.POINTER(Stats)]
     lib.fslrc_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fslrc_choose_alignment_host.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]

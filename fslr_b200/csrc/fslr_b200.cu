@@ -59,9 +59,11 @@ struct fslrc_ctx {
 static void tsv_free(fslrc_ctx *ctx);
 static void bam_free(fslrc_ctx *ctx);
 
+enum { ST_H2D = 0, ST_KEEP, ST_ORDER, ST_QRANK, ST_CHROM, ST_BANDS, ST_CAND, ST_PAIR, ST_HEAVY, ST_SAT, ST_REPLAY, ST_UNION, ST_NUMBER, ST_D2H };
 static const char *STAGE_NAMES[FSLRC_N_STAGES] = {
     "h2d", "keep_fillings", "data_order_mask", "query_rank_read_lists", "chrom_sort", "records_bands",
-    "pair_kernel", "saturating_set", "replay", "union_find", "numbering", "d2h"};
+    "candidates", "pair_kernel", "pair_heavy", "saturating_set", "replay", "union_find", "numbering", "d2h"};
+static_assert(ST_D2H + 1 == FSLRC_N_STAGES, "stage list");
 
 static int fail(fslrc_ctx *c, int code, const char *fmt, const char *a = "") {
     snprintf(c->err, sizeof(c->err), fmt, a);
@@ -106,6 +108,7 @@ static inline int nblk(int64_t n, int t) { return (int)((n + t - 1) / t); }
 
 #include "kernels_ingest.cuh"
 #include "kernels_pair.cuh"
+#include "kernels_hits.cuh"
 #include "kernels_replay.cuh"
 #include "kernels_graph.cuh"
 #include "bam.cuh"
@@ -119,11 +122,15 @@ struct Pipe {
     int A, R, F, D, Q, nP, Tedge, pair_blocks;
     int *err;
     int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entry slots,6 nP,7 pedge slots,8 edges,9 ncl,10 forest,
-                             //                  11 singletons, 12 runs, 13 entries, 14 tight band
+                             //                  11 singletons, 12 runs, 13 entries, 14 tight band, 40-43 partner-record slots / stats,
+                             //                  44 tight band of light positions, 45 light partner records, 46 heavy reads, 47 P-pairs (mg)
     int *q_of_rid, *rid_of_q;
     int4 *SR0, *SR1, *RM, *RI;
     int *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
     int *isP, *plist, *stop, *stopS;
+    unsigned *cp;            // per light read: passing partners | partners << 16 | CP_LONG (k_eval), then k_plist's fill counter
+    int *rclass, *heavy_list, *plcount, *ploff;
+    int hits_blocks;
     int2 *entries, *pedges;
     int4 *PL; PLInfo *plinfo;
     unsigned long long cap_entries, cap_pedges, cap_pl;
@@ -261,7 +268,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     DA(FR0, F); DA(FR1, F);
     if (A > 0) KL(k_fill_records, nblk(A, TB), TB, A, flagA, posA, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size, tb.n_alignments,
                   pr.n_chrom, FR0, FR1, P->err);
-    { int r = mark(ctx, 1); if (r) return r; }
+    { int r = mark(ctx, ST_KEEP); if (r) return r; }
     // ---- stage 2: mask (cluster.py:89-106; dropping masked fillings before or after the sort is the same list) + data order
     // (cluster.py:114): the caller's permutation, or a stable radix sort by start (ties keep bed order)
     int *flagF, *posF;
@@ -289,7 +296,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         DA(tkey, D); DA(tkey2, D); DA(tval, D); DA(tval2, D);
         KL(k_tie_delta, nblk(D, TB), TB, D, IT0, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
     }
-    { int r = mark(ctx, 2); if (r) return r; }
+    { int r = mark(ctx, ST_ORDER); if (r) return r; }
     // ---- stage 3: query rank + per-read lists
     int *flagD, *posD, *it_q;
     DA(flagD, D); DA(posD, D); DA(it_q, D);
@@ -311,7 +318,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         KL(k_read_bounds, nblk(D, TB), TB, D, qs, rm_dp, rmidx, off, len_end);
         KL(k_read_info, nblk(Q, TB), TB, Q, P->rid_of_q, off, len_end, rm_dp, IT1, qmin, qmax, pr.qlen_c, pr.naln_c, P->RI, P->err);
     }
-    { int r = mark(ctx, 3); if (r) return r; }
+    { int r = mark(ctx, ST_QRANK); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
     int *s_dp; DA(s_dp, D);
     const bool tie_ok = tkey && ctx->h_pin[41] == 0;                 // (read back with the stage-3 counters)
@@ -329,7 +336,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         KL(k_gather_key, nblk(D, TB), TB, D, v2, IT0, 1, ek);
         r = sort_pairs(ctx, P, ek, ek2, v2, s_dp, D, 0, bits_for(pr.n_chrom)); if (r) return r;
     }
-    { int r = mark(ctx, 4); if (r) return r; }
+    { int r = mark(ctx, ST_CHROM); if (r) return r; }
     // ---- stage 5: records, thresholds, bands
     int *s_end;
     DA(P->SR0, D); DA(P->SR1, D); DA(P->RM, 2 * (int64_t)D); DA(P->s_chrom, D); DA(s_end, D);
@@ -341,9 +348,11 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
         KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
                                                s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi, P->err);
         int r = segmax_scan(ctx, P, P->s_chrom, s_end, P->pmaxS, D); if (r) return r;
-        KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM,
-           (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14));
-    }
+        DA(P->rclass, Q);
+        CK(cudaMemsetAsync(P->rclass, 0, sizeof(int) * (size_t)std::max(Q, 1), st));
+        KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM, P->rclass,
+           (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14), (unsigned long long *)(P->cnt + 44));
+    } else DA(P->rclass, Q);
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     long long T = pr.edge_threshold;
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
@@ -351,47 +360,74 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     t.SR0 = P->SR0; t.SR1 = P->SR1; t.RM = P->RM; t.RI = P->RI; t.pmaxS = P->pmaxS;
     t.chrom_lo = P->chrom_lo; t.chrom_hi = P->chrom_hi; t.sib = nullptr; t.D = D; t.Q = Q; t.Tedge = P->Tedge;
     memcpy(P->um.v, pr.umax, sizeof(P->um.v));
-    // relation entries: a read records at most edge_threshold + 7 passing partners (one step past the threshold), and every
-    // entry is a distinct (filling of a, band position) hit
-    const unsigned long long tight = (unsigned long long)ctx->h_pin[14];
+    // hit / relation-entry slots: k_hits lists at most one hit per (light position, tight-band position) pair; k_pair records
+    // for a heavy read at most edge_threshold + 7 passing partners (one step past the threshold), each a distinct
+    // (filling of a, band position) hit
+    const unsigned long long tight = (unsigned long long)ctx->h_pin[14], lightT = (unsigned long long)ctx->h_pin[44];
     unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * ((unsigned long long)P->Tedge + 7ull) : 0ull;
     P->pair_blocks = std::max(1, std::min(nblk(Q, PK_GROUPS), n_sms(ctx) * 8));
-    P->cap_entries = std::min<unsigned long long>(capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks + 64;
+    P->hits_blocks = std::max(1, std::min(nblk(Q, HK_GROUPS), n_sms(ctx) * 8));
+    P->cap_entries = std::min<unsigned long long>(lightT + capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks +
+                     (unsigned long long)HK_CHUNK * HK_WARPS * P->hits_blocks + 64;
     DA(P->entries, P->cap_entries);
+    DA(P->cp, Q); DA(P->heavy_list, Q); DA(P->plcount, Q); DA(P->ploff, Q);
     // partner records of saturating reads (replay LIST mode): at most RP_K per read and never more than tight-band hits
     P->cap_pl = std::min<unsigned long long>((unsigned long long)Q * RP_K, tight) + (unsigned long long)PL_CHUNK * PK_WARPS * P->pair_blocks * 2 + 64;
     DA(P->PL, 2 * P->cap_pl); DA(P->plinfo, Q);
     DA(P->isP, Q); DA(P->stop, D); DA(P->stopS, D); DA(P->parent, Q); DA(P->ing, Q); DA(P->ticket, 1);
     if (Q > 0) CK(cudaMemsetAsync(P->isP, 0, sizeof(int) * Q, st));
-    return mark(ctx, 5);
+    return mark(ctx, ST_BANDS);
 }
 
 
-// ---- stage 6: pair kernel on one shard
-static int launch_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, int lists_only) {
-    cudaStream_t st = ctx->stream;
-    if (P->pr.overlap > 0.0)
-        KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
-           P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
-           (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
-    else
-        KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, lists_only, P->isP, P->entries, (unsigned long long *)(P->cnt + 5),
-           P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cap_pl,
-           (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err);
-    return 0;
-}
+// ---- stage 6: pair stage on one shard: k_hits -> k_eval for the light reads, k_pair for the heavy ones (--overlap <= 0: all)
 static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
-    if (P->Q > 0) { int r = launch_pair(ctx, P, shard, nshard, 0); if (r) return r; }
-    return mark(ctx, 6);
+    cudaStream_t st = ctx->stream;
+    const bool dense = P->Q > 0 && P->pr.overlap > 0.0;
+    if (P->Q > 0) CK(cudaMemsetAsync(P->cp, 0, sizeof(unsigned) * (size_t)P->Q, st));
+    if (dense)
+        KL(k_hits, P->hits_blocks, HK_WARPS * 32, P->tab, shard, nshard, P->rclass, P->entries, (unsigned long long *)(P->cnt + 5), P->cap_entries,
+           P->heavy_list, (unsigned *)(P->cnt + 46), P->err);
+    { int r = mark(ctx, ST_CAND); if (r) return r; }
+    if (dense)
+        KL(k_eval, n_sms(ctx) * 8, EV_THREADS, P->tab, P->um, P->entries, (const unsigned long long *)(P->cnt + 5), P->cap_entries, P->cp,
+           (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13));
+    { int r = mark(ctx, ST_PAIR); if (r) return r; }
+#define PAIR_ARGS P->isP, P->entries, (unsigned long long *)(P->cnt + 5), P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), \
+                  P->cap_pl, (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13), P->err
+    if (dense)
+        KL(k_pair<false>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, (const int *)P->heavy_list, (const unsigned *)(P->cnt + 46), PAIR_ARGS);
+    else if (P->Q > 0)
+        KL(k_pair<true>, P->pair_blocks, PK_WARPS * 32, P->tab, P->um, shard, nshard, (const int *)nullptr, (const unsigned *)nullptr, PAIR_ARGS);
+#undef PAIR_ARGS
+    return mark(ctx, ST_HEAVY);
+}
+// ---- stage 7a (after the counters are complete): saturating set of the light reads, where their partner records go
+static int pipe_sat(fslrc_ctx *ctx, Pipe *P) {
+    cudaStream_t st = ctx->stream;
+    const int Q = P->Q, TB = 256;
+    if (Q > 0 && P->pr.overlap > 0.0) {
+        KL(k_light_sat, nblk(Q, TB), TB, P->tab, P->rclass, P->cp, P->isP, P->plinfo, P->plcount, (unsigned long long *)(P->cnt + 40));
+        int r = xscan(ctx, P, P->plcount, P->ploff, Q, P->cnt + 45); if (r) return r;
+        KL(k_plinfo, nblk(Q, TB), TB, Q, P->plcount, P->ploff, P->plinfo, (unsigned long long *)(P->cnt + 40), P->cnt + 45, P->cap_pl, P->err);
+    }
+    return 0;
 }
 
 // ---- stages 7-9 (after isP is complete): saturating set, replay, union-find
-static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
+// pairs / n_pairs: the recorded pairs of light saturating reads of ALL ranks (multi-GPU, after the all-gather); NULL: this
+// context's own list holds them all
+static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, const int2 *pairs, unsigned long long n_pairs) {
     cudaStream_t st = ctx->stream;
     const int Q = P->Q, D = P->D, TB = 256;
     int *posQ;
     DA(posQ, Q);
-    if (Q > 0 && nshard > 1) { int r = launch_pair(ctx, P, shard, nshard, 1); if (r) return r; }
+    if (Q > 0 && P->pr.overlap > 0.0) {                                   // partner records of the light saturating reads
+        if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * 8), PLT_THREADS, P->tab, pairs, (const unsigned long long *)nullptr,
+                                       n_pairs, n_pairs, P->isP, P->plinfo, P->cp, P->PL, P->err); }
+        else KL(k_plist, n_sms(ctx) * 8, PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull, P->cap_entries,
+                P->isP, P->plinfo, P->cp, P->PL, P->err);
+    }
     if (Q > 0) {
         int r = xscan(ctx, P, P->isP, posQ, Q, P->cnt + 6); if (r) return r;
     }
@@ -402,7 +438,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     // stops: a read that never breaks walks every filling's scan to the chromosome start (0 <= any position)
     if (D > 0) { CK(cudaMemsetAsync(P->stop, 0, sizeof(int) * D, st)); CK(cudaMemsetAsync(P->stopS, 0, sizeof(int) * D, st)); }
     CK(cudaMemsetAsync(P->ticket, 0, sizeof(unsigned), st));
-    { int r = mark(ctx, 7); if (r) return r; }
+    { int r = mark(ctx, ST_SAT); if (r) return r; }
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
     const int replay_blocks_max = n_sms(ctx) * 16;
     unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
@@ -434,7 +470,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
         else KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
 #undef REPLAY_ARGS
     }
-    { int r = mark(ctx, 8); if (r) return r; }
+    { int r = mark(ctx, ST_REPLAY); if (r) return r; }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
     const unsigned long long nped = std::min<unsigned long long>((unsigned long long)ctx->h_pin[7], P->cap_pedges);
@@ -447,7 +483,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     // replayed edges are identical on every rank; rank 0 contributes them once
     if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));
     (void)nshard;
-    return mark(ctx, 9);
+    return mark(ctx, ST_UNION);
 }
 
 // ---- stage 10: numbering
@@ -466,7 +502,7 @@ static int pipe_number(fslrc_ctx *ctx, Pipe *P, int *out_cluster, int *out_n) {
         int r = xscan(ctx, P, sflag, spos, R, P->cnt + 11); if (r) return r;
         KL(k_number, nblk(R, TB), TB, R, P->q_of_rid, P->ing, P->parent, cidx, csize, spos, P->cnt + 9, out_cluster, out_n);
     }
-    return mark(ctx, 10);
+    return mark(ctx, ST_NUMBER);
 }
 
 static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
@@ -507,7 +543,8 @@ static int check_args(fslrc_ctx *ctx, const fslrc_table *tb, const fslrc_params 
 static int run_device(fslrc_ctx *ctx, Pipe *P, int32_t *oc, int32_t *on, fslrc_stats *stats) {
     int r = pipe_prepare(ctx, P); if (r) return r;
     r = pipe_pair(ctx, P, 0, 1); if (r) return r;
-    r = pipe_replay_union(ctx, P, 0, 1); if (r) return r;
+    r = pipe_sat(ctx, P); if (r) return r;
+    r = pipe_replay_union(ctx, P, 0, 1, nullptr, 0); if (r) return r;
     r = pipe_number(ctx, P, oc, on); if (r) return r;
     return 0;
 }
@@ -563,7 +600,7 @@ int fslrc_cluster_device(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_p
     P.tb = *table; P.pr = *params; P.A = (int)table->n_rows; P.R = (int)table->n_reads;
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
     r = run_device(ctx, &P, out_cluster, out_n_reads, stats);
-    if (!r) { r = mark(ctx, 11); }
+    if (!r) { r = mark(ctx, ST_D2H); }
     if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, &P, stats);
     free_all(ctx);
@@ -624,7 +661,7 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
         CK(cudaMemcpyAsync(out_cluster, d_oc, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(out_n_reads, d_on, sizeof(int32_t) * R, cudaMemcpyDeviceToHost, st));
     }
-    if (!r) r = mark(ctx, 11);
+    if (!r) r = mark(ctx, ST_D2H);
     if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, &P, stats);
     free_all(ctx);
@@ -653,14 +690,31 @@ int fslrc_mg_pair(fslrc_ctx *ctx, int rank, int world, int32_t **counts, int64_t
     CK(cudaSetDevice(ctx->device));
     int r = pipe_pair(ctx, P, rank, world); if (r) return r;
     CK(cudaStreamSynchronize(ctx->stream));
-    *counts = P->isP; *n_counts = P->Q;
+    *counts = (int32_t *)P->cp; *n_counts = P->Q;
     return 0;
 }
-int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64_t *n_forest_edges) {
-    if (!ctx || !ctx->pipe || !forest || !n_forest_edges) return FSLRC_ERR_ARG;
+int fslrc_mg_partners(fslrc_ctx *ctx, int rank, int world, int32_t **pairs, int64_t *n_pairs) {
+    if (!ctx || !ctx->pipe || !pairs || !n_pairs || world < 1 || rank < 0 || rank >= world) return FSLRC_ERR_ARG;
     Pipe *P = ctx->pipe;
     CK(cudaSetDevice(ctx->device));
-    int r = pipe_replay_union(ctx, P, rank, world); if (r) return r;
+    cudaStream_t st = ctx->stream;
+    int r = pipe_sat(ctx, P); if (r) return r;
+    r = read_counts(ctx, P); if (r) return r;
+    r = err_code(ctx); if (r) return r;
+    const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
+    int2 *pent; DA(pent, nent);
+    if (nent > 0) KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->entries, nent, P->isP, P->plinfo, pent, (unsigned long long *)(P->cnt + 47));
+    r = read_counts(ctx, P); if (r) return r;
+    *pairs = (int32_t *)pent; *n_pairs = ctx->h_pin[47];
+    return 0;
+}
+int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, const int32_t *all_pairs, int64_t n_all_pairs, int32_t **forest,
+                    int64_t *n_forest_edges) {
+    if (!ctx || !ctx->pipe || !forest || !n_forest_edges || n_all_pairs < 0 || (n_all_pairs > 0 && !all_pairs)) return FSLRC_ERR_ARG;
+    Pipe *P = ctx->pipe;
+    CK(cudaSetDevice(ctx->device));
+    static const int2 none = {-1, -1};
+    int r = pipe_replay_union(ctx, P, rank, world, all_pairs ? (const int2 *)all_pairs : &none, (unsigned long long)n_all_pairs); if (r) return r;
     cudaStream_t st = ctx->stream;
     const int Q = P->Q, TB = 256;
     int *isroot, *csize; int2 *fo;
@@ -688,7 +742,7 @@ int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges, 
     }
     if (n_edges > 0) KL(k_union_edges, nblk(n_edges, TB), TB, (unsigned long long)n_edges, (const int2 *)all_forest, P->parent, P->ing, (unsigned long long *)nullptr);
     int r = pipe_number(ctx, P, out_cluster, out_n_reads);
-    if (!r) r = mark(ctx, 11);
+    if (!r) r = mark(ctx, ST_D2H);
     if (!r) { r = read_counts(ctx, P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, P, stats);
     free_all(ctx);
@@ -784,11 +838,7 @@ static int tsv_intern(fslrc_ctx *ctx, Pipe *P, const unsigned char *text, int n,
     KL(tsv::k_tsv_intern_ids, nblk(n, TB), TB, n, slot, first, idat, id_out, first_row_of_id);
     return 0;
 }
-extern "C" {
-
-int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t hash_seed, fslrc_tsv_info *info, void *stream) {
-    if (!ctx) return FSLRC_ERR_ARG;
-    if (!text || !info || n_bytes <= 0) return fail(ctx, FSLRC_ERR_ARG, "tsv: null or empty input");
+static int tsv_open_impl(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t hash_seed, fslrc_tsv_info *info, void *stream) {
     CK(cudaSetDevice(ctx->device));
     ctx->stream = (cudaStream_t)stream;
     cudaStream_t st = ctx->stream;
@@ -880,6 +930,18 @@ int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t h
     if (cudaEventElapsedTime(&ms, ctx->ev[0 + 1], ctx->ev[2]) == cudaSuccess) info->parse_ms = ms; else cudaGetLastError();
     return 0;
 }
+extern "C" {
+
+int fslrc_tsv_open(fslrc_ctx *ctx, const char *text, int64_t n_bytes, uint64_t hash_seed, fslrc_tsv_info *info, void *stream) {
+    if (!ctx) return FSLRC_ERR_ARG;
+    if (!text || !info || n_bytes <= 0) return fail(ctx, FSLRC_ERR_ARG, "tsv: null or empty input");
+    const int r = tsv_open_impl(ctx, text, n_bytes, hash_seed, info, stream);
+    if (r) {                                                           // every error path: scratch and the half-built table go
+        free_all(ctx); tsv_free(ctx);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    return r;
+}
 int fslrc_tsv_chrom_name(fslrc_ctx *ctx, int32_t chrom_id, char *buf, int32_t cap) {
     if (!ctx || !ctx->tsv || !buf || chrom_id < 0 || chrom_id >= ctx->tsv->n_chrom) return FSLRC_ERR_ARG;
     const std::string &s = ctx->tsv->chrom_names[chrom_id];
@@ -912,9 +974,11 @@ int fslrc_tsv_write_cluster_bed(fslrc_ctx *ctx, const int32_t *cluster_dev, cons
     cudaStream_t st = ctx->stream;
     Pipe Pp; memset((void *)&Pp, 0, sizeof(Pp)); Pipe *P = &Pp;
     const int L = T->n_lines, TB = 256;
-    long long *len, *off; int64_t *tot;
-    DA(len, L); DA(off, L); DA(tot, 1);
-    KL(tsv::k_tsv_outlen, nblk(L, TB), TB, L, T->line_start, T->read_id, cluster_dev, n_reads_dev, len);
+    long long *len, *off; int64_t *tot; int *any_single;
+    DA(len, L); DA(off, L); DA(tot, 1); DA(any_single, 1);
+    CK(cudaMemsetAsync(any_single, 0, sizeof(int), st));
+    if (T->n_reads > 0) KL(tsv::k_tsv_any_single, nblk(T->n_reads, TB), TB, T->n_reads, n_reads_dev, any_single);
+    KL(tsv::k_tsv_outlen, nblk(L, TB), TB, L, T->line_start, T->read_id, cluster_dev, n_reads_dev, any_single, len);
     {
         const int tiles = nblk(L, prims::SC_TILE);
         int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
@@ -928,7 +992,7 @@ int fslrc_tsv_write_cluster_bed(fslrc_ctx *ctx, const int32_t *cluster_dev, cons
         if (cap < *n_out) rc = fail(ctx, FSLRC_ERR_ARG, "tsv: output buffer too small");
         else {
             unsigned char *d_out; DA(d_out, *n_out);
-            KL(tsv::k_tsv_emit, nblk((int64_t)L * 32, TB), TB, L, T->text, T->line_start, T->read_id, cluster_dev, n_reads_dev, off, d_out);
+            KL(tsv::k_tsv_emit, nblk((int64_t)L * 32, TB), TB, L, T->text, T->line_start, T->read_id, cluster_dev, n_reads_dev, any_single, off, d_out);
             CK(cudaMemcpyAsync(out, d_out, *n_out, cudaMemcpyDeviceToHost, st));
         }
     }

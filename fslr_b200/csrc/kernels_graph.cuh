@@ -20,16 +20,17 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
         if (atomicCAS(&parent[a], a, b) == a) return;
     }
 }
-// entries (a, b) recorded by k_pair: a not saturating; b > a -> a tested it (edge); b < a -> edge only if b is
-// saturating and its scan stopped before reaching a (then a's query tested the pair, direction a -> b)
+// entries (a, b) recorded by k_eval / k_pair (a -> b evaluated; only the passing ones matter here): a not saturating;
+// b > a -> a tested it (edge); b < a -> edge only if b is saturating and its scan stopped before reaching a (then a's
+// query tested the pair, direction a -> b)
 __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP, Tab t,
                                 const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     bool e = false;
     if (k < n) {
         const int2 ab = entries[k];
-        const int a = ab.x, b = ab.y;
-        if (a >= 0 && !isP[a]) {
+        const int a = ab.x, b = ab.y & QMASK;                                      // y: b | EB_NOPASS | EB_HEAVY
+        if (a >= 0 && ab.y >= 0 && !isP[a]) {                                      // (y < 0: a partner whose pair does not pass)
             if (b > a) e = true;
             else if (isP[b]) {
                 const int wa = t.RI[a].w, wb = t.RI[b].w;

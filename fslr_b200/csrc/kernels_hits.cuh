@@ -1,0 +1,281 @@
+// Part of fslr_b200.cu (one translation unit; included after kernels_pair.cuh).
+// Stage 6, dense form: the pair stage of reads with <= 4 fillings and short tight bands ("light" reads, nearly all of
+// them) is split into the three kernels the north star names —
+//   k_hits   candidate generation: a group of 8 lanes per query read walks the tight bands of the read's fillings with
+//            coalesced int4 loads and does nothing but the interval-level test of cluster.py:157; every hit
+//            (a, filling fa, sorted position p) goes to a list through warp-aggregated chunk reservations;
+//   k_eval   pair test proper, ONE LANE PER HIT, every lane of a warp busy: different_lengths_or_alignments
+//            (cluster.py:178-183), the match matrix, the greedy N-1 intersection (cluster.py:152-161) and the per-N
+//            Jaccard cutoff (cluster.py:165-170,218-219).  A read pair (a, b) is evaluated exactly once in direction a -> b:
+//            at its CANONICAL hit = the first one in k_hits' scan order (lowest fa, then lowest position), which the lane
+//            verifies from the match matrix and the positions of b's fillings.  The result overwrites the hit in place
+//            (no compaction pass, no atomics on the list): {a, b | flags}, or {-1, -1};
+//   k_plist  after the saturating set is known: one lane per recorded pair of a saturating read writes the partner record
+//            the replay's LIST mode consumes (keys, cg; same content as k_pair's records).
+// Reads with more than 4 fillings or with a tight band longer than PCAP positions (hotspots) are "heavy": they keep the
+// sequential per-read kernel k_pair with its early exit (a 500k-read clique must not enumerate 10^11 hits).
+#pragma once
+
+#define HK_WARPS 8
+#define HK_GROUPS (HK_WARPS * 4)
+#define HK_HASH 32              // per-group filter of partners already hit during this read's scan
+#define HK_CHUNK 256            // hit slots a warp reserves at a time (multiple of 32: k_eval's warps stay whole)
+__device__ __forceinline__ bool shard_owns(int q, int shard, int nshard) { return nshard <= 1 || ((q >> 8) % nshard) == shard; }
+__device__ __forceinline__ bool read_is_heavy(int La, const int *__restrict__ rclass, int q) { return La > 4 || __ldg(&rclass[q]) != 0; }
+
+__global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
+                                                        unsigned long long *n_slots, unsigned long long cap, int *heavy_list,
+                                                        unsigned *n_heavy, int *err) {
+    __shared__ int2 sHash[HK_GROUPS][HK_HASH];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, grp = w * 4 + (lane >> 3);
+    const unsigned ltmask = (1u << lane) - 1u;
+    unsigned long long chunk_base = 0;
+    int chunk_used = HK_CHUNK;                                                     // nothing reserved yet
+    for (int k = gl; k < HK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
+    __syncwarp();
+    const int stride = gridDim.x * HK_GROUPS;
+    for (int q0 = blockIdx.x * HK_GROUPS; q0 < t.Q; q0 += stride) {                // block-uniform trip count
+        const int q = q0 + grp;
+        const bool inq = q < t.Q;
+        int4 ri = make_int4(0, 0, 0, 0);
+        if (inq) ri = __ldg(&t.RI[q]);
+        const int off = (int)((unsigned)ri.w >> 6), La = inq ? (ri.w & 63) + 1 : 0;
+        const bool heavy = inq && read_is_heavy(La, rclass, q);                    // every rank lists (and later runs) ALL heavy reads
+        const unsigned hv = __ballot_sync(FULL, heavy && gl == 0);
+        if (hv) {
+            unsigned hb = 0;
+            if (lane == 0) hb = atomicAdd(n_heavy, (unsigned)__popc(hv));
+            hb = __shfl_sync(FULL, hb, 0);
+            if (heavy && gl == 0) heavy_list[hb + __popc(hv & ltmask)] = q;
+        }
+        const bool light = inq && !heavy && shard_owns(q, shard, nshard);
+        const int maxLa = __reduce_max_sync(FULL, light ? La : 0);
+        for (int fi = 0; fi < maxLa; fi++) {
+            const bool act = light && fi < La;
+            int4 f = make_int4(0, 0, 0, 0);
+            int2 band = make_int2(1, 0);
+            if (act) { f = rm0(t, off + fi); band = rm2(t, off + fi); }
+            for (int ch = 0;; ch++) {
+                const int p = band.x + ch * 8 + gl;
+                const bool v = act && p <= band.y;
+                if (!__any_sync(FULL, v)) break;                                    // every group of the warp is through its band
+                int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
+                if (v) c0 = __ldg(&t.SR0[p]);
+                const int b = c0.w & QMASK;
+                bool hit = v && b != q && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z);   // cluster.py:157, T >= 1
+                if (hit) {                                                          // a filter only: k_eval's canonical rule is exact
+                    int2 *hs = &sHash[grp][b & (HK_HASH - 1)];
+                    const int2 h = *hs;
+                    if (h.x == b && h.y == q) hit = false;                          // an earlier hit of (q, b) is on the list already
+                    else *hs = make_int2(b, q);
+                }
+                const unsigned hm = __ballot_sync(FULL, hit);
+                if (hm) {
+                    const int n = __popc(hm);
+                    if (chunk_used + n > HK_CHUNK) {
+                        for (int k = chunk_used + lane; k < HK_CHUNK; k += 32) hits[chunk_base + k] = make_int2(-1, -1);
+                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)HK_CHUNK);
+                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                        chunk_used = 0;
+                        if (chunk_base + HK_CHUNK > cap) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                    }
+                    if (hit) hits[chunk_base + chunk_used + __popc(hm & ltmask)] = make_int2((int)((unsigned)q | ((unsigned)fi << 26)), p);
+                    chunk_used += n;
+                }
+                __syncwarp();                                                       // filter updates visible to the next step
+            }
+        }
+    }
+    if (chunk_used < HK_CHUNK)
+        for (int k = chunk_used + lane; k < HK_CHUNK; k += 32) hits[chunk_base + k] = make_int2(-1, -1);
+}
+
+// One lane per hit.  La <= 4 always (light reads); partners with more than 4 fillings take the loop over global lists.
+#define EV_THREADS 256
+__global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
+                                                     unsigned long long cap, unsigned *cp, unsigned long long *n_tests,
+                                                     unsigned long long *n_real) {
+    __shared__ int s_umax[LMAX + 1];
+    for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long n = *n_slots;
+    if (n > cap) n = cap;
+    unsigned long long tests = 0, real = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * EV_THREADS;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * EV_THREADS + (threadIdx.x & ~31u); i0 < n; i0 += stride) {   // warp-uniform
+        const unsigned long long i = i0 + (threadIdx.x & 31);
+        int2 h = make_int2(-1, -1);
+        if (i < n) h = hits[i];
+        int q = 0, fa = 0, p = 0, b = 0, La = 0, Lb = 0, offa = 0, offb = 0;
+        bool small = false, gen = false;
+        if (h.x >= 0) {
+            q = h.x & QMASK; fa = (int)((unsigned)h.x >> 26); p = h.y;
+            const int4 c0 = __ldg(&t.SR0[p]), c1 = __ldg(&t.SR1[p]), ria = __ldg(&t.RI[q]);
+            b = c0.w & QMASK;
+            if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {               // cluster.py:178-183
+                offa = (int)((unsigned)ria.w >> 6); La = (ria.w & 63) + 1;
+                offb = (int)((unsigned)c1.w >> 6); Lb = (c1.w & 63) + 1;
+                gen = Lb > 4;
+                small = !gen;
+            }
+        }
+        // ---- lists of up to 4 fillings in registers; rows / columns nobody in the warp has are skipped warp-uniformly
+        const int mLa = __reduce_max_sync(FULL, small ? La : 0), mLb = __reduce_max_sync(FULL, small ? Lb : 0);
+        int4 A[4], B[4];
+        int pb[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            A[k] = make_int4(-1, 0, 0, 0x7fffffff); B[k] = make_int4(-2, 0, 0, 0x7fffffff); pb[k] = 0x7fffffff;
+            if (k < mLa) { if (small && k < La) A[k] = rm0(t, offa + k); }
+            if (k < mLb) { if (small && k < Lb) { B[k] = rm0(t, offb + k); pb[k] = rm1(t, offb + k).x; } }
+        }
+        unsigned m[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned r = 0;
+            if (k < mLa) {
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    if (g < mLb) r |= (matchT<false>(A[k], B[g]) ? 1u : 0u) << g;
+            }
+            m[k] = r;
+        }
+        bool canon = small;
+        int nmatch = 0;
+        {
+            unsigned used = 0, row = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < fa && m[k]) canon = false;                                  // an earlier filling of a matches b: not the first hit
+                if (k == fa) row = m[k];
+                const unsigned avail = m[k] & ~used;                                // greedy first fit (cluster.py:152-161)
+                if (avail) { used |= avail & (0u - avail); nmatch++; }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                if (((row >> g) & 1u) && pb[g] < p) canon = false;                  // b has a matching filling at a lower position
+        }
+        if (gen) {                                                                  // b has more than 4 fillings (rare): global lists
+            unsigned long long used = 0;
+            canon = true; nmatch = 0;
+            for (int k = 0; k < La; k++) {
+                const int4 a = rm0(t, offa + k);
+                bool taken = false;
+                for (int g = 0; g < Lb; g++) {
+                    const int4 bq = rm0(t, offb + g);
+                    if (matchT<false>(a, bq)) {
+                        if (k < fa || (k == fa && rm1(t, offb + g).x < p)) canon = false;
+                        if (!taken && !((used >> g) & 1ull)) { used |= 1ull << g; nmatch++; taken = true; }
+                    }
+                }
+            }
+            if (canon) atomicOr(&cp[q], CP_LONG);                                   // the replay has to WALK this read
+        }
+        int2 e = make_int2(-1, -1);
+        if ((small || gen) && canon && nmatch > 0) {
+            const bool pass = (La + Lb - nmatch) <= s_umax[nmatch];                 // cluster.py:165-170,218-219
+            tests++; real += pass;
+            e = make_int2(q, (int)((unsigned)b | (pass ? 0u : EB_NOPASS)));
+            atomicAdd(&cp[q], 0x10000u + (pass ? 1u : 0u));
+        }
+        if (i < n) hits[i] = e;
+    }
+    for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
+    if ((threadIdx.x & 31) == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
+}
+
+// Saturating set of the light reads from their counters (complete for every read after the multi-GPU sum-all-reduce of cp):
+// isP, how many partner records the replay will get (plinfo.n: -1 = WALK), and the counter reset for k_plist's fill.
+__global__ void k_light_sat(Tab t, const int *__restrict__ rclass, unsigned *cp, int *isP, PLInfo *plinfo, int *plcount,
+                            unsigned long long *pl_slots) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= t.Q) return;
+    const int La = (__ldg(&t.RI[q]).w & 63) + 1;
+    if (read_is_heavy(La, rclass, q)) { plcount[q] = 0; return; }                  // isP / plinfo of heavy reads: k_pair
+    const unsigned c = cp[q];
+    const int pass = (int)(c & 0xffffu), np = (int)((c >> 16) & 0x7fffu);
+    const bool sat = pass >= t.Tedge;
+    isP[q] = sat;
+    int n = 0;
+    if (sat) n = (np <= RP_K && !(c & CP_LONG)) ? np : -1;
+    if (n < 0) atomicAdd(pl_slots + 3, 1ull);                                      // (reads the replay has to WALK)
+    PLInfo pi; pi.off = 0; pi.n = n; pi.pad = 0;
+    plinfo[q] = pi;
+    plcount[q] = n > 0 ? n : 0;
+    cp[q] = 0;
+}
+// where the records of every light saturating read start: after the heavy reads' chunks (*pl_slots) + the scan of plcount
+__global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__restrict__ ploff, PLInfo *plinfo,
+                         unsigned long long *pl_slots, const int64_t *__restrict__ light_total, unsigned long long cap_pl, int *err) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q == 0) {
+        if (pl_slots[0] + (unsigned long long)*light_total > cap_pl) atomicOr(err, EF_OVERFLOW);
+        atomicAdd(pl_slots + 2, (unsigned long long)*light_total);                  // (statistics: records written)
+    }
+    if (q >= Q) return;
+    if (plcount[q] > 0) plinfo[q].off = pl_slots[0] + (unsigned long long)ploff[q];
+}
+// One lane per recorded pair: the partner record of saturating read a about partner b (see PLInfo / k_pair for the fields)
+#define PLT_THREADS 256
+__global__ void __launch_bounds__(PLT_THREADS) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
+                                                       unsigned long long n_fixed, unsigned long long cap, const int *__restrict__ isP,
+                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
+    unsigned long long n = n_slots ? *n_slots : n_fixed;
+    if (n > cap) n = cap;
+    const unsigned long long stride = (unsigned long long)gridDim.x * PLT_THREADS;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * PLT_THREADS + threadIdx.x; i < n; i += stride) {
+        const int2 e = ent[i];
+        const int a = e.x;
+        if (a < 0 || ((unsigned)e.y & EB_HEAVY)) continue;
+        if (!__ldg(&isP[a])) continue;
+        const PLInfo pi = plinfo[a];
+        if (pi.n <= 0) continue;
+        const int b = e.y & QMASK;
+        const int wa = __ldg(&t.RI[a]).w, wb = __ldg(&t.RI[b]).w;
+        const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
+        const unsigned slot = atomicAdd(&cp[a], 1u);
+        if ((int)slot >= pi.n || La > 4 || Lb > 4) { atomicOr(err, EF_OVERFLOW); continue; }   // (cannot happen: counted by k_eval)
+        int4 A[4]; int pa[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            A[k] = make_int4(-1, 0, 0, 0); pa[k] = -1;
+            if (k < La) { A[k] = rm0(t, offa + k); pa[k] = rm1(t, offa + k).x; }
+        }
+        int key[4] = {-1, -1, -1, -1};
+        unsigned cg = 0;
+        for (int gb = 0; gb < Lb; gb++) {
+            const int4 i0 = rm0(t, offb + gb);
+            const int pg = rm1(t, offb + gb).x;
+            int best = -1, bestfa = 0;
+#pragma unroll
+            for (int fa = 0; fa < 4; fa++) {
+                if (fa < La && A[fa].x == i0.x && A[fa].y <= i0.z && A[fa].z >= i0.y) {   // closed overlap: a scan of one visits the other
+                    key[fa] = max(key[fa], pg);
+                    if (pa[fa] > best) { best = pa[fa]; bestfa = fa; }
+                }
+            }
+            if (best >= 0) cg |= (4u | (unsigned)bestfa) << (4 * gb);
+        }
+        const unsigned long long at = pi.off + slot;
+        PL[2 * at] = make_int4((int)((unsigned)b | (((unsigned)e.y & EB_NOPASS) ? 0u : 0x80000000u)), wb, (int)cg, 0);
+        PL[2 * at + 1] = make_int4(key[0], key[1], key[2], key[3]);
+    }
+}
+// multi-GPU: this rank's recorded pairs of light saturating reads with partner lists, compacted for the all-gather
+__global__ void k_pent_compact(const int2 *__restrict__ ent, unsigned long long n, const int *__restrict__ isP,
+                               const PLInfo *__restrict__ plinfo, int2 *out, unsigned long long *n_out) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    bool keep = false;
+    int2 e = make_int2(-1, -1);
+    if (i < n) {
+        e = ent[i];
+        keep = e.x >= 0 && !((unsigned)e.y & EB_HEAVY) && isP[e.x] && plinfo[e.x].n > 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    unsigned long long at = 0;
+    if ((threadIdx.x & 31) == 0 && m) at = atomicAdd(n_out, (unsigned long long)__popc(m));
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (keep) out[at + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = e;
+}

@@ -215,6 +215,11 @@ __global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp
 // RM[2m] = {chrom, start, end, T}, RM[2m+1] = {pos, ub (closed band, replay), lbT, ubT (tight band, pair kernel)}: one
 // 32-byte sector per filling in read-major order, written once by k_bands
 #define QMASK 0x3ffffff
+#define PCAP 128                // a sorted position whose tight band is longer makes its read "heavy" (kernels_hits.cuh)
+#define EB_NOPASS 0x80000000u   // entry.y bit 31: b is a partner of a (n > 0) but a -> b fails the Jaccard cutoff
+#define EB_HEAVY 0x40000000u    // entry.y bit 30: recorded by k_pair for a heavy read (its partner records exist already)
+// per-read word `cp` (light reads): bits 0-15 passing partners, bits 16-30 partners, bit 31 a partner has > 4 fillings
+#define CP_LONG 0x80000000u
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
                           const int4 *__restrict__ IT0, const int2 *__restrict__ IT1, const int4 *__restrict__ RI,
                           double overlap, int4 *SR0, int4 *SR1, int *s_m,
@@ -245,9 +250,10 @@ __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__rest
 // nothing before the first position whose prefix-max end reaches start_p + T_p.
 __global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restrict__ s_m, const int *__restrict__ s_chrom,
                         const int *__restrict__ pmaxS, const int *__restrict__ chrom_lo, const int *__restrict__ chrom_hi,
-                        int4 *RM, unsigned long long *band_pairs, unsigned long long *tight_pairs) {
+                        int4 *RM, int *rclass, unsigned long long *band_pairs, unsigned long long *tight_pairs,
+                        unsigned long long *light_pairs) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    long long mine = 0, mineT = 0;
+    long long mine = 0, mineT = 0, mineL = 0;
     if (p < D) {
         const int4 me = SR0[p];
         const int c = s_chrom[p];
@@ -273,16 +279,22 @@ __global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restri
         RM[2 * m + 1] = make_int4(p, lo, lb, tl);
         mine = lo - p;
         mineT = tl - lb;
+        if (mineT > PCAP) atomicOr(&rclass[me.w & QMASK], 1);        // hotspot: its read goes through k_pair (early exit)
+        else mineL = mineT;                                          // upper bound of the hits k_hits can list for this position
     }
-    __shared__ long long s_sum[2][8];                                 // one pair of global atomics per block
+    __shared__ long long s_sum[3][8];                                 // one triple of global atomics per block
 #pragma unroll
-    for (int o = 16; o; o >>= 1) { mine += __shfl_down_sync(0xffffffffu, mine, o); mineT += __shfl_down_sync(0xffffffffu, mineT, o); }
-    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = mine; s_sum[1][threadIdx.x >> 5] = mineT; }
+    for (int o = 16; o; o >>= 1) {
+        mine += __shfl_down_sync(0xffffffffu, mine, o); mineT += __shfl_down_sync(0xffffffffu, mineT, o);
+        mineL += __shfl_down_sync(0xffffffffu, mineL, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = mine; s_sum[1][threadIdx.x >> 5] = mineT; s_sum[2][threadIdx.x >> 5] = mineL; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        long long a = 0, b = 0;
-        for (int w = 0; w < 8; w++) { a += s_sum[0][w]; b += s_sum[1][w]; }
+        long long a = 0, b = 0, c = 0;
+        for (int w = 0; w < 8; w++) { a += s_sum[0][w]; b += s_sum[1][w]; c += s_sum[2][w]; }
         if (a) atomicAdd(band_pairs, (unsigned long long)a);
         if (b) atomicAdd(tight_pairs, (unsigned long long)b);
+        if (c) atomicAdd(light_pairs, (unsigned long long)c);
     }
 }

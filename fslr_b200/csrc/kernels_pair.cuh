@@ -134,8 +134,12 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 //           a's scan of fa first meets b.
 struct PLInfo { unsigned long long off; int n; int pad; };
 
+// heavy_list != NULL: the kernel runs over the reads k_hits listed as heavy (more than 4 fillings, or a hotspot band), every
+// rank over all of them (their partner records and isP are needed everywhere; they are few); NULL: over all query reads
+// (--overlap <= 0).  Relation entries are only recorded for the reads this shard owns.
 template <bool ALLMATCH>
-__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um, int shard, int nshard, int lists_only, int *isP, int2 *entries,
+__global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um, int shard, int nshard, const int *__restrict__ heavy_list,
+                                                         const unsigned *__restrict__ n_heavy, int *isP, int2 *entries,
                                                          unsigned long long *n_slots, unsigned long long cap_entries,
                                                          int4 *PL, PLInfo *plinfo, unsigned long long *pl_slots, unsigned long long cap_pl,
                                                          unsigned long long *n_tests, unsigned long long *n_real, int *err) {
@@ -153,12 +157,11 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
     int chunk_used = PK_CHUNK, pl_used = PL_CHUNK;                                 // nothing reserved yet
     for (int k = gl; k < PK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
     const int stride = gridDim.x * PK_GROUPS;
-    for (int q0 = blockIdx.x * PK_GROUPS; q0 < t.Q; q0 += stride) {                // block-uniform trip count
-        const int q = q0 + grp;
-        const bool mine = nshard <= 1 || ((q >> 8) % nshard) == shard;             // 256-read groups, round robin over ranks
-        // pass 0: the reads of this shard; pass 1 (multi-GPU, after the exchange of isP): partner lists of the saturating
-        // reads the other shards own
-        const bool live = q < t.Q && (lists_only ? (!mine && __ldg(&isP[q]) != 0) : mine);
+    const int nq = heavy_list ? (int)*n_heavy : t.Q;
+    for (int q0 = blockIdx.x * PK_GROUPS; q0 < nq; q0 += stride) {                 // block-uniform trip count
+        const bool live = q0 + grp < nq;
+        const int q = live ? (heavy_list ? __ldg(&heavy_list[q0 + grp]) : q0 + grp) : -1;
+        const bool mine = live && (nshard <= 1 || ((q >> 8) % nshard) == shard);   // 256-read groups, round robin over ranks
         int4 ri = make_int4(0, 0, 0, 0);
         if (live) ri = __ldg(&t.RI[q]);
         const int off = (int)((unsigned)ri.w >> 6), La = live ? (ri.w & 63) + 1 : 0;
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
             sB[grp][gl] = make_int4(bd.x, bd.y, pu.x, pu.y);
         }
         __syncwarp();
-        int cnt = lists_only ? t.Tedge : 0;                                        // passing partners so far
+        int cnt = 0;                                                               // passing partners so far
         int nPart = 0;                                                             // partners buffered for the replay; -1: too many / too long
         const int maxLa = __reduce_max_sync(FULL, La);
         for (int fi = 0; fi < maxLa; fi++) {
@@ -224,8 +227,11 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
                     }
                 }
                 // ---- relation entries of reads still below the threshold: warp-aggregated append
-                pass = pass && !lists_only && cnt < t.Tedge;
+                pass = pass && cnt < t.Tedge;
+                const unsigned pc = __ballot_sync(FULL, pass);
+                pass = pass && mine;
                 const unsigned pm = __ballot_sync(FULL, pass);
+                cnt += __popc(pc & gmask);
                 if (pm) {
                     const int n = __popc(pm);
                     if (chunk_used + n > PK_CHUNK) {
@@ -235,17 +241,16 @@ __global__ void __launch_bounds__(PK_WARPS * 32) k_pair(Tab t, const UmaxTab um,
                         chunk_used = 0;
                         if (chunk_base + PK_CHUNK > cap_entries) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
                     }
-                    if (pass) entries[chunk_base + chunk_used + __popc(pm & ltmask)] = make_int2(q, b);
+                    if (pass) entries[chunk_base + chunk_used + __popc(pm & ltmask)] = make_int2(q, (int)((unsigned)b | EB_HEAVY));
                     chunk_used += n;
                     real += (lane == 0) ? n : 0;
-                    cnt += __popc(pm & gmask);
                 }
                 __syncwarp();                                                       // filter updates visible to the next step
             }
         }
         // ---- saturating read: publish its partner records for the replay
         const bool sat = live && cnt >= t.Tedge;
-        if (live && gl == 0 && !lists_only) isP[q] = sat;
+        if (live && gl == 0) isP[q] = sat;
         const int nrec = (sat && nPart > 0) ? nPart : 0;
         int tot = nrec;                                                             // records of the warp's 4 groups
         tot = __shfl_sync(FULL, tot, 0) + __shfl_sync(FULL, tot, 8) + __shfl_sync(FULL, tot, 16) + __shfl_sync(FULL, tot, 24);

@@ -159,19 +159,28 @@ __device__ __forceinline__ unsigned char *put_dec(unsigned char *o, int v) {
     for (int k = nd - 1; k >= (v < 0); k--) { o[k] = (unsigned char)('0' + u % 10u); u /= 10u; }
     return o + nd;
 }
-// output length of every line: header + "\tcluster\tn_reads\n"; row: line + "\t<c>.0\t<n>.0\n"
+// main.py:334-342: the left merge leaves NaN for singletons, which makes `cluster` / `n_reads` float columns ("12.0");
+// a table in which every read ended in a cluster has no NaN and keeps integer columns ("12").  *any_single != 0 <=> floats.
+__global__ void k_tsv_any_single(int n_reads, const int *__restrict__ nreads, int *any_single) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool s = r < n_reads && nreads[r] == 1;
+    if (__syncthreads_or(s) && threadIdx.x == 0) *any_single = 1;
+}
+// output length of every line: header + "\tcluster\tn_reads\n"; row: line + "\t<c>.0\t<n>.0\n" (floats) or "\t<c>\t<n>\n"
 __global__ void k_tsv_outlen(int n_lines, const long long *__restrict__ line_start, const int *__restrict__ rid,
-                             const int *__restrict__ cluster, const int *__restrict__ nreads, long long *len) {
+                             const int *__restrict__ cluster, const int *__restrict__ nreads, const int *__restrict__ any_single,
+                             long long *len) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= n_lines) return;
     const long long body = line_start[l + 1] - 1 - line_start[l];
+    const int frac = *any_single ? 2 : 0;
     if (l == 0) len[l] = body + 17;                                     // "\tcluster\tn_reads\n"
-    else { const int r = rid[l - 1]; len[l] = body + 1 + dec_digits(cluster[r]) + 2 + 1 + dec_digits(nreads[r]) + 2 + 1; }
+    else { const int r = rid[l - 1]; len[l] = body + 1 + dec_digits(cluster[r]) + frac + 1 + dec_digits(nreads[r]) + frac + 1; }
 }
 // one warp per line: coalesced byte copy, lane 0 appends the two columns
 __global__ void k_tsv_emit(int n_lines, const unsigned char *__restrict__ text, const long long *__restrict__ line_start,
                            const int *__restrict__ rid, const int *__restrict__ cluster, const int *__restrict__ nreads,
-                           const long long *__restrict__ out_off, unsigned char *out) {
+                           const int *__restrict__ any_single, const long long *__restrict__ out_off, unsigned char *out) {
     const long long wg = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wg >= n_lines) return;
@@ -184,8 +193,10 @@ __global__ void k_tsv_emit(int n_lines, const unsigned char *__restrict__ text, 
         if (l == 0) { const char *h = "\tcluster\tn_reads\n"; for (int i = 0; i < 17; i++) q[i] = (unsigned char)h[i]; }
         else {
             const int r = rid[l - 1];
-            *q++ = '\t'; q = put_dec(q, cluster[r]); *q++ = '.'; *q++ = '0';
-            *q++ = '\t'; q = put_dec(q, nreads[r]); *q++ = '.'; *q++ = '0'; *q++ = '\n';
+            const bool fl = *any_single != 0;
+            *q++ = '\t'; q = put_dec(q, cluster[r]); if (fl) { *q++ = '.'; *q++ = '0'; }
+            *q++ = '\t'; q = put_dec(q, nreads[r]); if (fl) { *q++ = '.'; *q++ = '0'; }
+            *q++ = '\n';
         }
     }
 }

@@ -205,11 +205,12 @@ class Engine:
         return ClusterResult(ptab.out_cluster[:n].numpy().copy(), ptab.out_n_reads[:n].numpy().copy(),
                              bool(stats["no_clusters"]), stats)
 
-    # ---- multi-GPU: pair space sharded over ranks, one all-reduce + one all-gather
+    # ---- multi-GPU: pair space sharded over ranks, three exchange steps
     def run_sharded(self, dtab: DeviceTable, chrom_table, params: ClusterParams, rank, world, group=None):
-        """Every rank holds the whole table in HBM (dtab); the pair kernel runs on shard `rank` of `world`.
-        Exchange steps (torch.distributed, NCCL on GPUs): sum-all-reduce of the per-read passing-candidate counts,
-        then all-gather of each rank's spanning forest.  Every rank ends with the full result in dtab.out_*."""
+        """Every rank holds the whole table in HBM (dtab); candidate generation and the pair tests run on shard `rank` of `world`.
+        Exchange steps (torch.distributed, NCCL on GPUs): sum-all-reduce of the per-read partner counters (4 bytes per query
+        read), all-gather of the recorded pairs of saturating reads (8 bytes per pair: the replay needs them on every
+        rank), all-gather of each rank's spanning forest.  Every rank ends with the full result in dtab.out_*."""
         from .sharded import exchange_counts, exchange_forests
         p = self._params(chrom_table, params)
         t = self._table(dtab)
@@ -220,7 +221,17 @@ class Engine:
         self._check(self.lib.fslrc_mg_pair(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
         if n.value > 0 and world > 1:
             exchange_counts(torch.as_tensor(_DevView(ptr.value, (n.value,)), device=self.device), group)
-        self._check(self.lib.fslrc_mg_replay(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        self._check(self.lib.fslrc_mg_partners(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        npairs = int(n.value)
+        if world > 1:
+            local = (torch.as_tensor(_DevView(ptr.value, (2 * npairs,)), device=self.device) if npairs > 0
+                     else torch.zeros(0, dtype=torch.int32, device=self.device))
+            pairs, per_rank = exchange_forests(local, group)                   # (same variable-length all-gather)
+            npairs = int(sum(per_rank))
+            pptr = pairs.data_ptr() if npairs > 0 else None
+        else:
+            pptr = ptr.value if npairs > 0 else None
+        self._check(self.lib.fslrc_mg_replay(self.ctx, rank, world, pptr, npairs, C.byref(ptr), C.byref(n)))
         ne = int(n.value)
         if world > 1:
             local = (torch.as_tensor(_DevView(ptr.value, (2 * ne,)), device=self.device) if ne > 0
@@ -287,8 +298,8 @@ class HostPipeline:
         import os
         from concurrent.futures import ThreadPoolExecutor
         self.engines = [Engine(device) for _ in range(depth)]
-        if blocking_sync is None:
-            blocking_sync = os.environ.get("FSLR_B200_BLOCKING_SYNC", "0") == "1"
+        if blocking_sync is None:                          # default: sleep in the waits — spinning worker threads starve each other
+            blocking_sync = os.environ.get("FSLR_B200_BLOCKING_SYNC", "1") == "1"   # on hosts that give the process few cores
         for e in self.engines:                            # worker threads sleep in their waits instead of spinning
             e.lib.fslrc_set_blocking_sync(e.ctx, int(bool(blocking_sync)))
         self.streams = [torch.cuda.Stream(device=self.engines[0].device) for _ in range(depth)]

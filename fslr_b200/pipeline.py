@@ -70,8 +70,11 @@ def cluster_step(bed_file, chr_lengths, cluster_mask="subtelomere", jaccard_cuto
         print("No clusters were found.", file=sys.stderr)                        # main.py:247-249
         return None
     bed_file = bed_file.copy()
-    bed_file["cluster"] = res.cluster[table.read_id].astype(np.float64)          # main.py:334-342 (floats from the NaN merge)
-    bed_file["n_reads"] = res.n_reads[table.read_id].astype(np.float64)
+    # main.py:334-342: the left merge leaves NaN on singleton rows, so the columns are floats — unless every read ended in
+    # a cluster, in which case pandas keeps the integer dtype
+    dt = np.float64 if bool((res.n_reads == 1).any()) else np.int64
+    bed_file["cluster"] = res.cluster[table.read_id].astype(dt)
+    bed_file["n_reads"] = res.n_reads[table.read_id].astype(dt)
     if out_base:
         bed_file.to_csv(f"{out_base}.mappings.cluster.bed", index=False, sep="\t")                 # main.py:349
         rep = gcluster.choose_alignment(bed_file)                                                   # main.py:351-352

@@ -21,7 +21,7 @@ extern "C" {
 #endif
 
 #define FSLRC_MAX_FILLINGS 64      /* fillings per read after keep_fillings/masking (n_alignments - 2) */
-#define FSLRC_N_STAGES 12
+#define FSLRC_N_STAGES 14
 
 enum {
     FSLRC_OK = 0,
@@ -92,7 +92,7 @@ typedef struct {
     int64_t n_query_reads;         /* reads with >= 1 interval (cluster.py:189-191) */
     int64_t band_pairs;            /* interval-level candidate pairs {i<j<=ub(i)} (what search_values can return) */
     int64_t pair_tests;            /* full read-pair tests evaluated on the GPU (a10+a11+a13 of SURVEY §8a) */
-    int64_t relation_entries;      /* passing (query, other) pairs recorded by the pair kernel */
+    int64_t relation_entries;      /* passing (query, other) pairs recorded by the pair stage */
     int64_t saturating_reads;      /* reads that can reach edge_threshold (replayed in query order) */
     int64_t edges;                 /* edges handed to union-find */
     int64_t components;            /* clusters with >= 2 reads */
@@ -108,7 +108,7 @@ void fslrc_destroy(fslrc_ctx *ctx);
 const char *fslrc_last_error(const fslrc_ctx *ctx);
 const char *fslrc_stage_name(int stage);
 int fslrc_version(void);
-/* number of this library's own kernels launched through `ctx` so far (CUB's sort/scan kernels are not counted) */
+/* number of kernels launched through `ctx` so far (every kernel on the path is this library's own: no CUB / Thrust) */
 long long fslrc_launch_count(const fslrc_ctx *ctx);
 
 /* The whole step, main.py:233-257,334-342 (keep_fillings -> prepare_data -> build_interval_trees ->
@@ -125,15 +125,21 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
 
 /* ---- multi-GPU staging: the interval table is replicated, the pair space is sharded ----
  * fslrc_mg_prepare     : ingestion + sort/band on this device (identical on every rank)
- * fslrc_mg_pair        : pair kernel on shard `rank` of `world`; leaves the per-read passing-candidate counts
- *                        in a device int32 [n_query_reads] buffer (*counts) that the caller sum-all-reduces
- * fslrc_mg_replay      : after the all-reduce: replay of saturating reads (replicated, it is sequential) and
- *                        union-find over this rank's edges; leaves a spanning forest (int32 pairs) in *forest
+ * fslrc_mg_pair        : candidate generation + pair tests for the query reads of shard `rank` of `world`; leaves one
+ *                        counter word per query read (passing partners / partners of the reads this rank owns, 0 for the
+ *                        others) in a device int32 [n_query_reads] buffer (*counts) that the caller SUM-all-reduces in place
+ * fslrc_mg_partners    : after the all-reduce: the saturating set, and this rank's recorded pairs (a, b | flags: int32
+ *                        pairs) of the saturating reads whose partner lists the replay needs (*pairs, device); the caller
+ *                        all-gathers them — 8 bytes per pair instead of re-evaluating the pairs on every rank
+ * fslrc_mg_replay      : takes the all-gathered pairs: partner records, replay of saturating reads (replicated, it is
+ *                        sequential) and union-find over this rank's edges; leaves a spanning forest (int32 pairs) in *forest
  * fslrc_mg_finish      : takes the all-gathered forests, final union-find + numbering
  */
 int fslrc_mg_prepare(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_params *params, void *stream);
 int fslrc_mg_pair(fslrc_ctx *ctx, int rank, int world, int32_t **counts, int64_t *n_counts);
-int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, int32_t **forest, int64_t *n_forest_edges);
+int fslrc_mg_partners(fslrc_ctx *ctx, int rank, int world, int32_t **pairs, int64_t *n_pairs);
+int fslrc_mg_replay(fslrc_ctx *ctx, int rank, int world, const int32_t *all_pairs, int64_t n_all_pairs,
+                    int32_t **forest, int64_t *n_forest_edges);
 int fslrc_mg_finish(fslrc_ctx *ctx, const int32_t *all_forest, int64_t n_edges,
                     int32_t *out_cluster, int32_t *out_n_reads, fslrc_stats *stats);
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
     assert lib.fslrc_version() >= 1
     lib.fslrc_stage_name.restype = ctypes.c_char_p
-    assert lib.fslrc_stage_name(6) == b"pair_kernel"
+    assert lib.fslrc_stage_name(7) == b"pair_kernel"
 
 
 def test_struct_layout_matches_header():

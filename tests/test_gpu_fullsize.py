@@ -35,3 +35,32 @@ def test_fullsize_vs_oracle(name):
     # idempotence: a second run gives the same answer (atomics only change internal edge order)
     res2 = get_engine(0).cluster(t, p)
     assert np.array_equal(res2.cluster, res.cluster)
+
+
+@pytest.fixture(scope="module")
+def c3_table():
+    from fslr_b200 import synth
+    from fslr_b200.table import ColumnarTable
+    return ColumnarTable.from_synth(synth.make_config("C3"))
+
+
+def _sweep():
+    from fslr_b200 import synth
+    return list(synth.C3_CUTOFF_SWEEP)
+
+
+@pytest.mark.parametrize("cut", _sweep())
+def test_c3_fullsize_cutoff_sweep(c3_table, cut):
+    """BASELINE config 3 at full size (1M reads, --cluster-mask subtelomere,L1_TALEN) under every --jaccard-cutoffs list of the
+    sweep (main.py:219), bit-exact against the oracle."""
+    from fslr_b200 import synth
+    from fslr_b200.engine import get_engine
+    from fslr_b200.table import ClusterParams
+    from oracle import oracle as orc
+    p = ClusterParams.from_options(c3_table, cluster_mask=synth.CONFIG_MASK["C3"], jaccard_cutoffs=cut)
+    res = get_engine(0).cluster(c3_table, p)
+    _props(res, c3_table.n_reads)
+    ocl, onr, ost = orc.oracle_cluster(c3_table, p)
+    assert np.array_equal(res.cluster, ocl)
+    assert np.array_equal(res.n_reads, onr)
+    assert res.stats["components"] == ost["components"]

@@ -1,7 +1,7 @@
 """The multi-GPU C-ABI stages (fslrc_mg_*) with world_size 2 and 3 EMULATED on one GPU: one context per rank, the
-ranks' kernels run one after the other (nothing waits across contexts) and the two exchange steps — sum of the per-read
-saturation flags, concatenation of the spanning forests — are done here with torch ops standing in for the NCCL
-all-reduce / all-gather of fslr_b200/sharded.py.  Every rank must end with the single-GPU (= oracle) result."""
+ranks' kernels run one after the other (nothing waits across contexts) and the three exchange steps — sum of the per-read
+partner counters, concatenation of the recorded pairs of saturating reads, concatenation of the spanning forests — are done
+here with torch ops standing in for the NCCL all-reduce / all-gathers of fslr_b200/sharded.py.  Every rank must end with the single-GPU (= oracle) result."""
 import ctypes as C
 
 import numpy as np
@@ -32,10 +32,19 @@ def _run_emulated(table, params, world):
         for c in counts:
             c.copy_(total)
     torch.cuda.synchronize()
+    pairs = []
+    for r, e in enumerate(engines):
+        ptr, n = C.c_void_p(), C.c_int64()
+        e._check(e.lib.fslrc_mg_partners(e.ctx, r, world, C.byref(ptr), C.byref(n)))
+        pairs.append(torch.as_tensor(_DevView(ptr.value, (2 * n.value,)), device=dev).clone() if n.value > 0
+                     else torch.zeros(0, dtype=torch.int32, device=dev))
+    allp = torch.cat(pairs).contiguous()                                                 # all-gather
+    torch.cuda.synchronize()
     forests = []
     for r, e in enumerate(engines):
         ptr, n = C.c_void_p(), C.c_int64()
-        e._check(e.lib.fslrc_mg_replay(e.ctx, r, world, C.byref(ptr), C.byref(n)))
+        e._check(e.lib.fslrc_mg_replay(e.ctx, r, world, allp.data_ptr() if allp.numel() else None, allp.numel() // 2,
+                                       C.byref(ptr), C.byref(n)))
         forests.append(torch.as_tensor(_DevView(ptr.value, (2 * n.value,)), device=dev).clone() if n.value > 0
                        else torch.zeros(0, dtype=torch.int32, device=dev))
     allf = torch.cat(forests).contiguous()                                               # all-gather
