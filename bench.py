@@ -271,7 +271,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fslr_b200.engine import DeviceTable, Engine, HostPipeline, PinnedTable
+    from fslr_b200.engine import DeviceTable, DeviceWireTable, Engine, HostPipeline, PinnedTable
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU port)")
     torch.cuda.set_device(local)
@@ -283,7 +283,7 @@ def main():
     R, A = ct.n_reads, ct.n_rows
     dtab = DeviceTable(ct, eng.device)
     t_prep = time.perf_counter()
-    ptab = PinnedTable(ct, compact=True)                      # the table in its wire format: 19 B/row (see PinnedTable)
+    ptab = PinnedTable(ct, compact=True)                      # the table in its wire format: 13.25 B/row (see PinnedTable)
     t_prep = time.perf_counter() - t_prep
 
     def barrier():
@@ -298,16 +298,18 @@ def main():
             return eng.run_sharded(dtab, ct, params, rank, world)
         return eng.run_resident(dtab, ct, params)
 
+    dwire = DeviceWireTable(ptab, eng.device, world) if (world > 1 and not samples) else None
+
     def step_e2e():
         if samples:
             return eng.run_host(ptab, ct, params)
         if world > 1:
-            # every rank uploads 1/world of the rows over its own PCIe link; NVLink all-gather rebuilds the columns
-            eng.upload_sharded(ptab, dtab, rank, world)
-            st = eng.run_sharded(dtab, ct, params, rank, world)
+            # every rank uploads 1/world of every wire column over its own PCIe link; in-place NVLink all-gathers complete them
+            dwire.upload(ptab, rank, world)
+            st = eng.run_sharded(dwire, ct, params, rank, world)
             if rank == 0:                                     # the job's result leaves the box once
-                ptab.out_cluster[:R].copy_(dtab.out_cluster[:R], non_blocking=True)
-                ptab.out_n_reads[:R].copy_(dtab.out_n_reads[:R], non_blocking=True)
+                ptab.out_cluster[:R].copy_(dwire.out_cluster[:R], non_blocking=True)
+                ptab.out_n_reads[:R].copy_(dwire.out_n_reads[:R], non_blocking=True)
             torch.cuda.synchronize()
             return st
         return eng.run_host(ptab, ct, params)
@@ -348,10 +350,11 @@ def main():
     ms, sts, launches = timed(step_resident, args.steps)
     step_e2e()
     ms_e2e, sts_e2e, _ = timed(step_e2e, args.steps)
-    e2e_mode = ("one blocking C-ABI call per step, one table at a time: pinned host columns in their 19 B/row wire format (chrom uint8, "
-                "n_alignments uint16, aln_size = qend - qstart and read_id from run lengths rebuilt on the device) in, both result columns out") \
+    e2e_mode = ("one blocking C-ABI call per step, one table at a time: pinned host columns in their %.2f B/row wire format (chrom uint8, "
+                "n_alignments / qstart / qend uint16, rend as int16 span, aln_size = qend - qstart and read_id from run lengths rebuilt on the "
+                "device) in, both result columns out" % (ptab.h2d_bytes / max(A, 1))) \
         if (world == 1 or samples) else \
-        "every rank uploads 1/%d of the rows (19 B/row on the wire), NVLink all-gather of the columns, sharded step, rank 0 downloads the result" % world
+        "every rank uploads 1/%d of the rows (%.2f B/row on the wire), in-place NVLink all-gather of every wire column, sharded step, rank 0 downloads the result" % (world, ptab.h2d_bytes / max(A, 1))
     e2e_serial = {"value": (world if samples else 1) * R * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                   "h2d_bytes_per_step": ptab.h2d_bytes, "d2h_bytes_per_step": ptab.d2h_bytes, "mode": e2e_mode,
                   "host_prep_s_untimed": t_prep}

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libfslr_b200.so")
+LIB_PATH = os.environ.get("FSLR_B200_LIB") or os.path.join(_HERE, "csrc", "libfslr_b200.so")   # (the variable: tuning builds)
 MAX_FILLINGS = 64
 N_STAGES = 14
 
@@ -24,7 +24,8 @@ class Table(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("n_reads", C.c_int64)] + \
                [(n, C.c_void_p) for n in ("read_id", "chrom", "rstart", "rend", "aln_size", "qstart", "qend", "n_alignments")] + \
                [("order", C.c_void_p), ("n_order", C.c_int64), ("chrom_u8", C.c_void_p), ("n_alignments_u16", C.c_void_p),
-                ("rows_per_read_u8", C.c_void_p), ("aln_size_is_qspan", C.c_int64)]
+                ("rows_per_read_u8", C.c_void_p), ("aln_size_is_qspan", C.c_int64), ("rspan_i16", C.c_void_p),
+                ("qstart_u16", C.c_void_p), ("qend_u16", C.c_void_p)]
 
 
 class Params(C.Structure):

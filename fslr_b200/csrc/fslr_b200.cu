@@ -36,6 +36,7 @@
 
 #define FSLRC_VERSION 1
 #define LMAX FSLRC_MAX_FILLINGS
+#define NCNT 56                 // device counters of one call (Pipe::cnt); the error word follows them in the pinned read-back
 
 enum { EF_RANGE = 1, EF_ZERO = 2, EF_TOOMANY = 4, EF_NALN = 8, EF_OVERFLOW = 16 };
 
@@ -123,7 +124,8 @@ struct Pipe {
     int *err;
     int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entry slots,6 nP,7 pedge slots,8 edges,9 ncl,10 forest,
                              //                  11 singletons, 12 runs, 13 entries, 14 tight band, 40-43 partner-record slots / stats,
-                             //                  44 tight band of light positions, 45 light partner records, 46 heavy reads, 47 P-pairs (mg)
+                             //                  44 tight band of light positions, 45 light partner records, 46 heavy reads, 47 P-pairs (mg),
+                             //                  48 largest start (fast ingest)
     int *q_of_rid, *rid_of_q;
     int4 *SR0, *SR1, *RM, *RI;
     int *pmaxS, *s_chrom, *chrom_lo, *chrom_hi;
@@ -215,13 +217,13 @@ static cudaError_t ctx_sync(fslrc_ctx *ctx) {
     return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_block);
 }
 static int read_counts(fslrc_ctx *ctx, Pipe *P) {   // device counters + error word -> pinned host
-    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, 48 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->h_pin + 48, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin, P->cnt, NCNT * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_pin + NCNT, P->err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx_sync(ctx));
     return 0;
 }
 static int err_code(fslrc_ctx *ctx) {
-    int e = (int)(ctx->h_pin[48] & 0xffffffff);
+    int e = (int)(ctx->h_pin[NCNT] & 0xffffffff);
     if (!e) return 0;
     if (e & EF_RANGE) return fail(ctx, FSLRC_ERR_RANGE, "a table value is out of range (read_id/chrom id, negative coordinate, n_alignments >= 65535 or a bad `order`)");
     if (e & EF_ZERO) return fail(ctx, FSLRC_ERR_ZERO_DIVISOR, "aln_size, qlen2 or n_alignments <= 0 on a filling (the reference raises ZeroDivisionError)");
@@ -231,19 +233,132 @@ static int err_code(fslrc_ctx *ctx) {
 }
 static int bits_for(int64_t n) { int b = 1; while ((1ll << b) < n && b < 32) b++; return b; }
 
+static int pipe_bands(fslrc_ctx *ctx, Pipe *P, const int *s_dp, const int *rmidx, const int *it_q, const int4 *IT0, const int2 *IT1, const int4 *DREC);
+
+// exclusive sum of int64 (k_reads_fast's packed (count << 32 | L) flags)
+static int xscan64(fslrc_ctx *ctx, Pipe *P, const long long *in, long long *out, int n, int64_t *total) {
+    cudaStream_t st = ctx->stream;
+    if (n <= 0) { if (total) CK(cudaMemsetAsync(total, 0, sizeof(int64_t), st)); return 0; }
+    const int tiles = nblk(n, prims::SC_TILE);
+    int r = prim_scratch(ctx, P, sizeof(unsigned long long) * tiles); if (r) return r;
+    KL(prims::k_scan_excl<long long>, tiles, prims::SC_THREADS, in, out, n, (unsigned long long *)(P->prim + 256), (unsigned *)P->prim, (long long *)total);
+    return 0;
+}
+// IntervalMap order from data order (stage 4): one stable partition by chromosome + local tie fix, or — long runs of equal
+// (chrom, start) — three stable sorts
+static int pipe_chrom_order(fslrc_ctx *ctx, Pipe *P, const int4 *IT0, unsigned *tkey, unsigned *tval, bool tie_ok, int *s_dp) {
+    cudaStream_t st = ctx->stream;
+    const int D = P->D, TB = 256;
+    if (D <= 0) return 0;
+    if (tie_ok) {
+        unsigned *tkey2, *tval2; DA(tkey2, D); DA(tval2, D);
+        int r = sort_pairs(ctx, P, tkey, tkey2, (const int *)tval, (int *)tval2, D, 0, bits_for(P->pr.n_chrom)); if (r) return r;
+        KL(k_apply_delta, nblk(D, TB), TB, D, tval2, s_dp);
+    } else {
+        // (chrom, start, end desc, data order) as three stable sorts from data order: ~end, start, chrom
+        unsigned *ek, *ek2; int *v1, *v2, *iotaD;
+        DA(ek, D); DA(ek2, D); DA(v1, D); DA(v2, D); DA(iotaD, D);
+        KL(k_iota, nblk(D, TB), TB, iotaD, D);
+        KL(k_end_keys, nblk(D, TB), TB, D, IT0, ek);
+        int r = sort_pairs(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
+        KL(k_gather_key, nblk(D, TB), TB, D, v1, IT0, 0, ek);
+        r = sort_pairs(ctx, P, ek, ek2, v1, v2, D, 0, 32); if (r) return r;
+        KL(k_gather_key, nblk(D, TB), TB, D, v2, IT0, 1, ek);
+        r = sort_pairs(ctx, P, ek, ek2, v2, s_dp, D, 0, bits_for(P->pr.n_chrom)); if (r) return r;
+    }
+    return 0;
+}
+
+// ---- stages 1-4, fast form (kernels_ingest.cuh: contiguous reads, no caller `order`).  Returns 1 when the table does not
+// meet the precondition (nothing useful was computed: the caller runs the general path), 0 on success, < 0 on error.
+static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, const unsigned char *d_cmask) {
+    const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
+    cudaStream_t st = ctx->stream;
+    const int A = P->A, R = P->R, TB = 256;
+    int *flagA, *posA, *qlen2;
+    DA(flagA, A); DA(posA, A); DA(qlen2, R); DA(P->q_of_rid, R);
+    if (R > 0) KL(k_fill<int>, nblk(R, TB), TB, P->q_of_rid, R, -1);
+    if (A > 0) {
+        KL(k_rows_fast, nblk(A, TB), TB, A, R, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.qstart, tb.qend, pr.n_chrom, d_clen, d_cmask,
+           pr.mask_subtelomere, (long long)pr.subtel, flagA, qlen2, (unsigned long long *)(P->cnt + 0), P->err);
+        int r = xscan(ctx, P, flagA, posA, A, P->cnt + 1); if (r) return r;
+    }
+    { int r = read_counts(ctx, P); if (r) return r; }
+    if (ctx->h_pin[NCNT] & EF_NONMONO) {                                    // rows of a read apart, or ids going down: general path
+        CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
+        CK(cudaMemsetAsync(P->cnt, 0, NCNT * sizeof(int64_t), st));
+        return 1;
+    }
+    { int r = err_code(ctx); if (r) return r; }
+    P->F = (int)ctx->h_pin[0];
+    const int D = P->D = (int)ctx->h_pin[1];
+    { int r = mark(ctx, ST_KEEP); if (r) return r; }
+    int4 *REC, *IT0; int2 *IT1; unsigned *key, *key2; int *val, *dfill; long long *flag64, *qo64, *QO;
+    DA(REC, 2 * (int64_t)D); DA(key, D); DA(key2, D); DA(val, D); DA(dfill, D); DA(IT0, D); DA(IT1, D);
+    DA(flag64, D); DA(qo64, D); DA(QO, R);
+    unsigned *tkey = nullptr, *tval = nullptr;
+    int kbits = 32;
+    if (D > 0) {
+        if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
+        KL(k_compact_fast, nblk(A, TB), TB, A, flagA, posA, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size, tb.n_alignments,
+           REC, key, val, (unsigned long long *)(P->cnt + 48), P->err);
+        // the genome bounds the sort key: 4 passes of 8 bits cover any int32 start, fewer when the chromosome lengths say so
+        long long mx = 0; bool known = pr.n_chrom > 0;
+        for (int c = 0; c < pr.n_chrom; c++) { if (pr.chrom_len[c] <= 0) known = false; mx = std::max<long long>(mx, pr.chrom_len[c]); }
+        kbits = (known && mx < 0x7fffffffLL) ? std::min(32, bits_for(mx + 2)) : 32;
+        KL(k_fi_fast, nblk(D, TB), TB, D, REC, P->err);
+        int r = sort_pairs(ctx, P, key, key2, val, dfill, D, 0, kbits); if (r) return r;
+        KL(k_items_fast, nblk(D, TB), TB, D, dfill, REC, IT0, IT1, flag64);
+        DA(tkey, D); DA(tval, D);
+        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
+    }
+    { int r = mark(ctx, ST_ORDER); if (r) return r; }
+    // ---- query rank + read-major offsets from one scan over data order
+    DA(P->RI, std::min(R, D));
+    if (D > 0) {
+        int r = xscan64(ctx, P, flag64, qo64, D, P->cnt + 2); if (r) return r;
+        KL(k_firsts_fast, nblk(D, TB), TB, D, flag64, qo64, IT0, IT1, qlen2, pr.qlen_c, pr.naln_c, QO, P->RI, P->err);
+        KL(k_assign_fast, nblk(D, TB), TB, D, REC, QO, P->q_of_rid);
+    }
+    { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
+    if (kbits < 32 && ((unsigned long long)ctx->h_pin[48] >> kbits) != 0) {   // a start beyond its chromosome's length: the short sort key was
+        CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));                      // wrong, the general path sorts on all 32 bits
+        CK(cudaMemsetAsync(P->cnt, 0, NCNT * sizeof(int64_t), st));
+        return 1;
+    }
+    if (D > 0 && (ctx->h_pin[2] & 0xffffffffLL) != D) return fail(ctx, FSLRC_ERR_CUDA, "internal: read-major offsets do not add up");
+    P->Q = (int)(ctx->h_pin[2] >> 32);
+    { int r = mark(ctx, ST_QRANK); if (r) return r; }
+    int *s_u; DA(s_u, D);
+    const bool tie_ok = tkey && ctx->h_pin[41] == 0;
+    if (D > 0 && tie_ok) KL(k_val_to_u, nblk(D, TB), TB, D, dfill, tval);         // the partition carries the filling index u
+    { int r = pipe_chrom_order(ctx, P, IT0, tkey, tval, tie_ok, s_u); if (r) return r; }
+    if (D > 0 && !tie_ok) {                                                        // (three-sort fallback yields data positions)
+        int *tmp; DA(tmp, D);
+        KL(k_gather_int, nblk(D, TB), TB, D, s_u, dfill, tmp);
+        s_u = tmp;
+    }
+    { int r = mark(ctx, ST_CHROM); if (r) return r; }
+    return pipe_bands(ctx, P, s_u, nullptr, nullptr, nullptr, nullptr, REC);
+}
+
 // ---- stages 1-5: ingestion, orders, records (replicated on every rank)
 static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
     cudaStream_t st = ctx->stream;
     const int A = P->A, R = P->R, TB = 256;
-    DA(P->err, 1); DA(P->cnt, 48);
+    DA(P->err, 1); DA(P->cnt, NCNT);
     CK(cudaMemsetAsync(P->err, 0, sizeof(int), st));
-    CK(cudaMemsetAsync(P->cnt, 0, 48 * sizeof(int64_t), st));
+    CK(cudaMemsetAsync(P->cnt, 0, NCNT * sizeof(int64_t), st));
     long long *d_clen; unsigned char *d_cmask;
     DA(d_clen, pr.n_chrom); DA(d_cmask, pr.n_chrom);
     if (pr.n_chrom > 0) {
         CK(cudaMemcpyAsync(d_clen, pr.chrom_len, sizeof(int64_t) * pr.n_chrom, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_cmask, pr.chrom_masked, pr.n_chrom, cudaMemcpyHostToDevice, st));
+    }
+    if (!tb.order && !getenv("FSLRC_GENERAL_INGEST")) {
+        const int r = pipe_ingest_fast(ctx, P, d_clen, d_cmask);
+        if (r <= 0) return r;
     }
     // ---- stage 1: keep_fillings
     int *first, *last, *qmin, *qmax, *flagA, *posA;
@@ -321,38 +436,35 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     { int r = mark(ctx, ST_QRANK); if (r) return r; }
     // ---- stage 4: IntervalMap order: (chrom, start asc, end desc, data order)
     int *s_dp; DA(s_dp, D);
-    const bool tie_ok = tkey && ctx->h_pin[41] == 0;                 // (read back with the stage-3 counters)
-    if (D > 0 && tie_ok) {                                           // one stable partition by chromosome + local tie fix
-        int r = sort_pairs(ctx, P, tkey, tkey2, (const int *)tval, (int *)tval2, D, 0, bits_for(pr.n_chrom)); if (r) return r;
-        KL(k_apply_delta, nblk(D, TB), TB, D, tval2, s_dp);
-    } else if (D > 0) {                                              // long runs of equal (chrom, start): two full radix sorts
-        // (chrom, start, end desc, data order) as three stable sorts from data order: ~end, start, chrom
-        unsigned *ek, *ek2; int *v1, *v2;
-        DA(ek, D); DA(ek2, D); DA(v1, D); DA(v2, D);
-        KL(k_end_keys, nblk(D, TB), TB, D, IT0, ek);
-        int r = sort_pairs(ctx, P, ek, ek2, iotaD, v1, D, 0, 32); if (r) return r;
-        KL(k_gather_key, nblk(D, TB), TB, D, v1, IT0, 0, ek);
-        r = sort_pairs(ctx, P, ek, ek2, v1, v2, D, 0, 32); if (r) return r;
-        KL(k_gather_key, nblk(D, TB), TB, D, v2, IT0, 1, ek);
-        r = sort_pairs(ctx, P, ek, ek2, v2, s_dp, D, 0, bits_for(pr.n_chrom)); if (r) return r;
-    }
+    { int r = pipe_chrom_order(ctx, P, IT0, tkey, tval, tkey && ctx->h_pin[41] == 0, s_dp); if (r) return r; }   // (flag read back with the stage-3 counters)
     { int r = mark(ctx, ST_CHROM); if (r) return r; }
-    // ---- stage 5: records, thresholds, bands
+    return pipe_bands(ctx, P, s_dp, rmidx, it_q, IT0, IT1, nullptr);
+}
+
+// ---- stage 5: records, thresholds, bands; sizes of the pair stage's buffers
+static int pipe_bands(fslrc_ctx *ctx, Pipe *P, const int *s_dp, const int *rmidx, const int *it_q, const int4 *IT0, const int2 *IT1, const int4 *DREC) {
+    const fslrc_params &pr = P->pr;
+    cudaStream_t st = ctx->stream;
+    const int D = P->D, Q = P->Q, TB = 256;
     int *s_end;
     DA(P->SR0, D); DA(P->SR1, D); DA(P->RM, 2 * (int64_t)D); DA(P->s_chrom, D); DA(s_end, D);
     DA(P->pmaxS, D); DA(P->chrom_lo, pr.n_chrom); DA(P->chrom_hi, pr.n_chrom);
     if (pr.n_chrom > 0) { CK(cudaMemsetAsync(P->chrom_lo, 0, sizeof(int) * pr.n_chrom, st)); CK(cudaMemsetAsync(P->chrom_hi, 0, sizeof(int) * pr.n_chrom, st)); }
+    DA(P->rclass, Q);
     if (D > 0) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
         int *s_m; DA(s_m, D);
-        KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
+        if (DREC) {                                                                // fast ingest: s_dp holds filling indices, DREC the packed records
+            KL(k_records_fast, nblk(D, TB), TB, D, s_dp, DREC, P->RI, pr.overlap, P->SR0, P->SR1, s_m, P->s_chrom, s_end);
+            KL(k_chrom_bounds, nblk(D, TB), TB, D, P->s_chrom, P->chrom_lo, P->chrom_hi);
+        }
+        else KL(k_records, nblk(D, TB), TB, D, s_dp, rmidx, it_q, IT0, IT1, P->RI, pr.overlap, P->SR0, P->SR1,
                                                s_m, P->s_chrom, s_end, P->chrom_lo, P->chrom_hi, P->err);
         int r = segmax_scan(ctx, P, P->s_chrom, s_end, P->pmaxS, D); if (r) return r;
-        DA(P->rclass, Q);
         CK(cudaMemsetAsync(P->rclass, 0, sizeof(int) * (size_t)std::max(Q, 1), st));
         KL(k_bands, nblk(D, 256), 256, D, P->SR0, s_m, P->s_chrom, P->pmaxS, P->chrom_lo, P->chrom_hi, P->RM, P->rclass,
            (unsigned long long *)(P->cnt + 3), (unsigned long long *)(P->cnt + 14), (unsigned long long *)(P->cnt + 44));
-    } else DA(P->rclass, Q);
+    }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
     long long T = pr.edge_threshold;
     P->Tedge = T > 0x7fffffffLL ? 0x7fffffff : (T < -0x7fffffffLL ? -0x7fffffff : (int)T);
@@ -423,10 +535,10 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     int *posQ;
     DA(posQ, Q);
     if (Q > 0 && P->pr.overlap > 0.0) {                                   // partner records of the light saturating reads
-        if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * 8), PLT_THREADS, P->tab, pairs, (const unsigned long long *)nullptr,
-                                       n_pairs, n_pairs, P->isP, P->plinfo, P->cp, P->PL, P->err); }
-        else KL(k_plist, n_sms(ctx) * 8, PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull, P->cap_entries,
-                P->isP, P->plinfo, P->cp, P->PL, P->err);
+        if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * 8), PLT_THREADS, P->tab, pairs,
+                                       (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->cp, P->PL, P->err); }
+        else KL(k_plist, n_sms(ctx) * 8, PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
+                P->cap_entries, P->plinfo, P->cp, P->PL, P->err);
     }
     if (Q > 0) {
         int r = xscan(ctx, P, P->isP, posQ, Q, P->cnt + 6); if (r) return r;
@@ -532,11 +644,66 @@ static int check_args(fslrc_ctx *ctx, const fslrc_table *tb, const fslrc_params 
     if (!ctx) return FSLRC_ERR_ARG;
     if (!tb || !pr || !oc || !on) return fail(ctx, FSLRC_ERR_ARG, "null argument");
     if (tb->n_rows < 0 || tb->n_reads < 0 || tb->n_rows > 0x7ffffff0LL || tb->n_reads > 0x7ffffff0LL) return fail(ctx, FSLRC_ERR_ARG, "table size out of range");
-    if (tb->n_rows > 0 && ((!tb->read_id && !tb->rows_per_read_u8) || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || !tb->rend || (!tb->aln_size && !oc_host_path_ok(tb)) || !tb->qstart || !tb->qend ||
+    if (tb->n_rows > 0 && ((!tb->read_id && !tb->rows_per_read_u8) || (!tb->chrom && !tb->chrom_u8) || !tb->rstart || (!tb->rend && !tb->rspan_i16) ||
+                           (!tb->aln_size && !oc_host_path_ok(tb)) || (!tb->qstart && !tb->qstart_u16) || (!tb->qend && !tb->qend_u16) ||
                            (!tb->n_alignments && !tb->n_alignments_u16)))
         return fail(ctx, FSLRC_ERR_ARG, "null column");
     if (pr->n_chrom < 0 || pr->n_chrom > (1 << 20) || (pr->n_chrom > 0 && (!pr->chrom_len || !pr->chrom_masked))) return fail(ctx, FSLRC_ERR_ARG, "bad chromosome tables");
     if (pr->overlap != pr->overlap || pr->qlen_c != pr->qlen_c || pr->naln_c != pr->naln_c) return fail(ctx, FSLRC_ERR_ARG, "NaN option");
+    return 0;
+}
+
+// The int32 device columns the kernels read, from whatever the caller gave: wide or narrow columns, in host memory (copied
+// in) or already on the device (used in place; only narrow / derived ones cost a kernel).  `out` receives device pointers.
+static int resolve_columns(fslrc_ctx *ctx, Pipe *P, const fslrc_table *in, bool host, fslrc_table *out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t A = in->n_rows, R = in->n_reads;
+    *out = *in;
+    out->chrom_u8 = nullptr; out->n_alignments_u16 = nullptr; out->rows_per_read_u8 = nullptr; out->rspan_i16 = nullptr;
+    out->qstart_u16 = nullptr; out->qend_u16 = nullptr;
+    auto bring = [&](const void *src, size_t bytes, const void **dst) -> int {          // a column as the device sees it
+        if (!host || !src || bytes == 0) { *dst = src; return 0; }
+        unsigned char *d; DA(d, bytes);
+        CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+        *dst = d;
+        return 0;
+    };
+#define BRING(src, bytes, dst) do { const void *q__; int r__ = bring((src), (bytes), &q__); if (r__) return r__; (dst) = (decltype(dst))q__; } while (0)
+    const size_t a4 = sizeof(int32_t) * (size_t)A;
+    // read ids: the column, or run lengths (the rows of read r are contiguous and the reads come in id order: verified by the caller)
+    if (in->read_id || A == 0) BRING(in->read_id, a4, out->read_id);
+    else {
+        const unsigned char *d_r8; int *cnt32, *first, *rid;
+        BRING(in->rows_per_read_u8, (size_t)R, d_r8);
+        DA(cnt32, R); DA(first, R); DA(rid, A);
+        KL(k_widen_u8, nblk(R, 256), 256, R, d_r8, cnt32);
+        int r = xscan(ctx, P, cnt32, first, (int)R); if (r) return r;
+        KL(k_rid_from_runs, nblk(R, 256), 256, (int)R, (int)A, first, cnt32, rid);
+        out->read_id = rid;
+    }
+    Widen w; memset(&w, 0, sizeof(w));
+    bool any = false;
+    BRING(in->rstart, a4, out->rstart);
+    w.rstart = out->rstart;
+    if (in->chrom || A == 0) BRING(in->chrom, a4, out->chrom);
+    else { BRING(in->chrom_u8, (size_t)A, w.c8); DA(w.chrom, A); out->chrom = w.chrom; any = true; }
+    if (in->rend || A == 0) BRING(in->rend, a4, out->rend);
+    else { BRING(in->rspan_i16, 2 * (size_t)A, w.span16); DA(w.rend, A); out->rend = w.rend; any = true; }
+    if (in->qstart || A == 0) BRING(in->qstart, a4, out->qstart);
+    else { BRING(in->qstart_u16, 2 * (size_t)A, w.qs16); DA(w.qstart, A); out->qstart = w.qstart; any = true; }
+    if (in->qend || A == 0) BRING(in->qend, a4, out->qend);
+    else { BRING(in->qend_u16, 2 * (size_t)A, w.qe16); DA(w.qend, A); out->qend = w.qend; any = true; }
+    if (in->n_alignments || A == 0) BRING(in->n_alignments, a4, out->n_alignments);
+    else { BRING(in->n_alignments_u16, 2 * (size_t)A, w.n16); DA(w.naln, A); out->n_alignments = w.naln; any = true; }
+    if (in->aln_size || A == 0) BRING(in->aln_size, a4, out->aln_size);
+    else {                                                                         // aln_size = qend - qstart (check_args saw the flag)
+        DA(w.aln, A); out->aln_size = w.aln; any = true;
+        if (!w.qstart) w.qstart = (int *)out->qstart;                              // (read only in that case)
+        if (!w.qend) w.qend = (int *)out->qend;
+    }
+    if (any && A > 0) KL(k_widen, nblk(A, 256), 256, A, w);
+    if (in->order) BRING(in->order, sizeof(int32_t) * (size_t)in->n_order, out->order);
+#undef BRING
     return 0;
 }
 
@@ -597,9 +764,11 @@ int fslrc_cluster_device(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_p
     CK(cudaSetDevice(ctx->device));
     ctx->stream = (cudaStream_t)stream;
     Pipe P; memset(&P, 0, sizeof(P));
-    P.tb = *table; P.pr = *params; P.A = (int)table->n_rows; P.R = (int)table->n_reads;
+    P.pr = *params; P.A = (int)table->n_rows; P.R = (int)table->n_reads;
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
-    r = run_device(ctx, &P, out_cluster, out_n_reads, stats);
+    r = resolve_columns(ctx, &P, table, false, &P.tb);
+    if (!r) CK(cudaEventRecord(ctx->ev[1], ctx->stream));                  // closes stage 0 (widening of narrow columns, if any)
+    if (!r) r = run_device(ctx, &P, out_cluster, out_n_reads, stats);
     if (!r) { r = mark(ctx, ST_D2H); }
     if (!r) { r = read_counts(ctx, &P); if (!r) r = err_code(ctx); }
     if (!r) fill_stats(ctx, &P, stats);
@@ -616,42 +785,9 @@ int fslrc_cluster_host(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_par
     cudaStream_t st = ctx->stream;
     const int64_t A = table->n_rows, R = table->n_reads;
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], st);
-    fslrc_table d = *table;
+    fslrc_table d;
     Pipe P; memset((void *)&P, 0, sizeof(P));
-    int32_t *cols[8]; const int32_t *src[8] = {table->read_id, table->chrom, table->rstart, table->rend, table->aln_size,
-                                               table->qstart, table->qend, table->n_alignments};
-    unsigned char *d_c8 = nullptr; unsigned short *d_n16 = nullptr;
-    if (table->rows_per_read_u8 && A > 0) {
-        // read ids from run lengths: the rows of read r are contiguous and the reads come in id order (verified by the caller)
-        unsigned char *d_r8; int *cnt32, *first;
-        DA(cols[0], A); DA(d_r8, R); DA(cnt32, R); DA(first, R);
-        CK(cudaMemcpyAsync(d_r8, table->rows_per_read_u8, (size_t)R, cudaMemcpyHostToDevice, st));
-        KL(k_widen, nblk(R, 256), 256, R, d_r8, (const unsigned short *)nullptr, cnt32, (int *)nullptr, (int *)nullptr, (const int *)nullptr, (const int *)nullptr);
-        r = xscan(ctx, &P, cnt32, first, (int)R); if (r) return r;
-        KL(k_rid_from_runs, nblk(R, 256), 256, (int)R, (int)A, first, cnt32, cols[0]);
-    }
-    for (int c = 0; c < 8; c++) {
-        if (!(c == 0 && table->rows_per_read_u8 && A > 0)) DA(cols[c], A);
-        if (c == 1 && table->chrom_u8) {
-            DA(d_c8, A);
-            if (A > 0) CK(cudaMemcpyAsync(d_c8, table->chrom_u8, (size_t)A, cudaMemcpyHostToDevice, st));
-        } else if (c == 7 && table->n_alignments_u16) {
-            DA(d_n16, A);
-            if (A > 0) CK(cudaMemcpyAsync(d_n16, table->n_alignments_u16, sizeof(unsigned short) * A, cudaMemcpyHostToDevice, st));
-        } else if ((c == 4 && !table->aln_size) || (c == 0 && table->rows_per_read_u8)) {
-            // derived on the device below
-        } else if (A > 0) CK(cudaMemcpyAsync(cols[c], src[c], sizeof(int32_t) * A, cudaMemcpyHostToDevice, st));
-    }
-    if (A > 0 && (d_c8 || d_n16 || !table->aln_size))
-        KL(k_widen, nblk(A, 256), 256, A, d_c8, d_n16, cols[1], cols[7], table->aln_size ? (int *)nullptr : cols[4], cols[5], cols[6]);
-    d.read_id = cols[0]; d.chrom = cols[1]; d.rstart = cols[2]; d.rend = cols[3]; d.aln_size = cols[4]; d.qstart = cols[5];
-    d.qend = cols[6]; d.n_alignments = cols[7];
-    int32_t *d_order = nullptr;
-    if (table->order) {
-        DA(d_order, table->n_order);
-        if (table->n_order > 0) CK(cudaMemcpyAsync(d_order, table->order, sizeof(int32_t) * table->n_order, cudaMemcpyHostToDevice, st));
-        d.order = d_order;
-    }
+    r = resolve_columns(ctx, &P, table, true, &d); if (r) { free_all(ctx); ctx_sync(ctx); return r; }
     int32_t *d_oc, *d_on;
     DA(d_oc, R); DA(d_on, R);
     CK(cudaEventRecord(ctx->ev[1], st));                                   // closes stage 0 (h2d)
@@ -678,9 +814,11 @@ int fslrc_mg_prepare(fslrc_ctx *ctx, const fslrc_table *table, const fslrc_param
     free_all(ctx);
     delete ctx->pipe;
     Pipe *P = ctx->pipe = new Pipe(); memset(P, 0, sizeof(*P));
-    P->tb = *table; P->pr = *params; P->A = (int)table->n_rows; P->R = (int)table->n_reads;
+    P->pr = *params; P->A = (int)table->n_rows; P->R = (int)table->n_reads;
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventRecord(ctx->ev[i], ctx->stream);
-    r = pipe_prepare(ctx, P);
+    r = resolve_columns(ctx, P, table, false, &P->tb);
+    if (!r) CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!r) r = pipe_prepare(ctx, P);
     if (r) { free_all(ctx); cudaStreamSynchronize(ctx->stream); }
     return r;
 }
@@ -703,7 +841,7 @@ int fslrc_mg_partners(fslrc_ctx *ctx, int rank, int world, int32_t **pairs, int6
     r = err_code(ctx); if (r) return r;
     const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
     int2 *pent; DA(pent, nent);
-    if (nent > 0) KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->entries, nent, P->isP, P->plinfo, pent, (unsigned long long *)(P->cnt + 47));
+    if (nent > 0) KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->entries, nent, P->plinfo, pent, (unsigned long long *)(P->cnt + 47));
     r = read_counts(ctx, P); if (r) return r;
     *pairs = (int32_t *)pent; *n_pairs = ctx->h_pin[47];
     return 0;

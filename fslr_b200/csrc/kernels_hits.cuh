@@ -7,8 +7,8 @@
 //   k_eval   pair test proper, ONE LANE PER HIT, every lane of a warp busy: different_lengths_or_alignments
 //            (cluster.py:178-183), the match matrix, the greedy N-1 intersection (cluster.py:152-161) and the per-N
 //            Jaccard cutoff (cluster.py:165-170,218-219).  A read pair (a, b) is evaluated exactly once in direction a -> b:
-//            at its CANONICAL hit = the first one in k_hits' scan order (lowest fa, then lowest position), which the lane
-//            verifies from the match matrix and the positions of b's fillings.  The result overwrites the hit in place
+//            at its CANONICAL hit = the lexicographically first matching filling pair (fa, fb), which the lane verifies
+//            from the match matrix.  The result overwrites the hit in place
 //            (no compaction pass, no atomics on the list): {a, b | flags}, or {-1, -1};
 //   k_plist  after the saturating set is known: one lane per recorded pair of a saturating read writes the partner record
 //            the replay's LIST mode consumes (keys, cg; same content as k_pair's records).
@@ -26,7 +26,8 @@ __device__ __forceinline__ bool read_is_heavy(int La, const int *__restrict__ rc
 __global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
                                                         unsigned long long *n_slots, unsigned long long cap, int *heavy_list,
                                                         unsigned *n_heavy, int *err) {
-    __shared__ int2 sHash[HK_GROUPS][HK_HASH];
+    __shared__ int2 sHash[HK_GROUPS][HK_HASH];                                     // {b, q}: partner b was hit during read q's scan ...
+    __shared__ int sHkey[HK_GROUPS][HK_HASH];                                      // ... at filling pair fa << 6 | fb (the lowest listed so far)
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, grp = w * 4 + (lane >> 3);
     const unsigned ltmask = (1u << lane) - 1u;
@@ -65,10 +66,10 @@ __global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int ns
                 const int b = c0.w & QMASK;
                 bool hit = v && b != q && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z);   // cluster.py:157, T >= 1
                 if (hit) {                                                          // a filter only: k_eval's canonical rule is exact
-                    int2 *hs = &sHash[grp][b & (HK_HASH - 1)];
-                    const int2 h = *hs;
-                    if (h.x == b && h.y == q) hit = false;                          // an earlier hit of (q, b) is on the list already
-                    else *hs = make_int2(b, q);
+                    const int slot = b & (HK_HASH - 1), key = (fi << 6) | (int)((unsigned)c0.w >> 26);
+                    const int2 h = sHash[grp][slot];
+                    if (h.x == b && h.y == q && sHkey[grp][slot] < key) hit = false;   // a hit of (q, b) at a lower filling pair is listed
+                    else { sHash[grp][slot] = make_int2(b, q); sHkey[grp][slot] = key; }
                 }
                 const unsigned hm = __ballot_sync(FULL, hit);
                 if (hm) {
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int ns
 
 // One lane per hit.  La <= 4 always (light reads); partners with more than 4 fillings take the loop over global lists.
 #define EV_THREADS 256
-__global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
+__global__ void __launch_bounds__(EV_THREADS, 4) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
                                                      unsigned long long cap, unsigned *cp, unsigned long long *n_tests,
                                                      unsigned long long *n_real) {
     __shared__ int s_umax[LMAX + 1];
@@ -108,12 +109,12 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, in
         const unsigned long long i = i0 + (threadIdx.x & 31);
         int2 h = make_int2(-1, -1);
         if (i < n) h = hits[i];
-        int q = 0, fa = 0, p = 0, b = 0, La = 0, Lb = 0, offa = 0, offb = 0;
+        int q = 0, fa = 0, fb = 0, p = 0, b = 0, La = 0, Lb = 0, offa = 0, offb = 0;
         bool small = false, gen = false;
         if (h.x >= 0) {
             q = h.x & QMASK; fa = (int)((unsigned)h.x >> 26); p = h.y;
             const int4 c0 = __ldg(&t.SR0[p]), c1 = __ldg(&t.SR1[p]), ria = __ldg(&t.RI[q]);
-            b = c0.w & QMASK;
+            b = c0.w & QMASK; fb = (int)((unsigned)c0.w >> 26);
             if (difflen_ok(ria.x, ria.y, ria.z, c1.x, c1.y, c1.z)) {               // cluster.py:178-183
                 offa = (int)((unsigned)ria.w >> 6); La = (ria.w & 63) + 1;
                 offb = (int)((unsigned)c1.w >> 6); Lb = (c1.w & 63) + 1;
@@ -124,12 +125,11 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, in
         // ---- lists of up to 4 fillings in registers; rows / columns nobody in the warp has are skipped warp-uniformly
         const int mLa = __reduce_max_sync(FULL, small ? La : 0), mLb = __reduce_max_sync(FULL, small ? Lb : 0);
         int4 A[4], B[4];
-        int pb[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            A[k] = make_int4(-1, 0, 0, 0x7fffffff); B[k] = make_int4(-2, 0, 0, 0x7fffffff); pb[k] = 0x7fffffff;
+            A[k] = make_int4(-1, 0, 0, 0x7fffffff); B[k] = make_int4(-2, 0, 0, 0x7fffffff);
             if (k < mLa) { if (small && k < La) A[k] = rm0(t, offa + k); }
-            if (k < mLb) { if (small && k < Lb) { B[k] = rm0(t, offb + k); pb[k] = rm1(t, offb + k).x; } }
+            if (k < mLb) { if (small && k < Lb) B[k] = rm0(t, offb + k); }
         }
         unsigned m[4];
 #pragma unroll
@@ -148,14 +148,12 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, in
             unsigned used = 0, row = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                if (k < fa && m[k]) canon = false;                                  // an earlier filling of a matches b: not the first hit
+                if (k < fa && m[k]) canon = false;                                  // an earlier filling of a matches b
                 if (k == fa) row = m[k];
                 const unsigned avail = m[k] & ~used;                                // greedy first fit (cluster.py:152-161)
                 if (avail) { used |= avail & (0u - avail); nmatch++; }
             }
-#pragma unroll
-            for (int g = 0; g < 4; g++)
-                if (((row >> g) & 1u) && pb[g] < p) canon = false;                  // b has a matching filling at a lower position
+            if (row & ((1u << fb) - 1u)) canon = false;                             // ... or this filling matches an earlier filling of b
         }
         if (gen) {                                                                  // b has more than 4 fillings (rare): global lists
             unsigned long long used = 0;
@@ -166,7 +164,7 @@ __global__ void __launch_bounds__(EV_THREADS) k_eval(Tab t, const UmaxTab um, in
                 for (int g = 0; g < Lb; g++) {
                     const int4 bq = rm0(t, offb + g);
                     if (matchT<false>(a, bq)) {
-                        if (k < fa || (k == fa && rm1(t, offb + g).x < p)) canon = false;
+                        if (k < fa || (k == fa && g < fb)) canon = false;
                         if (!taken && !((used >> g) & 1ull)) { used |= 1ull << g; nmatch++; taken = true; }
                     }
                 }
@@ -220,17 +218,16 @@ __global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__re
 // One lane per recorded pair: the partner record of saturating read a about partner b (see PLInfo / k_pair for the fields)
 #define PLT_THREADS 256
 __global__ void __launch_bounds__(PLT_THREADS) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
-                                                       unsigned long long n_fixed, unsigned long long cap, const int *__restrict__ isP,
+                                                       unsigned long long n_fixed, unsigned long long cap,
                                                        const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
     unsigned long long n = n_slots ? *n_slots : n_fixed;
     if (n > cap) n = cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * PLT_THREADS;
     for (unsigned long long i = (unsigned long long)blockIdx.x * PLT_THREADS + threadIdx.x; i < n; i += stride) {
-        const int2 e = ent[i];
+        const int2 e = __ldg(&ent[i]);
         const int a = e.x;
         if (a < 0 || ((unsigned)e.y & EB_HEAVY)) continue;
-        if (!__ldg(&isP[a])) continue;
-        const PLInfo pi = plinfo[a];
+        const PLInfo pi = plinfo[a];                                                // n > 0: saturating, and the replay takes its list
         if (pi.n <= 0) continue;
         const int b = e.y & QMASK;
         const int wa = __ldg(&t.RI[a]).w, wb = __ldg(&t.RI[b]).w;
@@ -264,14 +261,14 @@ __global__ void __launch_bounds__(PLT_THREADS) k_plist(Tab t, const int2 *__rest
     }
 }
 // multi-GPU: this rank's recorded pairs of light saturating reads with partner lists, compacted for the all-gather
-__global__ void k_pent_compact(const int2 *__restrict__ ent, unsigned long long n, const int *__restrict__ isP,
-                               const PLInfo *__restrict__ plinfo, int2 *out, unsigned long long *n_out) {
+__global__ void k_pent_compact(const int2 *__restrict__ ent, unsigned long long n, const PLInfo *__restrict__ plinfo, int2 *out,
+                               unsigned long long *n_out) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     bool keep = false;
     int2 e = make_int2(-1, -1);
     if (i < n) {
         e = ent[i];
-        keep = e.x >= 0 && !((unsigned)e.y & EB_HEAVY) && isP[e.x] && plinfo[e.x].n > 0;
+        keep = e.x >= 0 && !((unsigned)e.y & EB_HEAVY) && plinfo[e.x].n > 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, keep);
     unsigned long long at = 0;

@@ -9,13 +9,25 @@ __global__ void k_fill(T *p, int64_t n, T v) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void k_widen(int64_t n, const unsigned char *__restrict__ c8, const unsigned short *__restrict__ n16, int *chrom, int *naln,
-                        int *aln, const int *__restrict__ qstart, const int *__restrict__ qend) {
+// narrow wire columns -> the int32 columns the kernels read (any source pointer may be NULL: that column is wide already)
+struct Widen {
+    const unsigned char *c8; const unsigned short *n16, *qs16, *qe16; const short *span16;
+    int *chrom, *naln, *qstart, *qend, *rend, *aln;      // destinations (NULL = nothing to do); aln = qend - qstart
+    const int *rstart;
+};
+__global__ void k_widen(int64_t n, Widen w) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (c8) chrom[i] = c8[i];
-    if (n16) naln[i] = n16[i];
-    if (aln) aln[i] = qend[i] - qstart[i];                             // aln_size = qend - qstart (collect_mapping_info.py:88)
+    if (w.c8) w.chrom[i] = w.c8[i];
+    if (w.n16) w.naln[i] = w.n16[i];
+    if (w.qs16) w.qstart[i] = w.qs16[i];
+    if (w.qe16) w.qend[i] = w.qe16[i];
+    if (w.span16) w.rend[i] = w.rstart[i] + (int)w.span16[i];
+    if (w.aln) w.aln[i] = w.qend[i] - w.qstart[i];                     // aln_size = qend - qstart (collect_mapping_info.py:88)
+}
+__global__ void k_widen_u8(int64_t n, const unsigned char *__restrict__ in, int *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
 }
 // read ids from run lengths (host calls with rows_per_read): read r owns the rows [first[r], first[r] + cnt[r])
 __global__ void k_rid_from_runs(int R, int A, const int *__restrict__ first, const int *__restrict__ cnt, int *rid) {
@@ -297,4 +309,172 @@ __global__ void k_bands(int D, const int4 *__restrict__ SR0, const int *__restri
         if (b) atomicAdd(tight_pairs, (unsigned long long)b);
         if (c) atomicAdd(light_pairs, (unsigned long long)c);
     }
+}
+
+// ================================================================ fast ingest (stages 1-3 when the rows of every read are
+// contiguous and the read ids never decrease along the table — what collect_mapping_info.py:174 writes and what
+// pandas.factorize(qname) numbers — and the caller gives no `order`).  Same results as the general kernels above with
+//   * no per-read atomics: a read's first / last row are the rows whose neighbour belongs to another read (cluster.py:14-24),
+//     its qlen2 (cluster.py:26-29) is folded by the thread of its first row;
+//   * no sort by query rank: a read's fillings are contiguous in bed order, so after the one sort by start every filling finds
+//     its read's first item in data order (= the dict order of cluster.py:189-191) among its neighbours, and ONE 64-bit scan
+//     over data order of (1, L) at those first items yields both the query rank and the read-major offset.
+// A table that violates the precondition raises EF_NONMONO and the general path runs instead.
+#define EF_NONMONO 0x40000000
+__global__ void k_rows_fast(int A, int R, const int *__restrict__ rid_, const int *__restrict__ chrom, const int *__restrict__ rstart,
+                            const int *__restrict__ rend, const int *__restrict__ qstart, const int *__restrict__ qend, int n_chrom,
+                            const long long *__restrict__ clen, const unsigned char *__restrict__ cmasked, int sub_on, long long subtel,
+                            int *flag, int *qlen2, unsigned long long *n_fillings, int *err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int kept = 0;
+    if (i < A) {
+        const int rid = rid_[i];
+        const int prev = i > 0 ? rid_[i - 1] : -1, next = i + 1 < A ? rid_[i + 1] : -1;
+        int f = 0;
+        if ((unsigned)rid >= (unsigned)R) atomicOr(err, EF_RANGE);
+        else {
+            if (rid < prev) atomicOr(err, EF_NONMONO);
+            const bool first = rid != prev, last = rid != next;
+            if (!first && !last) {                                                  // a filling (cluster.py:14-24)
+                kept = 1;
+                const int c = chrom[i], rs = rstart[i], re = rend[i];
+                if ((unsigned)c >= (unsigned)n_chrom || min(rs, re) < 0) atomicOr(err, EF_RANGE);
+                else f = is_masked(make_int4(rid, c, min(rs, re), max(rs, re)), n_chrom, clen, cmasked, sub_on, subtel) ? 0 : 1;
+            }
+            if (first) {                                                            // qlen2 over the read's kept rows (cluster.py:26-29)
+                int qmn = 0x7fffffff, qmx = (int)0x80000000;
+                for (int j = i + 1; j + 1 < A && rid_[j + 1] == rid; j++) { qmn = min(qmn, qstart[j]); qmx = max(qmx, qend[j]); }
+                long long ql = qmx >= qmn ? (long long)qmx - (long long)qmn : 0;
+                if (ql > 0x7fffffffLL) { atomicOr(err, EF_RANGE); ql = 1; }
+                qlen2[rid] = (int)ql;
+            }
+        }
+        flag[i] = f;
+    }
+    const int cnt = __syncthreads_count(kept);
+    if (threadIdx.x == 0 && cnt) atomicAdd(n_fillings, (unsigned long long)cnt);
+}
+// unmasked fillings in bed order, one 32-byte sector each: REC[2u] = {read_id, chrom, start, end},
+// REC[2u+1] = {aln_size, n_alignments, q | fi << 26, m} (.z/.w filled in by k_assign_fast); sort key = start
+__global__ void k_compact_fast(int A, const int *__restrict__ flag, const int *__restrict__ pos, const int *__restrict__ rid,
+                               const int *__restrict__ chrom, const int *__restrict__ rstart, const int *__restrict__ rend,
+                               const int *__restrict__ aln, const int *__restrict__ naln, int4 *REC, unsigned *key, int *val,
+                               unsigned long long *max_start, int *err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = 0;
+    if (i < A && flag[i]) {
+        const int u = pos[i];
+        const int rs = rstart[i], re = rend[i], a = aln[i], na = naln[i];
+        s = min(rs, re);
+        if (a <= 0 || na <= 0) atomicOr(err, EF_ZERO);
+        if (na >= 65535) atomicOr(err, EF_RANGE);
+        REC[2 * u] = make_int4(rid[i], chrom[i], s, max(rs, re));
+        REC[2 * u + 1] = make_int4(a, na, 0, 0);
+        key[u] = (unsigned)s; val[u] = u;
+    }
+    __shared__ int s_max;                                                           // one atomic per block, and only when it can matter
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    s = __reduce_max_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&s_max, s);
+    __syncthreads();
+    if (threadIdx.x == 0 && (unsigned long long)s_max > *(volatile unsigned long long *)max_start) atomicMax(max_start, (unsigned long long)s_max);
+}
+// Data order = the stable sort of the fillings by start, so two fillings of a read compare in data order like (start, u):
+// the index fi of a filling among its read's fillings in data order, and the read's filling count L, are known BEFORE the sort
+// from the neighbouring records in bed order (coalesced).  Kept in REC[2u+1].zw = {fi, L} until k_assign_fast overwrites them.
+__global__ void k_fi_fast(int D, int4 *REC, int *err) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= D) return;
+    const int4 r0 = REC[2 * u];
+    int fi = 0, L = 1;
+    bool over = false;
+    for (int k = u - 1; k >= 0; k--) {
+        const int4 o = REC[2 * k];
+        if (o.x != r0.x) break;
+        if (++L > LMAX) { over = true; break; }
+        fi += o.z <= r0.z;                                                          // (start', u') < (start, u) with u' < u
+        if (k == u - 1 && REC[2 * k + 1].y != REC[2 * u + 1].y) atomicOr(err, EF_NALN);   // n_alignments constant over a read's rows
+    }
+    for (int k = u + 1; !over && k < D; k++) {
+        const int4 o = REC[2 * k];
+        if (o.x != r0.x) break;
+        if (++L > LMAX) { over = true; break; }
+        fi += o.z < r0.z;                                                           // u' > u
+    }
+    if (over) { atomicOr(err, EF_TOOMANY); L = LMAX; fi &= 63; }
+    int2 *zw = (int2 *)&REC[2 * u + 1] + 1;
+    *zw = make_int2(fi, L);
+}
+// per data position d (filling u = dfill[d]): the filling's record, gathered as one sector, written out coalesced;
+// flag64[d] = (1 << 32 | L) when the filling is its read's first item in data order (fi == 0), else 0
+__global__ void k_items_fast(int D, const int *__restrict__ dfill, const int4 *__restrict__ REC, int4 *IT0, int2 *IT1, long long *flag64) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int u = dfill[d];
+    const int4 r0 = REC[2 * u], r1 = REC[2 * u + 1];
+    IT0[d] = r0;
+    IT1[d] = make_int2(r1.x, r1.y);
+    flag64[d] = r1.z == 0 ? ((1ll << 32) | (long long)r1.w) : 0ll;
+}
+// the read's first item in data order knows the read's query rank q and read-major offset `off` (the scan at its position):
+// QO[read_id] = (q << 32 | off) — the only scattered write of the fast ingest, one per query read — and RI[q] (k_read_info;
+// consecutive first items write consecutive q)
+__global__ void k_firsts_fast(int D, const long long *__restrict__ flag64, const long long *__restrict__ qo64, const int4 *__restrict__ IT0,
+                              const int2 *__restrict__ IT1, const int *__restrict__ qlen2, double qlen_c, double naln_c, long long *QO,
+                              int4 *RI, int *err) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const long long fl = flag64[d];
+    if (!fl) return;
+    const long long qo = qo64[d];
+    const int q = (int)(qo >> 32), off = (int)(qo & 0xffffffffll), L = (int)(fl & 0xffffffffll), rid = IT0[d].x;
+    QO[rid] = qo;
+    int ql = qlen2[rid], na = IT1[d].y;
+    if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
+    int Ln = thr_f64(na, naln_c);
+    if (Ln > 65535) Ln = 65535;
+    RI[q] = make_int4(ql, thr_f64(ql, qlen_c), (na & 0xffff) | (Ln << 16), (int)(((unsigned)off << 6) | (unsigned)((L - 1) & 63)));
+}
+// per filling in bed order (coalesced: the reads are contiguous and QO is indexed by the non-decreasing read id): its query
+// rank, its index fi in the read's list and its read-major index m = off + fi into REC[2u+1].zw; q_of_rid
+__global__ void k_assign_fast(int D, int4 *REC, const long long *__restrict__ QO, int *q_of_rid) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= D) return;
+    const int rid = REC[2 * u].x;
+    int4 r1 = REC[2 * u + 1];
+    const int fi = r1.z;
+    const long long qo = QO[rid];
+    const int q = (int)(qo >> 32), off = (int)(qo & 0xffffffffll);
+    r1.z = (int)((unsigned)q | ((unsigned)(fi & 63) << 26)); r1.w = off + fi;
+    REC[2 * u + 1] = r1;
+    if (u == 0 || REC[2 * (u - 1)].x != rid) q_of_rid[rid] = q;
+}
+// k_tie_delta's value is the data position; the fast path sends the filling index u through the partition instead
+__global__ void k_val_to_u(int D, const int *__restrict__ dfill, unsigned *val) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < D) { const unsigned v = val[d]; val[d] = (v & ~0x3ffffffu) | (unsigned)dfill[v & 0x3ffffffu]; }
+}
+// sorted order: one sector gather per position
+__global__ void k_records_fast(int D, const int *__restrict__ s_u, const int4 *__restrict__ REC, const int4 *__restrict__ RI, double overlap,
+                               int4 *SR0, int4 *SR1, int *s_m, int *s_chrom, int *s_end) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int u = s_u[p];
+    const int4 r0 = REC[2 * u], r1 = REC[2 * u + 1];
+    SR0[p] = make_int4(r0.z, r0.w, thr_f64(max(r1.x, 1), overlap), r1.z);
+    SR1[p] = RI[r1.z & QMASK];
+    s_m[p] = r1.w;
+    s_chrom[p] = r0.y; s_end[p] = r0.w;
+}
+__global__ void k_gather_int(int n, const int *__restrict__ idx, const int *__restrict__ src, int *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void k_chrom_bounds(int D, const int *__restrict__ s_chrom, int *chrom_lo, int *chrom_hi) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= D) return;
+    const int c = s_chrom[p];
+    if (p == 0 || s_chrom[p - 1] != c) chrom_lo[c] = p;
+    if (p == D - 1 || s_chrom[p + 1] != c) chrom_hi[c] = p + 1;
 }

@@ -123,7 +123,9 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 #define PK_CHUNK 256            // relation-entry slots a warp reserves at a time (>= 32)
 #define RP_K 64                 // partners a saturating read may have for the replay's LIST mode
 #define PL_CHUNK 512            // partner records a warp reserves at a time (>= 4 * RP_K)
-#define RP_KL 4                  // partners per lane of a replay group handled in one batch (32 partners per batch)
+#ifndef RP_KL
+#define RP_KL 4                  // partners per lane of a replay group handled in one batch (8 * RP_KL partners per batch)
+#endif
 
 // Partner record of a saturating read a (replay LIST mode): everything the replay needs to know about partner b without
 // touching b's geometry again.  r0 = {b | edge << 31, off_b << 6 | L_b - 1, cg, 0}, r1 = {key[0..3]}:

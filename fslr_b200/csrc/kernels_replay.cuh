@@ -137,14 +137,17 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *umax, c
 //     scan of that very interval already passed a's filling are skipped on two coalesced loads, 64 positions per step.
 static_assert(RP_K <= RP_CHUNK && 4 * RP_K <= PL_CHUNK, "chunk sizes");
 // group-wide max over the 8 lanes of a group
-__device__ __forceinline__ int gmax8(unsigned gmask, int v) {
-    v = max(v, __shfl_xor_sync(gmask, v, 1)); v = max(v, __shfl_xor_sync(gmask, v, 2)); v = max(v, __shfl_xor_sync(gmask, v, 4));
-    return v;
-}
+__device__ __forceinline__ int gmax8(unsigned gmask, int v) { return __reduce_max_sync(gmask, v); }   // one REDUX instead of 3 shuffles
 // WALK = false: an instantiation without the band-walking code (half the registers, twice the resident groups) for the
 // usual case that every saturating read has partner records
+#ifndef RG_MINB
+#define RG_MINB 8               // resident blocks per SM the LIST-only instantiation is compiled for (registers <= 65536 / (64 * RG_MINB))
+#endif
+#ifndef RG_REC
+#define RG_REC 32               // reads a group remembers the final stops of (direct mapped by rank)
+#endif
 template <bool ALLMATCH, bool WALK>
-__global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
+__global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
                                                            const int *__restrict__ rstart, const int *__restrict__ isP,
                                                            const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                            int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
@@ -152,14 +155,14 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
                                                            unsigned long long *dbg) {
     __shared__ int4 sA0[RG_GROUPS][4];
     __shared__ int2 sA1[RG_GROUPS][4];
-    __shared__ int sStop[RG_GROUPS][LMAX];
+    __shared__ int sStop[RG_GROUPS][WALK ? LMAX : 1];                              // (WALK mode only)
     __shared__ int4 sP0[RG_GROUPS][RP_K];    // partner records: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}; flags: 1 visited by a,
     __shared__ int4 sP1[RG_GROUPS][RP_K];    //   4 b saw a first, 8 b did not;  {key[0..3]}
     __shared__ int sKey[RG_GROUPS][RP_K];    // first-visit position in the current filling's scan
-    __shared__ int2 sAchr[RG_GROUPS][4];     // [chrom_lo, chrom_hi) of a's fillings (sibling test of the WALK mode)
+    __shared__ int2 sAchr[RG_GROUPS][WALK ? 4 : 1];     // [chrom_lo, chrom_hi) of a's fillings (sibling test of the WALK mode)
     __shared__ int s_umax[LMAX + 1];
-    __shared__ int sRecTag[RG_GROUPS][32];   // the reads this group replayed last (direct mapped by rank & 31) and their final
-    __shared__ int4 sRecStop[RG_GROUPS][32]; //   stops: partners of one run mostly look each other up here, not in global memory
+    __shared__ int sRecTag[RG_GROUPS][RG_REC];   // the reads this group replayed last (direct mapped by rank) and their final
+    __shared__ int4 sRecStop[RG_GROUPS][RG_REC]; //   stops: partners of one run mostly look each other up here, not in global memory
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, gsh = lane & 24, grp = w * 4 + (lane >> 3);
     const unsigned gmask = 0xffu << gsh;
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
     int chunk_used = RP_CHUNK;
     for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
     __syncthreads();
-    for (int k = gl; k < 32; k += 8) sRecTag[grp][k] = -1;
+    for (int k = gl; k < RG_REC; k += 8) sRecTag[grp][k] = -1;
     int wit = 0;
     for (;;) {
         __syncwarp();
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
                 phase = 1;
                 const PLInfo pi = plinfo[a];
                 if (!WALK && pi.n < 0) { atomicOr(err, EF_OVERFLOW); phase = 3; }  // (cannot happen: the host picks WALK when such reads exist)
-                if (gl == 0) { sRecTag[grp][a & 31] = La <= 4 ? a : -1; sRecStop[grp][a & 31] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff); }
+                if (gl == 0) { sRecTag[grp][a & (RG_REC - 1)] = La <= 4 ? a : -1; sRecStop[grp][a & (RG_REC - 1)] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff); }
                 if (!ALLMATCH && pi.n >= 0) {                                      // the pair kernel left a's partner records
                     nPart = pi.n;
                     for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {
@@ -323,8 +326,8 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
             for (int k = 0; k < RP_KL; k++) {                                      // stage B: all the loads, back to back
                 if (poll[k]) {
                     const int b = q0[k].x & QMASK;
-                    if (sRecTag[grp][b & 31] == b) {                               // replayed by this very group a moment ago
-                        const int4 c = sRecStop[grp][b & 31];
+                    if (sRecTag[grp][b & (RG_REC - 1)] == b) {                               // replayed by this very group a moment ago
+                        const int4 c = sRecStop[grp][b & (RG_REC - 1)];
                         sv[k][0] = c.x; sv[k][1] = c.y; sv[k][2] = c.z; sv[k][3] = c.w;
                     } else {
                         const int offb = (int)((unsigned)q0[k].y >> 6), Lb = (q0[k].y & 63) + 1;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
             int brkkey = -1;
             if (need <= 0) brkkey = gmax8(gmask, mxReach);
             else {
-                nEdge += __shfl_xor_sync(gmask, nEdge, 1); nEdge += __shfl_xor_sync(gmask, nEdge, 2); nEdge += __shfl_xor_sync(gmask, nEdge, 4);
+                nEdge = __reduce_add_sync(gmask, nEdge);
                 if (nEdge >= need) {                                               // the need-th highest edge partner
                     int thr = 0x7fffffff;
                     for (int r = 0; r < need; r++) {
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
                 }
                 edges += ne;
                 const int stopf = brkkey >= 0 ? brkkey : lo;
-                if (gl == 0) { st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf); ((int *)&sRecStop[grp][a & 31])[fi] = stopf; }
+                if (gl == 0) { st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf); ((int *)&sRecStop[grp][a & (RG_REC - 1)])[fi] = stopf; }
                 fi++;
                 if (fi == La) { tk++; phase = 0; }
             }
@@ -597,7 +600,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, 8) k_replay(Tab t, const UmaxTa
             if (stopf >= 0) {                                                      // publish the stop; next filling / read
                 if (gl == 0) {
                     sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf);
-                    if (La <= 4) ((int *)&sRecStop[grp][a & 31])[fi] = stopf;
+                    if (La <= 4) ((int *)&sRecStop[grp][a & (RG_REC - 1)])[fi] = stopf;
                 }
                 if (dbg && gl == 0 && d_fsteps > 2000) {
                     if (atomicMax(dbg + 4, (unsigned long long)d_fsteps) < (unsigned long long)d_fsteps) {

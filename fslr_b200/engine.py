@@ -53,31 +53,50 @@ class DeviceTable:
         self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=device)
 
 
+NARROW_OF = {"chrom": ("chrom_u8", np.uint8), "n_alignments": ("n_alignments_u16", np.uint16), "rend": ("rspan_i16", np.int16),
+             "qstart": ("qstart_u16", np.uint16), "qend": ("qend_u16", np.uint16)}
+
+
 class PinnedTable:
-    """The table's columns in pinned host memory (the e2e path copies them in every call).  compact=True keeps `chrom` as
-    uint8 and `n_alignments` as uint16 when they fit, and leaves out `aln_size` when it equals qend - qstart on every row (what
-    collect_mapping_info.py:88 writes), and `read_id` when the rows of every read are contiguous and in id order (run lengths
-    travel instead): 19 instead of 32 bytes per row over PCIe, widened / derived on the device."""
+    """The table's columns in pinned host memory (the e2e path copies them in every call).  compact=True stores the table in
+    its WIRE FORMAT, 13.25 instead of 32 bytes per row over PCIe / NVLink: `chrom` as uint8, `n_alignments`, `qstart`, `qend` as
+    uint16 and `rend` as the int16 difference to `rstart` when the values fit, no `aln_size` when it equals qend - qstart on
+    every row (what collect_mapping_info.py:88 writes), and run lengths instead of `read_id` when the rows of every read are
+    contiguous and in id order.  Every identity is verified here before it is relied on; the library widens on the device."""
 
     def __init__(self, table: ColumnarTable, order=None, compact=False):
         self.n_rows, self.n_reads = table.n_rows, table.n_reads
         self.cols, self.narrow = {}, {}
-        if compact and self.n_rows > 0 and table.n_chrom <= 256 and int(np.max(table.n_alignments)) < 65536 and int(np.min(table.n_alignments)) >= 0:
-            self.narrow = {"chrom": torch.from_numpy(np.ascontiguousarray(table.chrom, dtype=np.uint8)).pin_memory(),
-                           "n_alignments": torch.from_numpy(np.ascontiguousarray(table.n_alignments).astype(np.uint16).view(np.int16)).pin_memory()}
-        self.aln_is_qspan = bool(compact and self.n_rows > 0 and np.array_equal(
+        n = self.n_rows
+
+        def pin(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        if compact and n > 0:
+            i64 = {k: np.asarray(getattr(table, k), dtype=np.int64) for k in ("chrom", "n_alignments", "rstart", "rend", "qstart", "qend")}
+            if table.n_chrom <= 256 and i64["chrom"].min() >= 0:
+                self.narrow["chrom_u8"] = pin(i64["chrom"].astype(np.uint8))
+            if 0 <= i64["n_alignments"].min() and i64["n_alignments"].max() < 65536:
+                self.narrow["n_alignments_u16"] = pin(i64["n_alignments"].astype(np.uint16).view(np.int16))
+            span = i64["rend"] - i64["rstart"]
+            if -32768 <= span.min() and span.max() < 32768:
+                self.narrow["rspan_i16"] = pin(span.astype(np.int16))
+            if 0 <= i64["qstart"].min() and i64["qstart"].max() < 65536 and 0 <= i64["qend"].min() and i64["qend"].max() < 65536:
+                self.narrow["qstart_u16"] = pin(i64["qstart"].astype(np.uint16).view(np.int16))
+                self.narrow["qend_u16"] = pin(i64["qend"].astype(np.uint16).view(np.int16))
+        self.aln_is_qspan = bool(compact and n > 0 and np.array_equal(
             np.asarray(table.aln_size, dtype=np.int64), np.asarray(table.qend, dtype=np.int64) - np.asarray(table.qstart, dtype=np.int64)))
         self.rows_per_read = None
-        if compact and self.n_rows > 0:                      # rows of a read contiguous, reads in id order: send run lengths
+        if compact and n > 0:                                # rows of a read contiguous, reads in id order: send run lengths
             rid = np.asarray(table.read_id)
             cnt = np.bincount(rid, minlength=self.n_reads)
             if cnt.min(initial=1) >= 1 and cnt.max(initial=0) <= 255 and np.array_equal(rid, np.repeat(np.arange(self.n_reads, dtype=rid.dtype), cnt)):
-                self.rows_per_read = torch.from_numpy(cnt.astype(np.uint8)).pin_memory()
+                self.rows_per_read = pin(cnt.astype(np.uint8))
         for k in _COLS:
-            if k in self.narrow or (k == "aln_size" and self.aln_is_qspan) or (k == "read_id" and self.rows_per_read is not None):
+            if (k in NARROW_OF and NARROW_OF[k][0] in self.narrow) or (k == "aln_size" and self.aln_is_qspan) or \
+                    (k == "read_id" and self.rows_per_read is not None):
                 continue
-            t = torch.empty(max(self.n_rows, 1), dtype=torch.int32).pin_memory()
-            t[:self.n_rows] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
+            t = torch.empty(max(n, 1), dtype=torch.int32).pin_memory()
+            t[:n] = torch.from_numpy(np.ascontiguousarray(getattr(table, k), dtype=np.int32))
             self.cols[k] = t
         self.order = None
         if order is not None:
@@ -85,15 +104,49 @@ class PinnedTable:
         self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32).pin_memory()
         self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32).pin_memory()
 
+    def wire_columns(self):
+        """name -> (host tensor, number of valid elements): everything that crosses PCIe for this table."""
+        out = {k: (v, self.n_rows) for k, v in self.cols.items()}
+        out.update({k: (v, self.n_rows) for k, v in self.narrow.items()})
+        if self.rows_per_read is not None:
+            out["rows_per_read_u8"] = (self.rows_per_read, self.n_reads)
+        return out
+
     @property
     def h2d_bytes(self):
-        per_row = 4 * len(self.cols) + (3 if self.narrow else 0)
-        return per_row * self.n_rows + (4 * int(self.order.numel()) if self.order is not None else 0) + \
-            (self.n_reads if self.rows_per_read is not None else 0)
+        return sum(n * t.element_size() for t, n in self.wire_columns().values()) + \
+            (4 * int(self.order.numel()) if self.order is not None else 0)
 
     @property
     def d2h_bytes(self):
         return 8 * self.n_reads
+
+
+class DeviceWireTable:
+    """Multi-GPU ingest of HOST columns: the table's wire columns on this rank's device, filled by `upload`: every rank copies
+    only its 1/world slice of every column over its own PCIe link straight into place and one in-place all-gather per column
+    over NVLink completes it (no staging buffer, no extra pass).  The library widens the narrow columns on the device
+    (fslrc_mg_prepare accepts them as they are)."""
+
+    def __init__(self, ptab: PinnedTable, device, world):
+        from .sharded import row_slice
+        self.n_rows, self.n_reads = ptab.n_rows, ptab.n_reads
+        self.aln_is_qspan, self.order = ptab.aln_is_qspan, None
+        self.world, self.device = world, device
+        self.wire = {}
+        for k, (t, n) in ptab.wire_columns().items():
+            chunk = row_slice(n, 0, world)[2]
+            self.wire[k] = (torch.zeros(max(chunk * world, 1), dtype=t.dtype, device=device), n)
+        self.cols = {k: v[0] for k, v in self.wire.items() if k in _COLS}
+        self.narrow = {k: v[0] for k, v in self.wire.items() if k not in _COLS and k != "rows_per_read_u8"}
+        self.rows_per_read = self.wire["rows_per_read_u8"][0] if "rows_per_read_u8" in self.wire else None
+        self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=device)
+        self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=device)
+
+    def upload(self, ptab: PinnedTable, rank, world, group=None):
+        from .sharded import gather_column_inplace
+        for k, (src, n) in ptab.wire_columns().items():
+            gather_column_inplace(src, self.wire[k][0], n, rank, world, group)
 
 
 class _DevView:
@@ -162,8 +215,8 @@ class Engine:
         for k in _COLS:
             setattr(t, k, buf.cols[k].data_ptr() if k in buf.cols else None)
         narrow = getattr(buf, "narrow", None) or {}
-        t.chrom_u8 = narrow["chrom"].data_ptr() if "chrom" in narrow else None
-        t.n_alignments_u16 = narrow["n_alignments"].data_ptr() if "n_alignments" in narrow else None
+        for k in ("chrom_u8", "n_alignments_u16", "rspan_i16", "qstart_u16", "qend_u16"):
+            setattr(t, k, narrow[k].data_ptr() if k in narrow else None)
         t.aln_size_is_qspan = int(bool(getattr(buf, "aln_is_qspan", False)))
         rpr = getattr(buf, "rows_per_read", None)
         t.rows_per_read_u8 = rpr.data_ptr() if rpr is not None else None
@@ -244,27 +297,6 @@ class Engine:
         self._check(self.lib.fslrc_mg_finish(self.ctx, fptr, tot, dtab.out_cluster.data_ptr(), dtab.out_n_reads.data_ptr(),
                                              C.byref(st)))
         return st.as_dict(self.lib)
-
-    def upload_sharded(self, ptab: PinnedTable, dtab: DeviceTable, rank, world, group=None):
-        """Multi-GPU ingest of HOST columns: every rank copies only its 1/world slice of the rows over its own PCIe link and
-        the slices are all-gathered over NVLink (fslr_b200.sharded.gather_columns), so the host->device time shrinks with
-        the number of GPUs instead of being paid in full by every rank.  Narrow columns of a compact PinnedTable travel
-        narrow (host->device and over NVLink) and are widened on the device."""
-        from .sharded import gather_columns
-        n = dtab.n_rows
-        gather_columns({k: ptab.cols[k] for k in ptab.cols}, {k: dtab.cols[k] for k in ptab.cols}, n, rank, world, group)
-        if ptab.narrow:
-            if not hasattr(dtab, "_narrow"):
-                dtab._narrow = {k: torch.empty(max(n, 1), dtype=v.dtype, device=self.device) for k, v in ptab.narrow.items()}
-            gather_columns(ptab.narrow, dtab._narrow, n, rank, world, group)
-            dtab.cols["chrom"][:n].copy_(dtab._narrow["chrom"][:n])
-            dtab.cols["n_alignments"][:n].copy_(dtab._narrow["n_alignments"][:n])
-            dtab.cols["n_alignments"][:n].bitwise_and_(0xffff)
-        if getattr(ptab, "aln_is_qspan", False):
-            torch.sub(dtab.cols["qend"][:n], dtab.cols["qstart"][:n], out=dtab.cols["aln_size"][:n])
-        if getattr(ptab, "rows_per_read", None) is not None:   # run lengths (one byte per read, sent by every rank) -> read ids
-            cnt = ptab.rows_per_read.to(self.device, non_blocking=True).to(torch.int64)
-            dtab.cols["read_id"][:n].copy_(torch.repeat_interleave(torch.arange(cnt.numel(), device=self.device, dtype=torch.int32), cnt))
 
     def choose_alignment(self, read_id, alignment_score, cluster, n_clusters):
         """cluster.py:237-254 on the GPU.  read_id/alignment_score: int32 per table row; cluster: int32 per read (dense ids).

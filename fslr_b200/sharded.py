@@ -1,10 +1,11 @@
 """Exchange steps of the multi-GPU path, written against torch.distributed only so the same code
 runs over NCCL/NVLink on the GPUs and over gloo in the CPU tests.
 
-The interval table is replicated; the pair space is sharded by query read.  With host inputs the upload is sharded too
-(gather_columns).  Two exchanges exist on the data path:
-  1. sum-all-reduce of the per-read passing-candidate counts (decides which reads are saturating);
-  2. all-gather of every rank's spanning forest (<= n_query_reads - 1 edges each), then one final union-find.
+The interval table is replicated; candidate generation and the pair tests are sharded by query read.  With host inputs the
+upload is sharded too (gather_column_inplace).  Three exchanges exist on the data path:
+  1. sum-all-reduce of the per-read partner counters (decides which reads are saturating), 4 bytes per query read;
+  2. all-gather of the recorded pairs of the saturating reads (8 bytes per pair; the replay runs replicated);
+  3. all-gather of every rank's spanning forest (<= n_query_reads - 1 edges each), then one final union-find.
 """
 import torch
 import torch.distributed as dist
@@ -45,22 +46,20 @@ def row_slice(n_rows, rank, world):
     return lo, min(lo + chunk, n_rows), chunk
 
 
-def gather_columns(host_cols, dev_cols, n_rows, rank, world, group=None):
-    """host_cols: name -> host tensor [>= n_rows] (pinned for the GPU path); dev_cols: name -> tensor [>= n_rows] on this
-    rank's device (CPU tensors under gloo).  Each rank moves rows row_slice(rank) of every column to its device and one
-    all-gather per column gives every rank the whole column."""
-    lo, hi, chunk = row_slice(n_rows, rank, world)
-    for k, dst in dev_cols.items():
-        src = host_cols[k]
-        if world == 1 or not dist.is_initialized():
-            dst[:n_rows].copy_(src[:n_rows], non_blocking=True)
-            continue
-        mine = torch.zeros(chunk, dtype=dst.dtype, device=dst.device)
-        if hi > lo:
-            mine[:hi - lo].copy_(src[lo:hi], non_blocking=True)
-        full = torch.empty(chunk * world, dtype=dst.dtype, device=dst.device)
-        dist.all_gather_into_tensor(full.view(torch.uint8), mine.view(torch.uint8), group=group)   # bytes: any column width
-        dst[:n_rows].copy_(full[:n_rows])
+def gather_column_inplace(src, dst, n, rank, world, group=None):
+    """src: host tensor [>= n] (pinned on the GPU path); dst: tensor [chunk * world] on this rank's device (a CPU tensor under
+    gloo).  This rank moves elements row_slice(rank) of the column into their place in dst; an all-gather whose send buffer
+    IS that slice of dst (NCCL's in-place form) completes the column on every rank: no staging buffer, no copy afterwards."""
+    lo, hi, chunk = row_slice(n, rank, world)
+    if world == 1 or not dist.is_initialized():
+        dst[:n].copy_(src[:n], non_blocking=True)
+        return
+    mine = dst[rank * chunk:(rank + 1) * chunk]
+    if hi > lo:
+        mine[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+    if not dst.is_cuda:
+        mine = mine.clone()                                   # (gloo: keep send and receive buffers apart)
+    dist.all_gather_into_tensor(dst.view(torch.uint8), mine.view(torch.uint8), group=group)   # bytes: any column width
 
 
 def shard_of_read(q, world):

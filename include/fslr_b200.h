@@ -59,15 +59,19 @@ typedef struct {
      * (ties keep bed order).  n_order must equal the number of fillings when given. */
     const int32_t *order;
     int64_t n_order;
-    /* optional narrow forms of two columns for HOST-buffer calls (fslrc_cluster_host): when non-NULL they replace `chrom` /
-     * `n_alignments` on the wire (down to 19 instead of 32 bytes per row over PCIe) and are widened on the device. */
+    /* optional narrow forms of the columns (the table's wire format: 13.25 instead of 32 bytes per row over PCIe / NVLink):
+     * when non-NULL they replace the int32 column of the same name, which may then be NULL, and are widened on the device.
+     * Accepted by the host-buffer call and by the device-resident calls alike (pointers of the same kind as the columns). */
     const uint8_t *chrom_u8;       /* [n_rows] chromosome id < 256 */
     const uint16_t *n_alignments_u16; /* [n_rows] */
     const uint8_t *rows_per_read_u8; /* [n_reads] number of rows of every read when the rows of a read are contiguous and the
-                                      reads appear in id order (every count in 1..255); `read_id` may then be NULL in a
-                                      host-buffer call and is rebuilt on the device */
+                                      reads appear in id order (every count in 1..255); `read_id` may then be NULL and is
+                                      rebuilt on the device */
     int64_t aln_size_is_qspan;     /* non-zero: every row has aln_size == qend - qstart (what collect_mapping_info.py:88
-                                      writes); `aln_size` may then be NULL in a host-buffer call and is derived on the device */
+                                      writes); `aln_size` may then be NULL and is derived on the device */
+    const int16_t *rspan_i16;      /* [n_rows] rend - rstart when every difference fits int16: replaces `rend` */
+    const uint16_t *qstart_u16;    /* [n_rows] when every qend < 65536: replace `qstart` / `qend` */
+    const uint16_t *qend_u16;
 } fslrc_table;
 
 /* The options of main.py:33-37,219-223,237 in numeric form.  The three `*_c`/umax fields are computed by the

@@ -1,5 +1,5 @@
 """Worker of tests/test_gpu_multirank.py: one process per GPU under torchrun, real NCCL.  Every rank uploads its slice of the
-HOST columns (Engine.upload_sharded), runs the sharded step (Engine.run_sharded) and compares its own copy of the result with
+HOST columns (DeviceWireTable.upload), runs the sharded step (Engine.run_sharded) and compares its own copy of the result with
 the CPU oracle; then the checksum of the results is compared across ranks."""
 import os
 import sys
@@ -18,7 +18,7 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from fslr_b200 import synth
-    from fslr_b200.engine import DeviceTable, Engine, PinnedTable
+    from fslr_b200.engine import DeviceWireTable, Engine, PinnedTable
     from fslr_b200.table import ClusterParams, ColumnarTable
     from oracle import oracle as orc
     eng = Engine(local)
@@ -30,10 +30,8 @@ def main():
         ocl, onr, ost = orc.oracle_cluster(t, p)
         for compact in (False, True):
             ptab = PinnedTable(t, compact=compact)
-            dtab = DeviceTable(t, eng.device)
-            for c in dtab.cols.values():                      # the columns must come from the sharded upload, not from DeviceTable
-                c.zero_()
-            eng.upload_sharded(ptab, dtab, rank, world)
+            dtab = DeviceWireTable(ptab, eng.device, world)
+            dtab.upload(ptab, rank, world)
             st = eng.run_sharded(dtab, t, p, rank, world)
             cl, nr = dtab.out_cluster[:t.n_reads].cpu().numpy(), dtab.out_n_reads[:t.n_reads].cpu().numpy()
             assert np.array_equal(cl, ocl), "rank %d %s compact=%s: cluster ids differ from the oracle" % (rank, name, compact)

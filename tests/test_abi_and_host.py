@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from fslr_b200 import _native
-    assert ctypes.sizeof(_native.Table) == 8 * 2 + 8 * 8 + 8 + 8 + 8 * 3 + 8
+    assert ctypes.sizeof(_native.Table) == 8 * 2 + 8 * 8 + 8 + 8 + 8 * 3 + 8 + 8 * 3
     assert ctypes.sizeof(_native.Stats) == 8 * 11 + 4 + 4 + 4 * _native.N_STAGES
     assert _native.Params.umax.offset == 24 and _native.Params.edge_threshold.offset == 24 + 4 * 65 + 4
     assert ctypes.sizeof(_native.BamInfo) == 8 * 4 + 4 * 2 + 8 * 15 + 4 + 4

@@ -135,7 +135,8 @@ def test_host_pipeline_concurrent_contexts():
 
 
 def test_narrow_wire_columns_match():
-    """chrom as uint8 / n_alignments as uint16 on the wire (PinnedTable(compact=True)) give the int32 result."""
+    """The wire format (PinnedTable(compact=True): narrow columns, derived aln_size, run lengths) gives the int32 result, through the
+    host-buffer call and through the device-resident call (narrow columns already in HBM)."""
     from fslr_b200 import synth
     from fslr_b200.engine import PinnedTable, get_engine
     from fslr_b200.table import ClusterParams, ColumnarTable
@@ -143,8 +144,15 @@ def test_narrow_wire_columns_match():
     p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK["C3"])
     eng = get_engine(0)
     wide, narrow = PinnedTable(t), PinnedTable(t, compact=True)
-    assert narrow.narrow and narrow.aln_is_qspan and narrow.rows_per_read is not None and narrow.h2d_bytes == 19 * t.n_rows + t.n_reads
+    assert set(narrow.narrow) == {"chrom_u8", "n_alignments_u16", "rspan_i16", "qstart_u16", "qend_u16"} and set(narrow.cols) == {"rstart"}
+    assert narrow.aln_is_qspan and narrow.rows_per_read is not None and narrow.h2d_bytes == 13 * t.n_rows + t.n_reads
     eng.run_host(wide, t, p)
     eng.run_host(narrow, t, p)
     assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), narrow.out_cluster[:t.n_reads].numpy())
     assert np.array_equal(wide.out_n_reads[:t.n_reads].numpy(), narrow.out_n_reads[:t.n_reads].numpy())
+    from fslr_b200.engine import DeviceWireTable
+    dw = DeviceWireTable(narrow, eng.device, 1)
+    dw.upload(narrow, 0, 1)
+    eng.run_resident(dw, t, p)
+    assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), dw.out_cluster[:t.n_reads].cpu().numpy())
+    assert np.array_equal(wide.out_n_reads[:t.n_reads].numpy(), dw.out_n_reads[:t.n_reads].cpu().numpy())

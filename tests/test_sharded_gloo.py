@@ -19,18 +19,19 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from fslr_b200 import synth
-    from fslr_b200.sharded import exchange_counts, exchange_forests, gather_columns, shard_of_read
+    from fslr_b200.sharded import exchange_counts, exchange_forests, gather_column_inplace, row_slice, shard_of_read
     from fslr_b200.table import ClusterParams, ColumnarTable
     from tests.proto_model import Model
     t = ColumnarTable.from_synth(synth.make_config("C1", 0.12))
     p = ClusterParams.from_options(t, edge_threshold=3)
     m = Model(t, p)
-    # ---- sharded upload: each rank holds 1/world of the rows, all-gather rebuilds the columns (Engine.upload_sharded)
-    host = {"rstart": torch.from_numpy(t.rstart.copy()), "read_id": torch.from_numpy(t.read_id.copy())}
-    devc = {k: torch.zeros(t.n_rows + 3, dtype=v.dtype) for k, v in host.items()}
-    gather_columns(host, devc, t.n_rows, rank, world)
-    for k in host:
-        assert torch.equal(devc[k][:t.n_rows], host[k])
+    # ---- sharded upload: each rank holds 1/world of the rows, an all-gather completes every column (DeviceWireTable.upload)
+    host = {"rstart": torch.from_numpy(t.rstart.copy()), "chrom_u8": torch.from_numpy(t.chrom.astype(np.uint8)),
+            "rspan_i16": torch.from_numpy((t.rend - t.rstart).astype(np.int16))}
+    for k, src in host.items():
+        dst = torch.zeros(row_slice(t.n_rows, 0, world)[2] * world, dtype=src.dtype)
+        gather_column_inplace(src, dst, t.n_rows, rank, world)
+        assert torch.equal(dst[:t.n_rows], src), k
     # ---- sharded phase A: this rank evaluates only the (a, b) pairs of the query reads `a` it owns
     m.degub = np.zeros(m.Q, np.int64)
     m.later, m.cond = [], []
