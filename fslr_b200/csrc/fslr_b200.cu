@@ -148,6 +148,13 @@ static int mark(fslrc_ctx *ctx, int stage_end) {   // record the event closing `
     CK(cudaEventRecord(ctx->ev[stage_end + 1], ctx->stream));
     return 0;
 }
+// resident blocks per SM of a persistent (grid-stride) kernel: its grid is one full wave, never a wave and a bit
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t dyn_smem = 0) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, dyn_smem) != cudaSuccess) { cudaGetLastError(); nb = 1; }
+    return std::max(nb, 1);
+}
 static int n_sms(fslrc_ctx *ctx) {
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -477,8 +484,8 @@ static int pipe_bands(fslrc_ctx *ctx, Pipe *P, const int *s_dp, const int *rmidx
     // (filling of a, band position) hit
     const unsigned long long tight = (unsigned long long)ctx->h_pin[14], lightT = (unsigned long long)ctx->h_pin[44];
     unsigned long long capT = P->Tedge > 0 ? (unsigned long long)Q * ((unsigned long long)P->Tedge + 7ull) : 0ull;
-    P->pair_blocks = std::max(1, std::min(nblk(Q, PK_GROUPS), n_sms(ctx) * 8));
-    P->hits_blocks = std::max(1, std::min(nblk(Q, HK_GROUPS), n_sms(ctx) * 8));
+    P->pair_blocks = std::max(1, std::min(nblk(Q, PK_GROUPS), n_sms(ctx) * resident_blocks(k_pair<false>, PK_WARPS * 32)));
+    P->hits_blocks = std::max(1, std::min(nblk(Q, HK_GROUPS), n_sms(ctx) * resident_blocks(k_hits, HK_WARPS * 32)));
     P->cap_entries = std::min<unsigned long long>(lightT + capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks +
                      (unsigned long long)HK_CHUNK * HK_WARPS * P->hits_blocks + 64;
     DA(P->entries, P->cap_entries);
@@ -497,12 +504,14 @@ static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     cudaStream_t st = ctx->stream;
     const bool dense = P->Q > 0 && P->pr.overlap > 0.0;
     if (P->Q > 0) CK(cudaMemsetAsync(P->cp, 0, sizeof(unsigned) * (size_t)P->Q, st));
-    if (dense)
-        KL(k_hits, P->hits_blocks, HK_WARPS * 32, P->tab, shard, nshard, P->rclass, P->entries, (unsigned long long *)(P->cnt + 5), P->cap_entries,
-           P->heavy_list, (unsigned *)(P->cnt + 46), P->err);
+    if (dense) {
+        KL(k_heavy_list, nblk(P->Q, 256), 256, P->tab, P->rclass, P->heavy_list, (unsigned *)(P->cnt + 46));
+        KL(k_hits, std::max(1, std::min(nblk((P->Q + nshard - 1) / nshard + 256, HK_GROUPS), P->hits_blocks)), HK_WARPS * 32, P->tab, shard, nshard, P->rclass,
+           P->entries, (unsigned long long *)(P->cnt + 5), P->cap_entries, P->err);
+    }
     { int r = mark(ctx, ST_CAND); if (r) return r; }
     if (dense)
-        KL(k_eval, n_sms(ctx) * 8, EV_THREADS, P->tab, P->um, P->entries, (const unsigned long long *)(P->cnt + 5), P->cap_entries, P->cp,
+        KL(k_eval, n_sms(ctx) * resident_blocks(k_eval, EV_THREADS), EV_THREADS, P->tab, P->um, P->entries, (const unsigned long long *)(P->cnt + 5), P->cap_entries, P->cp,
            (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13));
     { int r = mark(ctx, ST_PAIR); if (r) return r; }
 #define PAIR_ARGS P->isP, P->entries, (unsigned long long *)(P->cnt + 5), P->cap_entries, P->PL, P->plinfo, (unsigned long long *)(P->cnt + 40), \
@@ -535,9 +544,9 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     int *posQ;
     DA(posQ, Q);
     if (Q > 0 && P->pr.overlap > 0.0) {                                   // partner records of the light saturating reads
-        if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * 8), PLT_THREADS, P->tab, pairs,
+        if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS)), PLT_THREADS, P->tab, pairs,
                                        (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->cp, P->PL, P->err); }
-        else KL(k_plist, n_sms(ctx) * 8, PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
+        else KL(k_plist, n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS), PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
                 P->cap_entries, P->plinfo, P->cp, P->PL, P->err);
     }
     if (Q > 0) {
@@ -590,7 +599,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
+    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB * UE_PER), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
                                                                            (unsigned long long *)(P->cnt + 8));
     // replayed edges are identical on every rank; rank 0 contributes them once
     if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));

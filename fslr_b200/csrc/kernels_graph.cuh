@@ -13,7 +13,8 @@ __device__ __forceinline__ int uf_find(int *parent, int x) {
     }
 }
 __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
-    for (;;) {
+    if (*(volatile int *)&parent[a] == *(volatile int *)&parent[b]) return;         // (both loads in flight at once) same tree already:
+    for (;;) {                                                                      //  most pairs of a PCR family after its first unions
         a = uf_find(parent, a); b = uf_find(parent, b);
         if (a == b) return;
         if (a < b) { int tmp = a; a = b; b = tmp; }                                  // hook the larger root under the smaller
@@ -23,16 +24,28 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 // entries (a, b) recorded by k_eval / k_pair (a -> b evaluated; only the passing ones matter here): a not saturating;
 // b > a -> a tested it (edge); b < a -> edge only if b is saturating and its scan stopped before reaching a (then a's
 // query tested the pair, direction a -> b)
+#define UE_PER 4
 __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP, Tab t,
                                 const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
-    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    bool e = false;
-    if (k < n) {
-        const int2 ab = entries[k];
-        const int a = ab.x, b = ab.y & QMASK;                                      // y: b | EB_NOPASS | EB_HEAVY
-        if (a >= 0 && ab.y >= 0 && !isP[a]) {                                      // (y < 0: a partner whose pair does not pass)
-            if (b > a) e = true;
-            else if (isP[b]) {
+    const unsigned long long k0 = (unsigned long long)blockIdx.x * (blockDim.x * UE_PER) + threadIdx.x;
+    int2 ab[UE_PER];
+    int pa[UE_PER];
+    int ne = 0;
+#pragma unroll
+    for (int u = 0; u < UE_PER; u++) {                                              // all entries, then all flags: loads in flight together
+        const unsigned long long k = k0 + (unsigned long long)u * blockDim.x;
+        ab[u] = k < n ? __ldg(&entries[k]) : make_int2(-1, -1);
+    }
+#pragma unroll
+    for (int u = 0; u < UE_PER; u++) pa[u] = (ab[u].x >= 0 && ab[u].y >= 0) ? __ldg(&isP[ab[u].x]) : 1;   // (y < 0: the pair does not pass)
+#pragma unroll
+    for (int u = 0; u < UE_PER; u++) {
+        if (pa[u]) continue;
+        const int a = ab[u].x, b = ab[u].y & QMASK;                                 // y: b | EB_NOPASS | EB_HEAVY
+        bool e = true;
+        if (b < a) {
+            e = false;
+            if (isP[b]) {
                 const int wa = t.RI[a].w, wb = t.RI[b].w;
                 const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
                 e = true;
@@ -47,10 +60,15 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
                 }
             }
         }
-        if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); }
+        if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); ne++; }
     }
-    const int cnt = __syncthreads_count(e);                                        // one counter update per block
-    if (threadIdx.x == 0 && cnt) atomicAdd(n_edges, (unsigned long long)cnt);
+    for (int o = 16; o; o >>= 1) ne += __shfl_down_sync(0xffffffffu, ne, o);
+    __shared__ int s_ne;
+    if (threadIdx.x == 0) s_ne = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && ne) atomicAdd(&s_ne, ne);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_ne) atomicAdd(n_edges, (unsigned long long)s_ne);    // one counter update per block
 }
 __global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing, unsigned long long *n_edges) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;

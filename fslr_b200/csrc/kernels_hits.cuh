@@ -23,9 +23,21 @@
 __device__ __forceinline__ bool shard_owns(int q, int shard, int nshard) { return nshard <= 1 || ((q >> 8) % nshard) == shard; }
 __device__ __forceinline__ bool read_is_heavy(int La, const int *__restrict__ rclass, int q) { return La > 4 || __ldg(&rclass[q]) != 0; }
 
-__global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
-                                                        unsigned long long *n_slots, unsigned long long cap, int *heavy_list,
-                                                        unsigned *n_heavy, int *err) {
+// the heavy reads, listed for k_pair (every rank lists — and later runs — ALL of them: their partner records are needed everywhere)
+__global__ void k_heavy_list(Tab t, const int *__restrict__ rclass, int *heavy_list, unsigned *n_heavy) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool heavy = q < t.Q && read_is_heavy((__ldg(&t.RI[q]).w & 63) + 1, rclass, q);
+    const unsigned hv = __ballot_sync(0xffffffffu, heavy);
+    if (!hv) return;
+    unsigned hb = 0;
+    if ((threadIdx.x & 31) == 0) hb = atomicAdd(n_heavy, (unsigned)__popc(hv));
+    hb = __shfl_sync(0xffffffffu, hb, 0);
+    if (heavy) heavy_list[hb + __popc(hv & ((1u << (threadIdx.x & 31)) - 1u))] = q;
+}
+// The query reads of this shard only: the j-th owned read is q = ((shard + (j >> 8) * nshard) << 8) | (j & 255) (256-read
+// groups, round robin over ranks: consecutive ranks = usually one PCR family stay on one rank).
+__global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
+                                                        unsigned long long *n_slots, unsigned long long cap, int *err) {
     __shared__ int2 sHash[HK_GROUPS][HK_HASH];                                     // {b, q}: partner b was hit during read q's scan ...
     __shared__ int sHkey[HK_GROUPS][HK_HASH];                                      // ... at filling pair fa << 6 | fb (the lowest listed so far)
     const unsigned FULL = 0xffffffffu;
@@ -36,21 +48,16 @@ __global__ void __launch_bounds__(HK_WARPS * 32) k_hits(Tab t, int shard, int ns
     for (int k = gl; k < HK_HASH; k += 8) sHash[grp][k] = make_int2(-1, -1);
     __syncwarp();
     const int stride = gridDim.x * HK_GROUPS;
-    for (int q0 = blockIdx.x * HK_GROUPS; q0 < t.Q; q0 += stride) {                // block-uniform trip count
-        const int q = q0 + grp;
-        const bool inq = q < t.Q;
+    const int nblocks256 = (t.Q + 255) >> 8;
+    const int owned = nshard <= 1 ? t.Q : ((nblocks256 - shard + nshard - 1) / nshard) << 8;   // (upper bound: the last group may be short)
+    for (int j0 = blockIdx.x * HK_GROUPS; j0 < owned; j0 += stride) {              // block-uniform trip count
+        const int j = j0 + grp;
+        const int q = nshard <= 1 ? j : (((shard + (j >> 8) * nshard) << 8) | (j & 255));
+        const bool inq = j < owned && q < t.Q;
         int4 ri = make_int4(0, 0, 0, 0);
         if (inq) ri = __ldg(&t.RI[q]);
         const int off = (int)((unsigned)ri.w >> 6), La = inq ? (ri.w & 63) + 1 : 0;
-        const bool heavy = inq && read_is_heavy(La, rclass, q);                    // every rank lists (and later runs) ALL heavy reads
-        const unsigned hv = __ballot_sync(FULL, heavy && gl == 0);
-        if (hv) {
-            unsigned hb = 0;
-            if (lane == 0) hb = atomicAdd(n_heavy, (unsigned)__popc(hv));
-            hb = __shfl_sync(FULL, hb, 0);
-            if (heavy && gl == 0) heavy_list[hb + __popc(hv & ltmask)] = q;
-        }
-        const bool light = inq && !heavy && shard_owns(q, shard, nshard);
+        const bool light = inq && !read_is_heavy(La, rclass, q);
         const int maxLa = __reduce_max_sync(FULL, light ? La : 0);
         for (int fi = 0; fi < maxLa; fi++) {
             const bool act = light && fi < La;
@@ -190,7 +197,7 @@ __global__ void k_light_sat(Tab t, const int *__restrict__ rclass, unsigned *cp,
                             unsigned long long *pl_slots) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= t.Q) return;
-    const int La = (__ldg(&t.RI[q]).w & 63) + 1;
+    const int wq = __ldg(&t.RI[q]).w, La = (wq & 63) + 1;
     if (read_is_heavy(La, rclass, q)) { plcount[q] = 0; return; }                  // isP / plinfo of heavy reads: k_pair
     const unsigned c = cp[q];
     const int pass = (int)(c & 0xffffu), np = (int)((c >> 16) & 0x7fffu);
@@ -199,7 +206,7 @@ __global__ void k_light_sat(Tab t, const int *__restrict__ rclass, unsigned *cp,
     int n = 0;
     if (sat) n = (np <= RP_K && !(c & CP_LONG)) ? np : -1;
     if (n < 0) atomicAdd(pl_slots + 3, 1ull);                                      // (reads the replay has to WALK)
-    PLInfo pi; pi.off = 0; pi.n = n; pi.pad = 0;
+    PLInfo pi; pi.off = 0; pi.n = n; pi.pad = wq;                                  // (pad: where a's fillings live, for k_plist)
     plinfo[q] = pi;
     plcount[q] = n > 0 ? n : 0;
     cp[q] = 0;
@@ -227,10 +234,11 @@ __global__ void __launch_bounds__(PLT_THREADS) k_plist(Tab t, const int2 *__rest
         const int2 e = __ldg(&ent[i]);
         const int a = e.x;
         if (a < 0 || ((unsigned)e.y & EB_HEAVY)) continue;
-        const PLInfo pi = plinfo[a];                                                // n > 0: saturating, and the replay takes its list
-        if (pi.n <= 0) continue;
         const int b = e.y & QMASK;
-        const int wa = __ldg(&t.RI[a]).w, wb = __ldg(&t.RI[b]).w;
+        const PLInfo pi = plinfo[a];                                                // n > 0: saturating, and the replay takes its list
+        const int wb = __ldg(&t.RI[b]).w;                                           // (both gathers in flight together)
+        if (pi.n <= 0) continue;
+        const int wa = pi.pad;
         const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
         const unsigned slot = atomicAdd(&cp[a], 1u);
         if ((int)slot >= pi.n || La > 4 || Lb > 4) { atomicOr(err, EF_OVERFLOW); continue; }   // (cannot happen: counted by k_eval)

@@ -478,3 +478,4 @@ __global__ void k_chrom_bounds(int D, const int *__restrict__ s_chrom, int *chro
     if (p == 0 || s_chrom[p - 1] != c) chrom_lo[c] = p;
     if (p == D - 1 || s_chrom[p + 1] != c) chrom_hi[c] = p + 1;
 }
+

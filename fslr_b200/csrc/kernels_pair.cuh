@@ -124,7 +124,7 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 #define RP_K 64                 // partners a saturating read may have for the replay's LIST mode
 #define PL_CHUNK 512            // partner records a warp reserves at a time (>= 4 * RP_K)
 #ifndef RP_KL
-#define RP_KL 4                  // partners per lane of a replay group handled in one batch (8 * RP_KL partners per batch)
+#define RP_KL 3                  // partners per lane of a replay group handled in one batch (8 * RP_KL partners per batch)
 #endif
 
 // Partner record of a saturating read a (replay LIST mode): everything the replay needs to know about partner b without

@@ -141,10 +141,10 @@ __device__ __forceinline__ int gmax8(unsigned gmask, int v) { return __reduce_ma
 // WALK = false: an instantiation without the band-walking code (half the registers, twice the resident groups) for the
 // usual case that every saturating read has partner records
 #ifndef RG_MINB
-#define RG_MINB 8               // resident blocks per SM the LIST-only instantiation is compiled for (registers <= 65536 / (64 * RG_MINB))
+#define RG_MINB 10              // resident blocks per SM the LIST-only instantiation is compiled for (registers <= 65536 / (64 * RG_MINB))
 #endif
 #ifndef RG_REC
-#define RG_REC 32               // reads a group remembers the final stops of (direct mapped by rank)
+#define RG_REC 16               // reads a group remembers the final stops of (direct mapped by rank)
 #endif
 template <bool ALLMATCH, bool WALK>
 __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
@@ -304,9 +304,11 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
             // pass 1: where does the scan first meet each partner (its highest interval inside the closed band); did an
             // earlier-ranked partner's own query see a first?  cls: 0 not met, 1 seen, 2 reach, 3 reach + edge, 4 undecided
             int mxReach = -1, mxUn = -1, nEdge = 0;
-            for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {                        // 32 partners per batch (usually one batch)
+            const bool one = nPart <= 8 * RP_KL;                                   // one batch: its partners stay in registers below
             int4 q0[RP_KL];
-            int keyk[RP_KL], sv[RP_KL][4];
+            int keyk[RP_KL], ekey[RP_KL];                                          // ekey: key of a reached edge partner, else -1
+            for (int jb = 0; jb < nPart; jb += 8 * RP_KL) {                        // 8 * RP_KL partners per batch (usually one batch)
+            int sv[RP_KL][4];
             bool poll[RP_KL];
 #pragma unroll
             for (int k = 0; k < RP_KL; k++) {                                      // stage A: keys; who needs b's stops?
@@ -352,11 +354,15 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                     if (vis) q0[k].w |= 4; else if (!unres) q0[k].w |= 8;
                     sP0[grp][j].w = q0[k].w;
                 }
+                ekey[k] = -1;
                 if (keyk[k] >= 0) {
-                    if ((q0[k].x & QMASK) > a || (q0[k].w & 8)) { mxReach = max(mxReach, keyk[k]); nEdge += (unsigned)q0[k].x >> 31; }
+                    if ((q0[k].x & QMASK) > a || (q0[k].w & 8)) {
+                        mxReach = max(mxReach, keyk[k]); nEdge += (unsigned)q0[k].x >> 31;
+                        if (q0[k].x < 0) ekey[k] = keyk[k];
+                    }
                     else if (!(q0[k].w & 4)) mxUn = max(mxUn, keyk[k]);
                 }
-                if (j < nPart) sKey[grp][j] = keyk[k];
+                if (!one && j < nPart) sKey[grp][j] = keyk[k];
             }
             }
             __syncwarp(gmask);
@@ -368,16 +374,25 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                 nEdge = __reduce_add_sync(gmask, nEdge);
                 if (nEdge >= need) {                                               // the need-th highest edge partner
                     int thr = 0x7fffffff;
-                    for (int r = 0; r < need; r++) {
-                        int m = -1;
-                        for (int j = gl; j < nPart; j += 8) {
-                            const int key = sKey[grp][j];
-                            if (key >= 0 && key < thr) {
-                                const int4 r0 = sP0[grp][j];
-                                if (r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8))) m = max(m, key);
-                            }
+                    if (one) {                                                     // selection over registers: one REDUX per round
+                        for (int r = 0; r < need; r++) {
+                            int m = -1;
+#pragma unroll
+                            for (int k = 0; k < RP_KL; k++) if (ekey[k] < thr) m = max(m, ekey[k]);
+                            thr = gmax8(gmask, m);
                         }
-                        thr = gmax8(gmask, m);
+                    } else {
+                        for (int r = 0; r < need; r++) {
+                            int m = -1;
+                            for (int j = gl; j < nPart; j += 8) {
+                                const int key = sKey[grp][j];
+                                if (key >= 0 && key < thr) {
+                                    const int4 r0 = sP0[grp][j];
+                                    if (r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8))) m = max(m, key);
+                                }
+                            }
+                            thr = gmax8(gmask, m);
+                        }
                     }
                     brkkey = thr;
                 }
@@ -390,12 +405,24 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                 for (int j0 = 0; j0 < nPart; j0 += 8) {                            // commit: everything met at or above the break
                     const int j = j0 + gl;
                     bool emit = false;
-                    if (j < nPart) {
+                    int bq = 0;
+                    if (one) {                                                     // (j0 = 8 k: this lane's k-th partner, still in registers)
+                        const int k = j0 >> 3;
+                        int key = -1; int4 r0 = make_int4(0, 0, 0, 0);
+#pragma unroll
+                        for (int kk = 0; kk < RP_KL; kk++) if (kk == k) { key = keyk[kk]; r0 = q0[kk]; }
+                        if (j < nPart && key >= 0 && key >= brkkey) {
+                            sP0[grp][j].w = r0.w | 1;                              // a's query has now seen this pair
+                            emit = r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8));
+                            bq = r0.x & QMASK;
+                        }
+                    } else if (j < nPart) {
                         const int key = sKey[grp][j];
                         if (key >= 0 && key >= brkkey) {
                             const int4 r0 = sP0[grp][j];
                             sP0[grp][j].w = r0.w | 1;                              // a's query has now seen this pair
                             emit = r0.x < 0 && ((r0.x & QMASK) > a || (r0.w & 8));
+                            bq = r0.x & QMASK;
                         }
                     }
                     const unsigned em = (__ballot_sync(gmask, emit) >> gsh) & 0xffu;
@@ -408,7 +435,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                             chunk_used = 0;
                             if (chunk_base + RP_CHUNK > cap_pedges) { if (gl == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
                         }
-                        if (emit) pedges[chunk_base + chunk_used + __popc(em & ((1u << gl) - 1u))] = make_int2(a, sP0[grp][j].x & QMASK);
+                        if (emit) pedges[chunk_base + chunk_used + __popc(em & ((1u << gl) - 1u))] = make_int2(a, bq);
                         chunk_used += n;
                         ne += n;
                     }

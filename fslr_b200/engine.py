@@ -264,17 +264,31 @@ class Engine:
         Exchange steps (torch.distributed, NCCL on GPUs): sum-all-reduce of the per-read partner counters (4 bytes per query
         read), all-gather of the recorded pairs of saturating reads (8 bytes per pair: the replay needs them on every
         rank), all-gather of each rank's spanning forest.  Every rank ends with the full result in dtab.out_*."""
+        import os
+        import time
         from .sharded import exchange_counts, exchange_forests
+        dbg = os.environ.get("FSLRC_DEBUG_MG") == "1"
+        tl = []
+
+        def lap(name):
+            if dbg:
+                torch.cuda.synchronize()
+                tl.append((name, time.perf_counter()))
         p = self._params(chrom_table, params)
         t = self._table(dtab)
         st = _native.Stats()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        lap("start")
         self._check(self.lib.fslrc_mg_prepare(self.ctx, C.byref(t), C.byref(p), C.c_void_p(stream)))
+        lap("prepare")
         ptr, n = C.c_void_p(), C.c_int64()
         self._check(self.lib.fslrc_mg_pair(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        lap("pair")
         if n.value > 0 and world > 1:
             exchange_counts(torch.as_tensor(_DevView(ptr.value, (n.value,)), device=self.device), group)
+        lap("allreduce_counters")
         self._check(self.lib.fslrc_mg_partners(self.ctx, rank, world, C.byref(ptr), C.byref(n)))
+        lap("partners")
         npairs = int(n.value)
         if world > 1:
             local = (torch.as_tensor(_DevView(ptr.value, (2 * npairs,)), device=self.device) if npairs > 0
@@ -284,7 +298,9 @@ class Engine:
             pptr = pairs.data_ptr() if npairs > 0 else None
         else:
             pptr = ptr.value if npairs > 0 else None
+        lap("allgather_pairs")
         self._check(self.lib.fslrc_mg_replay(self.ctx, rank, world, pptr, npairs, C.byref(ptr), C.byref(n)))
+        lap("replay_union")
         ne = int(n.value)
         if world > 1:
             local = (torch.as_tensor(_DevView(ptr.value, (2 * ne,)), device=self.device) if ne > 0
@@ -294,8 +310,14 @@ class Engine:
             fptr = forest.data_ptr() if tot > 0 else None
         else:
             tot, fptr = ne, ptr.value if ne > 0 else None
+        lap("allgather_forests")
         self._check(self.lib.fslrc_mg_finish(self.ctx, fptr, tot, dtab.out_cluster.data_ptr(), dtab.out_n_reads.data_ptr(),
                                              C.byref(st)))
+        lap("finish")
+        if dbg and rank == 0:
+            import sys
+            print("[mg] " + "  ".join("%s %.2f" % (b[0], 1e3 * (b[1] - a[1])) for a, b in zip(tl, tl[1:])) + "  (ms; pairs %d, forest edges %d)" % (npairs, tot),
+                  file=sys.stderr)
         return st.as_dict(self.lib)
 
     def choose_alignment(self, read_id, alignment_score, cluster, n_clusters):
