@@ -300,8 +300,8 @@ static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, co
     P->F = (int)ctx->h_pin[0];
     const int D = P->D = (int)ctx->h_pin[1];
     { int r = mark(ctx, ST_KEEP); if (r) return r; }
-    int4 *REC, *IT0; int2 *IT1; unsigned *key, *key2; int *val, *dfill; long long *flag64, *qo64, *QO;
-    DA(REC, 2 * (int64_t)D); DA(key, D); DA(key2, D); DA(val, D); DA(dfill, D); DA(IT0, D); DA(IT1, D);
+    int4 *REC, *IT0; unsigned *key, *key2; int *val, *dfill, *ITn; long long *flag64, *qo64, *QO;
+    DA(REC, 2 * (int64_t)D); DA(key, D); DA(key2, D); DA(val, D); DA(dfill, D); DA(IT0, D); DA(ITn, D);
     DA(flag64, D); DA(qo64, D); DA(QO, R);
     unsigned *tkey = nullptr, *tval = nullptr;
     int kbits = 32;
@@ -315,16 +315,16 @@ static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, co
         kbits = (known && mx < 0x7fffffffLL) ? std::min(32, bits_for(mx + 2)) : 32;
         KL(k_fi_fast, nblk(D, TB), TB, D, REC, P->err);
         int r = sort_pairs(ctx, P, key, key2, val, dfill, D, 0, kbits); if (r) return r;
-        KL(k_items_fast, nblk(D, TB), TB, D, dfill, REC, IT0, IT1, flag64);
+        KL(k_items_fast, nblk(D, TB), TB, D, dfill, REC, IT0, ITn, flag64);
         DA(tkey, D); DA(tval, D);
-        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
+        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, (const int *)dfill, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
     }
     { int r = mark(ctx, ST_ORDER); if (r) return r; }
     // ---- query rank + read-major offsets from one scan over data order
     DA(P->RI, std::min(R, D));
     if (D > 0) {
         int r = xscan64(ctx, P, flag64, qo64, D, P->cnt + 2); if (r) return r;
-        KL(k_firsts_fast, nblk(D, TB), TB, D, flag64, qo64, IT0, IT1, qlen2, pr.qlen_c, pr.naln_c, QO, P->RI, P->err);
+        KL(k_firsts_fast, nblk(D, TB), TB, D, flag64, qo64, IT0, ITn, qlen2, pr.qlen_c, pr.naln_c, QO, P->RI, P->err);
         KL(k_assign_fast, nblk(D, TB), TB, D, REC, QO, P->q_of_rid);
     }
     { int r = read_counts(ctx, P); if (r) return r; r = err_code(ctx); if (r) return r; }
@@ -338,9 +338,8 @@ static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, co
     { int r = mark(ctx, ST_QRANK); if (r) return r; }
     int *s_u; DA(s_u, D);
     const bool tie_ok = tkey && ctx->h_pin[41] == 0;
-    if (D > 0 && tie_ok) KL(k_val_to_u, nblk(D, TB), TB, D, dfill, tval);         // the partition carries the filling index u
     { int r = pipe_chrom_order(ctx, P, IT0, tkey, tval, tie_ok, s_u); if (r) return r; }
-    if (D > 0 && !tie_ok) {                                                        // (three-sort fallback yields data positions)
+    if (D > 0 && !tie_ok) {                                                        // (the three-sort fallback yields data positions, not filling indices)
         int *tmp; DA(tmp, D);
         KL(k_gather_int, nblk(D, TB), TB, D, s_u, dfill, tmp);
         s_u = tmp;
@@ -416,7 +415,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (D > 0) KL(k_build_items, nblk(D, TB), TB, D, dfill, FR0, FR1, IT0, IT1, firstdp, P->err);
     if (D > 0 && D < (1 << 26)) {
         DA(tkey, D); DA(tkey2, D); DA(tval, D); DA(tval2, D);
-        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
+        KL(k_tie_delta, nblk(D, TB), TB, D, IT0, (const int *)nullptr, tkey, tval, (unsigned long long *)(P->cnt + 41), P->err);
     }
     { int r = mark(ctx, ST_ORDER); if (r) return r; }
     // ---- stage 3: query rank + per-read lists

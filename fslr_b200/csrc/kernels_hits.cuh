@@ -36,12 +36,16 @@ __global__ void k_heavy_list(Tab t, const int *__restrict__ rclass, int *heavy_l
 }
 // The query reads of this shard only: the j-th owned read is q = ((shard + (j >> 8) * nshard) << 8) | (j & 255) (256-read
 // groups, round robin over ranks: consecutive ranks = usually one PCR family stay on one rank).
+// The tight bands of a read's (<= 4) fillings are walked as ONE concatenated list of (filling, position) pairs, 8 per step:
+// no per-filling loop, and the lanes of a group stay busy whatever the individual band lengths are.
 __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
-                                                        unsigned long long *n_slots, unsigned long long cap, int *err) {
+                                                           unsigned long long *n_slots, unsigned long long cap, int *err) {
     __shared__ int2 sHash[HK_GROUPS][HK_HASH];                                     // {b, q}: partner b was hit during read q's scan ...
     __shared__ int sHkey[HK_GROUPS][HK_HASH];                                      // ... at filling pair fa << 6 | fb (the lowest listed so far)
+    __shared__ int4 sF[HK_GROUPS][4];                                              // the read's fillings {chrom, start, end, T}
+    __shared__ int2 sBd[HK_GROUPS][4];                                             // {first band position - its offset in the list, offset of the next filling}
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, grp = w * 4 + (lane >> 3);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, gl = lane & 7, gsh = lane & 24, grp = w * 4 + (lane >> 3);
     const unsigned ltmask = (1u << lane) - 1u;
     unsigned long long chunk_base = 0;
     int chunk_used = HK_CHUNK;                                                     // nothing reserved yet
@@ -58,41 +62,53 @@ __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int
         if (inq) ri = __ldg(&t.RI[q]);
         const int off = (int)((unsigned)ri.w >> 6), La = inq ? (ri.w & 63) + 1 : 0;
         const bool light = inq && !read_is_heavy(La, rclass, q);
-        const int maxLa = __reduce_max_sync(FULL, light ? La : 0);
-        for (int fi = 0; fi < maxLa; fi++) {
-            const bool act = light && fi < La;
-            int4 f = make_int4(0, 0, 0, 0);
-            int2 band = make_int2(1, 0);
-            if (act) { f = rm0(t, off + fi); band = rm2(t, off + fi); }
-            for (int ch = 0;; ch++) {
-                const int p = band.x + ch * 8 + gl;
-                const bool v = act && p <= band.y;
-                if (!__any_sync(FULL, v)) break;                                    // every group of the warp is through its band
-                int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
-                if (v) c0 = __ldg(&t.SR0[p]);
-                const int b = c0.w & QMASK;
-                bool hit = v && b != q && (min(f.z, c0.y) - max(f.y, c0.x)) >= max(f.w, c0.z);   // cluster.py:157, T >= 1
-                if (hit) {                                                          // a filter only: k_eval's canonical rule is exact
-                    const int slot = b & (HK_HASH - 1), key = (fi << 6) | (int)((unsigned)c0.w >> 26);
-                    const int2 h = sHash[grp][slot];
-                    if (h.x == b && h.y == q && sHkey[grp][slot] < key) hit = false;   // a hit of (q, b) at a lower filling pair is listed
-                    else { sHash[grp][slot] = make_int2(b, q); sHkey[grp][slot] = key; }
-                }
-                const unsigned hm = __ballot_sync(FULL, hit);
-                if (hm) {
-                    const int n = __popc(hm);
-                    if (chunk_used + n > HK_CHUNK) {
-                        for (int k = chunk_used + lane; k < HK_CHUNK; k += 32) hits[chunk_base + k] = make_int2(-1, -1);
-                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)HK_CHUNK);
-                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
-                        chunk_used = 0;
-                        if (chunk_base + HK_CHUNK > cap) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
-                    }
-                    if (hit) hits[chunk_base + chunk_used + __popc(hm & ltmask)] = make_int2((int)((unsigned)q | ((unsigned)fi << 26)), p);
-                    chunk_used += n;
-                }
-                __syncwarp();                                                       // filter updates visible to the next step
+        // ---- lane fi < La fetches filling fi and its band; an 8-lane prefix sum of the band lengths lays the list out
+        int len = 0;
+        int4 f = make_int4(0, 0, 0, 0);
+        int2 band = make_int2(1, 0);
+        if (light && gl < La) { f = rm0(t, off + gl); band = rm2(t, off + gl); len = band.y - band.x + 1; }
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) { const int y = __shfl_up_sync(FULL, incl, o, 8); if (gl >= o) incl += y; }
+        const int total = __shfl_sync(FULL, incl, gsh + 3);                        // (lanes 4-7 of a group hold len = 0)
+        __syncwarp();
+        if (gl < 4) { sF[grp][gl] = f; sBd[grp][gl] = make_int2(band.x - (incl - len), incl); }
+        __syncwarp();
+        const int steps = __reduce_max_sync(FULL, (total + 7) >> 3);
+        const int e0 = sBd[grp][0].y, e1 = sBd[grp][1].y, e2 = sBd[grp][2].y;
+        for (int sidx = 0; sidx < steps; sidx++) {
+            const int flat = sidx * 8 + gl;
+            const bool v = flat < total;
+            int4 c0 = make_int4(0, 0, 0x7fffffff, -1);
+            int fi = 0, p = 0;
+            if (v) {
+                fi = (flat >= e0) + (flat >= e1) + (flat >= e2);
+                p = sBd[grp][fi].x + flat;
+                c0 = __ldg(&t.SR0[p]);
             }
+            const int4 ff = sF[grp][fi];
+            const int b = c0.w & QMASK;
+            bool hit = v && b != q && (min(ff.z, c0.y) - max(ff.y, c0.x)) >= max(ff.w, c0.z);   // cluster.py:157, T >= 1
+            if (hit) {                                                              // a filter only: k_eval's canonical rule is exact
+                const int slot = b & (HK_HASH - 1), key = (fi << 6) | (int)((unsigned)c0.w >> 26);
+                const int2 h = sHash[grp][slot];
+                if (h.x == b && h.y == q && sHkey[grp][slot] < key) hit = false;   // a hit of (q, b) at a lower filling pair is listed
+                else { sHash[grp][slot] = make_int2(b, q); sHkey[grp][slot] = key; }
+            }
+            const unsigned hm = __ballot_sync(FULL, hit);
+            if (hm) {
+                const int n = __popc(hm);
+                if (chunk_used + n > HK_CHUNK) {
+                    for (int k = chunk_used + lane; k < HK_CHUNK; k += 32) hits[chunk_base + k] = make_int2(-1, -1);
+                    if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)HK_CHUNK);
+                    chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                    chunk_used = 0;
+                    if (chunk_base + HK_CHUNK > cap) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                }
+                if (hit) hits[chunk_base + chunk_used + __popc(hm & ltmask)] = make_int2((int)((unsigned)q | ((unsigned)fi << 26)), p);
+                chunk_used += n;
+            }
+            __syncwarp();                                                           // filter updates visible to the next step
         }
     }
     if (chunk_used < HK_CHUNK)

@@ -191,7 +191,9 @@ __global__ void k_gather_key(int D, const int *__restrict__ dp_in, const int4 *_
 // as a block, so the item's final position is its partition position + (rank - idx).  val[d] = d | (rank - idx + 32) << 26.
 // Runs that do not fit the window raise `overflow` and the caller falls back to the two full radix sorts.
 #define TIE_WIN 48
-__global__ void k_tie_delta(int D, const int4 *__restrict__ IT0, unsigned *ckey, unsigned *val, unsigned long long *overflow, int *err) {
+// vmap (optional): the value sent through the partition is vmap[d] instead of d (fast ingest: the filling index)
+__global__ void k_tie_delta(int D, const int4 *__restrict__ IT0, const int *__restrict__ vmap, unsigned *ckey, unsigned *val,
+                            unsigned long long *overflow, int *err) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     const int4 me = IT0[d];
@@ -215,7 +217,7 @@ __global__ void k_tie_delta(int D, const int4 *__restrict__ IT0, unsigned *ckey,
     if (idx > 31 || rank > 31) ovf = true;
     if (ovf) { atomicAdd(overflow, 1ull); rank = idx; }
     ckey[d] = (unsigned)me.y;
-    val[d] = (unsigned)d | ((unsigned)(rank - idx + 32) << 26);
+    val[d] = (unsigned)(vmap ? vmap[d] : d) | ((unsigned)(rank - idx + 32) << 26);
 }
 __global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -408,21 +410,21 @@ __global__ void k_fi_fast(int D, int4 *REC, int *err) {
 }
 // per data position d (filling u = dfill[d]): the filling's record, gathered as one sector, written out coalesced;
 // flag64[d] = (1 << 32 | L) when the filling is its read's first item in data order (fi == 0), else 0
-__global__ void k_items_fast(int D, const int *__restrict__ dfill, const int4 *__restrict__ REC, int4 *IT0, int2 *IT1, long long *flag64) {
+__global__ void k_items_fast(int D, const int *__restrict__ dfill, const int4 *__restrict__ REC, int4 *IT0, int *ITn, long long *flag64) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     const int u = dfill[d];
-    const int4 r0 = REC[2 * u], r1 = REC[2 * u + 1];
+    const int4 r0 = REC[2 * u], r1 = REC[2 * u + 1];                                // (one sector) r1 = {aln_size, n_alignments, fi, L}
     IT0[d] = r0;
-    IT1[d] = make_int2(r1.x, r1.y);
+    ITn[d] = r1.y;
     flag64[d] = r1.z == 0 ? ((1ll << 32) | (long long)r1.w) : 0ll;
 }
 // the read's first item in data order knows the read's query rank q and read-major offset `off` (the scan at its position):
 // QO[read_id] = (q << 32 | off) — the only scattered write of the fast ingest, one per query read — and RI[q] (k_read_info;
 // consecutive first items write consecutive q)
 __global__ void k_firsts_fast(int D, const long long *__restrict__ flag64, const long long *__restrict__ qo64, const int4 *__restrict__ IT0,
-                              const int2 *__restrict__ IT1, const int *__restrict__ qlen2, double qlen_c, double naln_c, long long *QO,
-                              int4 *RI, int *err) {
+                              const int *__restrict__ ITn, const int *__restrict__ qlen2, double qlen_c,
+                              double naln_c, long long *QO, int4 *RI, int *err) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= D) return;
     const long long fl = flag64[d];
@@ -430,7 +432,7 @@ __global__ void k_firsts_fast(int D, const long long *__restrict__ flag64, const
     const long long qo = qo64[d];
     const int q = (int)(qo >> 32), off = (int)(qo & 0xffffffffll), L = (int)(fl & 0xffffffffll), rid = IT0[d].x;
     QO[rid] = qo;
-    int ql = qlen2[rid], na = IT1[d].y;
+    int ql = qlen2[rid], na = ITn[d];
     if (ql <= 0 || na <= 0) { atomicOr(err, EF_ZERO); ql = ql <= 0 ? 1 : ql; na = na <= 0 ? 1 : na; }
     int Ln = thr_f64(na, naln_c);
     if (Ln > 65535) Ln = 65535;
@@ -449,11 +451,6 @@ __global__ void k_assign_fast(int D, int4 *REC, const long long *__restrict__ QO
     r1.z = (int)((unsigned)q | ((unsigned)(fi & 63) << 26)); r1.w = off + fi;
     REC[2 * u + 1] = r1;
     if (u == 0 || REC[2 * (u - 1)].x != rid) q_of_rid[rid] = q;
-}
-// k_tie_delta's value is the data position; the fast path sends the filling index u through the partition instead
-__global__ void k_val_to_u(int D, const int *__restrict__ dfill, unsigned *val) {
-    const int d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d < D) { const unsigned v = val[d]; val[d] = (v & ~0x3ffffffu) | (unsigned)dfill[v & 0x3ffffffu]; }
 }
 // sorted order: one sector gather per position
 __global__ void k_records_fast(int D, const int *__restrict__ s_u, const int4 *__restrict__ REC, const int4 *__restrict__ RI, double overlap,
