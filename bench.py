@@ -235,7 +235,8 @@ def run_reference(args, rank):
 def hbm_stage_table(st, R):
     F, E, R1 = st["n_fillings"], st["relation_entries"], st["n_query_reads"]
     return [
-        ("sort", ["data_order_mask", "query_rank_read_lists", "chrom_sort"], 2 * 16 * F, "2*16*F: one read + one write of every 16-byte interval record"),
+        ("sort", ["keep_fillings", "data_order_mask", "query_rank_read_lists", "chrom_sort"], 2 * 16 * F,
+         "2*16*F: one read + one write of every 16-byte interval record (stages: keep_fillings + the sort by start + query rank + chromosome partition)"),
         ("band_bucket", ["records_bands"], 16 * F + 4 * F, "16*F + 4*F"),
         ("compaction", ["candidates"], 8 * E, "8*E written for E recorded pairs (here: the hit list written by k_hits)"),
         ("union_find", ["union_find"], 8 * E + 4 * R1 + 4 * R1, "8*E read + 4*R1 parent init + 4*R1 final labels"),
@@ -419,9 +420,13 @@ def main():
     for name, stages, nbytes, formula in hbm_stage_table(st, R):
         t_ms = sum(stage_ms[s] for s in stages)
         ach = nbytes / (t_ms * 1e-3) / 1e9 if t_ms > 0 else 0.0
+        tr = traffic.get(name)
+        if name == "sort" and tr is not None:
+            tr += traffic.get("keep_fillings", 0)
         stage_rooflines.append({"stage": name, "library_stages": stages, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "algorithmic_bytes": nbytes, "formula": formula, "ms": t_ms,
-                                "traffic": traffic.get(name)})
+                                "traffic": tr,       # DRAM bytes the stage really moved (ncu, per step): sort passes, permutation gathers
+                                "traffic_frac": (tr / (t_ms * 1e-3) / 1e9 / peak) if (tr and t_ms > 0) else None})
     # ---- the pair-test kernel against the integer-issue roofline: 12 + 7*L1*L2 lane-ops per evaluated read pair
     # against the measured dependent-free IADD/LOP/VIMNMX rate of this device
     roofline = None
