@@ -45,7 +45,7 @@ __device__ __forceinline__ int aux_size(unsigned char t) {
 }
 
 __global__ void k_bam_parse(const unsigned char *__restrict__ text, long long n_bytes, const long long *__restrict__ rec_off, int M,
-                            unsigned long long seed, Recs R, int *maxlen, int *err) {
+                            int n_ref, unsigned long long seed, Recs R, int *maxlen, int *err) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     int nl = 0, bad = 0;
     if (m < M) {
@@ -53,9 +53,11 @@ __global__ void k_bam_parse(const unsigned char *__restrict__ text, long long n_
         const unsigned char *p = text + o;
         const long long end = o + 4 + (long long)rd32(p);
         const int l_name = p[12], n_cig = rd16(p + 16), l_seq = rd32(p + 20);
-        const long long c0 = o + 36 + l_name, s0 = c0 + 4LL * n_cig, a0 = s0 + (l_seq + 1) / 2 + l_seq;
+        const long long c0 = o + 36 + l_name, s0 = c0 + 4LL * n_cig, a0 = s0 + ((long long)l_seq + 1) / 2 + (long long)l_seq;
         if (end > n_bytes || a0 > end || l_name < 1 || l_seq < 0) bad |= BE_TRUNC;
         R.flag[m] = rd16(p + 18); R.ref[m] = rd32(p + 4); R.mapq[m] = p[13];
+        // a mapped record (no flag 0x4) must name a reference of the header: its id indexes the chromosome tables downstream
+        if (!(rd16(p + 18) & 4) && (unsigned)rd32(p + 4) >= (unsigned)n_ref) bad |= BE_RANGE;
         const int pos = rd32(p + 8);
         R.pos1[m] = pos + 1;
         nl = l_name - 1;

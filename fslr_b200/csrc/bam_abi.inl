@@ -90,7 +90,7 @@ static int bam_build(fslrc_ctx *ctx, BamState *B, Pipe *P, const long long *rec_
     DA(err, 1); DA(dmax, 2); DA(dcount, 4);
     CK(cudaMemsetAsync(err, 0, sizeof(int), st)); CK(cudaMemsetAsync(dmax, 0, 2 * sizeof(int), st));
     CK(cudaMemsetAsync(dcount, 0, 4 * sizeof(int64_t), st));
-    KL(bam::k_bam_parse, nblk(M, TB), TB, B->text, (long long)n_bytes, rec_off, M, (unsigned long long)hash_seed, R, dmax, err);
+    KL(bam::k_bam_parse, nblk(M, TB), TB, B->text, (long long)n_bytes, rec_off, M, (int)n_ref, (unsigned long long)hash_seed, R, dmax, err);
     // ---- read ids in order of first appearance (the dict of :23-26), records grouped by read in file order
     int *rid; DA(rid, M);
     BPA(B->first_rec, M);
@@ -109,7 +109,7 @@ static int bam_build(fslrc_ctx *ctx, BamState *B, Pipe *P, const long long *rec_
         if ((e) & bam::BE_NOCIGAR) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: mapped record without CIGAR (collect_mapping_info.py:12)"); \
         if ((e) & bam::BE_AUX) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: malformed aux block or non-integer AS tag");           \
         if ((e) & bam::BE_NOAS) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: record without AS tag (collect_mapping_info.py:44,88)"); \
-        if ((e) & bam::BE_RANGE) return bam_fail(ctx, FSLRC_ERR_RANGE, "bam: coordinate or score beyond int32");                 \
+        if ((e) & bam::BE_RANGE) return bam_fail(ctx, FSLRC_ERR_RANGE, "bam: coordinate or score beyond int32, or a mapped record whose reference id is not in the header");                 \
         if ((e) & bam::BE_NOPRIMARY) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: read without a primary record (collect_mapping_info.py:46-48)"); \
         if ((e) & bam::BE_NOSEQ) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: primary record without sequence (collect_mapping_info.py:101-103)"); \
         if ((e) & bam::BE_NAME) return bam_fail(ctx, FSLRC_ERR_ARG, "bam: single-alignment read whose name does not end in <primer>_<primer> (collect_mapping_info.py:112-113)"); \

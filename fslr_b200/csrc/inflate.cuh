@@ -1,4 +1,4 @@
-// DEFLATE (RFC 1951) decoder for BGZF blocks, written against the RFC: one decoder instance per BGZF block (<= 64 KiB of
+// DEFLATE (RFC 1951) decoder for BGZF blocks, written against the RFC (Huffman helpers after puff.c, see below): one decoder instance per BGZF block (<= 64 KiB of
 // output), so a BAM file inflates block-parallel on the device and only the COMPRESSED bytes cross PCIe.
 // The decoder is a plain sequential function compiled for both host and device (FSLR_HD): the host build is what
 // tests/test_inflate_host.py checks against zlib on CPU; the device build runs one decoder per warp (lane 0 decodes,
@@ -40,7 +40,10 @@ FSLR_HD unsigned bits_get(Bits &b, int need) {          // need <= 16
     return v;
 }
 
-// canonical Huffman code: count[l] codes of length l, symbols ordered by (length, symbol value)
+// canonical Huffman code: count[l] codes of length l, symbols ordered by (length, symbol value).
+// huff_build / huff_decode follow the canonical-code construction and the bit-by-bit first-code-per-length decoder of
+// zlib's contrib/puff/puff.c (`construct` / `decode`, Mark Adler, zlib licence) — the textbook form of RFC 1951 3.2.2; the
+// table lookup for short codes, the warp-cooperative copies and the block driver around them are this file's own.
 struct Huff {
     unsigned short *count;         // [16]
     unsigned short *symbol;

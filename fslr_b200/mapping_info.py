@@ -165,6 +165,16 @@ class BamTable:
         self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=dev)
         self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=dev)
         self._names = None
+        # one table per library context (fslrc_bam_open frees the previous one): see ParsedBed
+        engine._bam_gen = getattr(engine, "_bam_gen", 0) + 1
+        self._gen = engine._bam_gen
+
+    def _live(self):
+        if self.engine is None:
+            raise RuntimeError("BamTable is closed")
+        if self._gen != self.engine._bam_gen:
+            raise RuntimeError("stale BamTable: a later read_bam_table() on this device replaced the table "
+                               "(the library context holds one at a time)")
 
     @property
     def n_chrom(self):
@@ -172,11 +182,13 @@ class BamTable:
 
     def column(self, name):
         """Host copy of one column (int32)."""
+        self._live()
         return self.columns[name].cpu().numpy()
 
     def _stream(self):
         """The inflated BAM stream on the host (fetched from the device when the file was inflated there)."""
         if self._data is None:
+            self._live()
             n = C.c_int64()
             self.engine._check(self.engine.lib.fslrc_bam_read_stream(self.engine.ctx, None, 0, C.byref(n)))
             self._data = np.empty(n.value, dtype=np.uint8)
@@ -211,6 +223,7 @@ class BamTable:
 
     def mappings_bed_bytes(self, fslr_version=None):
         """`<base>.mappings.bed` (collect_mapping_info.py:176-181) as bytes, rendered on the device."""
+        self._live()
         lib, ctx = self.engine.lib, self.engine.ctx
         ver = (fslr_version if fslr_version is not None else _default_version()).encode()
         names = b"".join(n.encode() + b"\x00" for n in self.chrom_names)
@@ -227,13 +240,15 @@ class BamTable:
     def cluster(self, cluster_mask="subtelomere", **options):
         """The clustering step (main.py:209-257,334-342) on the device-resident table, GPU stable tie order."""
         params = ClusterParams.from_options(self, cluster_mask=cluster_mask, **options)
+        self._live()
         stats = self.engine.run_resident(self, self, params)
         n = self.n_reads
         return ClusterResult(self.out_cluster[:n].cpu().numpy(), self.out_n_reads[:n].cpu().numpy(), bool(stats["no_clusters"]), stats)
 
     def close(self):
         if self.engine is not None:
-            self.engine.lib.fslrc_bam_close(self.engine.ctx)
+            if self._gen == self.engine._bam_gen:
+                self.engine.lib.fslrc_bam_close(self.engine.ctx)
             self.engine = None
 
 

@@ -37,6 +37,17 @@ class ParsedBed:
         self.out_cluster = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=dev)
         self.out_n_reads = torch.empty(max(self.n_reads, 1), dtype=torch.int32, device=dev)
         self._names = None
+        # the library context keeps ONE parsed table (fslrc_tsv_open frees the previous one): a later read_mappings_bed on the
+        # same engine invalidates this object, whose device columns would then point at freed memory
+        engine._tsv_gen = getattr(engine, "_tsv_gen", 0) + 1
+        self._gen = engine._tsv_gen
+
+    def _live(self):
+        if self.engine is None:
+            raise RuntimeError("ParsedBed is closed")
+        if self._gen != self.engine._tsv_gen:
+            raise RuntimeError("stale ParsedBed: a later read_mappings_bed() on this device replaced the parsed table "
+                               "(the library context holds one at a time)")
 
     @property
     def n_chrom(self):
@@ -44,12 +55,14 @@ class ParsedBed:
 
     def column(self, name):
         """Host copy of one parsed column (int32)."""
+        self._live()
         t = self.alignment_score if name == "alignment_score" else self.cols[name]
         return t.cpu().numpy()
 
     def qnames(self):
         """qname of every read id (order of first appearance), sliced out of the file bytes on the host."""
         if self._names is None:
+            self._live()
             off = np.zeros(max(self.n_reads, 1), dtype=np.int64)
             ln = np.zeros(max(self.n_reads, 1), dtype=np.int32)
             self.engine._check(self.engine.lib.fslrc_tsv_read_names(self.engine.ctx, off.ctypes.data, ln.ctypes.data))
@@ -60,13 +73,17 @@ class ParsedBed:
     def cluster(self, cluster_mask="subtelomere", **options):
         """The clustering step on the device-resident table (GPU stable tie order).  Returns ClusterResult; the per-read
         result also stays on the device (out_cluster / out_n_reads) for write_cluster_bed."""
+        self._live()
         params = ClusterParams.from_options(self, cluster_mask=cluster_mask, **options)
         stats = self.engine.run_resident(self, self, params)
         n = self.n_reads
         return ClusterResult(self.out_cluster[:n].cpu().numpy(), self.out_n_reads[:n].cpu().numpy(), bool(stats["no_clusters"]), stats)
 
     def cluster_bed_bytes(self):
-        """`<base>.mappings.cluster.bed` (main.py:349) as bytes, rendered on the device from out_cluster / out_n_reads."""
+        """`<base>.mappings.cluster.bed` (main.py:349) as bytes, rendered on the device from out_cluster / out_n_reads.  The
+        returned array is a VIEW of the engine's reused pinned staging buffer: valid until the next rendering call of any
+        table on this engine (copy it, or write it out, before that)."""
+        self._live()
         lib, ctx = self.engine.lib, self.engine.ctx
         stream = C.c_void_p(torch.cuda.current_stream(self.engine.device).cuda_stream)
         n = C.c_int64()
@@ -82,7 +99,8 @@ class ParsedBed:
 
     def close(self):
         if self.engine is not None:
-            self.engine.lib.fslrc_tsv_close(self.engine.ctx)
+            if self._gen == self.engine._tsv_gen:             # (a stale object owns nothing any more)
+                self.engine.lib.fslrc_tsv_close(self.engine.ctx)
             self.engine = None
 
 

@@ -59,6 +59,7 @@ def error_cases():
         "err_unknown_primer": [ok, ("r.1.9z9F_False", 0, 0, 100, 60, [(M, 40)], seq, [("AS", "C", 5)])],
         "err_no_cigar": [ok, ("r.1.False_False", 0, 0, 100, 60, [], seq, [("AS", "C", 5)])],
         "err_empty": [("r.1.False_False", 4, -1, -1, 0, [], seq, [])],
+        "err_bad_refid": [ok, ("r.1.False_False", 0, 1000, 100, 60, [(M, 40)], seq, [("AS", "C", 5)])],   # mapped, but no such reference
     }
 
 

@@ -64,3 +64,24 @@ def test_malformed_inputs():
     no_trailing_newline = tsv.read_mappings_bed(raw.rstrip(b"\n"), lens)
     assert no_trailing_newline.n_rows == len(lines) - 2
     no_trailing_newline.close()
+
+
+def test_a_second_parse_invalidates_the_first_handle():
+    """The library context holds ONE parsed table: an older ParsedBed must refuse to be used (its device columns are freed)
+    and closing it must not free the newer table."""
+    from fslr_b200 import tsv
+    raw1, lens = _bed_bytes("C1", 0.2)
+    raw2, _ = _bed_bytes("C1", 0.3)
+    pb1 = tsv.read_mappings_bed(raw1, lens)
+    pb2 = tsv.read_mappings_bed(raw2, lens)
+    with pytest.raises(RuntimeError, match="stale"):
+        pb1.column("rstart")
+    with pytest.raises(RuntimeError, match="stale"):
+        pb1.cluster()
+    pb1.close()                                                          # must not touch pb2's table
+    res = pb2.cluster()
+    assert res.cluster.shape[0] == pb2.n_reads
+    assert pb2.cluster_bed_bytes().tobytes().startswith(raw2[:raw2.index(b"\n")])
+    pb2.close()
+    with pytest.raises(RuntimeError, match="closed"):
+        pb2.column("rstart")
