@@ -143,11 +143,14 @@ __device__ __forceinline__ int gmax8(unsigned gmask, int v) { return __reduce_ma
 #ifndef RG_MINB
 #define RG_MINB 10              // resident blocks per SM the LIST-only instantiation is compiled for (registers <= 65536 / (64 * RG_MINB))
 #endif
+#ifndef RG_MINB_WALK
+#define RG_MINB_WALK 6          // ... and the instantiation with the band-walking code (wide skip steps: 32 loads per lane in flight)
+#endif
 #ifndef RG_REC
 #define RG_REC 16               // reads a group remembers the final stops of (direct mapped by rank)
 #endif
 template <bool ALLMATCH, bool WALK>
-__global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
+__global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) k_replay(Tab t, const UmaxTab um, int nP, const int *__restrict__ plist, int nRuns,
                                                            const int *__restrict__ rstart, const int *__restrict__ isP,
                                                            const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                            int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
@@ -195,24 +198,32 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                 const int src = sel * 8, wgrp = w * 4 + sel;
                 const int wa = __shfl_sync(FULL, a, src), wlo = __shfl_sync(FULL, lo, src), wbase = __shfl_sync(FULL, base, src);
                 const int wposf = __shfl_sync(FULL, posf, src), wLa = __shfl_sync(FULL, La, src), wfy = __shfl_sync(FULL, f.y, src);
-                if (!(wbase < wlo || __ldg(&t.pmaxS[wbase]) < wfy)) {
-                    int wq[8], we[8], ws[8];
+                if (wbase >= wlo) {
+                    // one round trip for everything a position can say by itself: its record, its own stop, where its read's other
+                    // filling sits — and the prefix max that tells whether anything at or below wbase still overlaps the filling
+                    const int pmx = __ldg(&t.pmaxS[wbase]);
+                    const bool sibs = t.sib && wLa <= 4;
+                    int wq[8], we[8], ws[8], wv[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const int p = wbase - 32 * k - lane;
-                        wq[k] = -1; we[k] = 0; ws[k] = 0;
-                        if (p >= wlo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
+                        wq[k] = -1; we[k] = 0; ws[k] = 0; wv[k] = 0;
+                        if (p >= wlo) {
+                            const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]);
+                            if (sibs) wv[k] = __ldg(&t.sib[p]);
+                        }
                     }
+                    if (pmx < wfy) { if ((lane >> 3) == sel) wide = false; continue; }     // the walk is over: the normal path closes it
                     bool needs[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++)
                         needs[k] = wq[k] >= 0 && wq[k] != wa && we[k] >= wfy && !(wq[k] < wa && stop_reached(ws[k]) <= wposf);
-                    if (t.sib && wLa <= 4) {
+                    if (sibs) {
                         int sp[8];
 #pragma unroll
                         for (int k = 0; k < 8; k++) {
                             sp[k] = -1;
-                            if (needs[k] && wq[k] < wa) { const int sv = __ldg(&t.sib[wbase - 32 * k - lane]); if (((unsigned)sv >> 26) == 1u) sp[k] = sv & QMASK; }
+                            if (needs[k] && wq[k] < wa && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
                         }
                         int cs[8], ce[8], cv[8];
 #pragma unroll
@@ -466,23 +477,27 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? 8 : RG_MINB) k_replay(Ta
                 // ---- nothing to do in the last step: skip ahead over candidates that are no candidates at all or whose read
                 // provably saw a first (its scan of this very interval already passed a's filling), 64 positions per step
                 int adv = 64;
-                int wq[8], we[8], ws[8];                                           // all 16 loads of the step are issued before any use
+                const bool sibs = t.sib && La <= 4;
+                int wq[8], we[8], ws[8], wv[8];                                    // all 24 loads of the step are issued before any use
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const int p = base - 8 * k - gl;
-                    wq[k] = -1; we[k] = 0; ws[k] = 0;
-                    if (p >= lo) { const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]); }
+                    wq[k] = -1; we[k] = 0; ws[k] = 0; wv[k] = 0;
+                    if (p >= lo) {
+                        const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]);
+                        if (sibs) wv[k] = __ldg(&t.sib[p]);
+                    }
                 }
                 bool needs[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     needs[k] = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
-                if (t.sib && La <= 4) {                                            // ... or through its other filling (reads of 2 fillings:
+                if (sibs) {                                                        // ... or through its other filling (reads of 2 fillings:
                     int sp[8];                                                     //     the loads of all 8 positions are batched)
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         sp[k] = -1;
-                        if (needs[k] && wq[k] < a) { const int sv = __ldg(&t.sib[base - 8 * k - gl]); if (((unsigned)sv >> 26) == 1u) sp[k] = sv & QMASK; }
+                        if (needs[k] && wq[k] < a && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
                     }
                     int cs[8], ce[8], cv[8];
 #pragma unroll
