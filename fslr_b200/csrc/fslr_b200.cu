@@ -313,7 +313,6 @@ static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, co
         long long mx = 0; bool known = pr.n_chrom > 0;
         for (int c = 0; c < pr.n_chrom; c++) { if (pr.chrom_len[c] <= 0) known = false; mx = std::max<long long>(mx, pr.chrom_len[c]); }
         kbits = (known && mx < 0x7fffffffLL) ? std::min(32, bits_for(mx + 2)) : 32;
-        KL(k_fi_fast, nblk(D, TB), TB, D, REC, P->err);
         int r = sort_pairs(ctx, P, key, key2, val, dfill, D, 0, kbits); if (r) return r;
         KL(k_items_fast, nblk(D, TB), TB, D, dfill, REC, IT0, ITn, flag64);
         DA(tkey, D); DA(tval, D);

@@ -366,12 +366,29 @@ __global__ void k_compact_fast(int A, const int *__restrict__ flag, const int *_
     int s = 0;
     if (i < A && flag[i]) {
         const int u = pos[i];
-        const int rs = rstart[i], re = rend[i], a = aln[i], na = naln[i];
+        const int r = rid[i], rs = rstart[i], re = rend[i], a = aln[i], na = naln[i];
         s = min(rs, re);
         if (a <= 0 || na <= 0) atomicOr(err, EF_ZERO);
         if (na >= 65535) atomicOr(err, EF_RANGE);
-        REC[2 * u] = make_int4(rid[i], chrom[i], s, max(rs, re));
-        REC[2 * u + 1] = make_int4(a, na, 0, 0);
+        // Data order = the stable sort of the unmasked fillings by start, so two fillings of a read compare in data order like
+        // (start, row): the index fi of this filling among its read's fillings in data order, and the read's filling count L,
+        // are known here, before the sort, from the neighbouring rows of the table (the read's rows are contiguous).
+        int fi = 0, L = 1;
+        bool over = false;
+        for (int j = i - 1; j >= 0 && rid[j] == r; j--) {
+            if (!flag[j]) continue;
+            if (++L > LMAX) { over = true; break; }
+            fi += min(rstart[j], rend[j]) <= s;                                     // (start', row') < (start, row) with row' < row
+            if (naln[j] != na) atomicOr(err, EF_NALN);                              // n_alignments constant over a read's rows
+        }
+        for (int j = i + 1; !over && j < A && rid[j] == r; j++) {
+            if (!flag[j]) continue;
+            if (++L > LMAX) { over = true; break; }
+            fi += min(rstart[j], rend[j]) < s;
+        }
+        if (over) { atomicOr(err, EF_TOOMANY); L = LMAX; fi &= 63; }
+        REC[2 * u] = make_int4(r, chrom[i], s, max(rs, re));
+        REC[2 * u + 1] = make_int4(a, na, fi, L);                                   // .zw = {fi, L} until k_assign_fast overwrites them
         key[u] = (unsigned)s; val[u] = u;
     }
     __shared__ int s_max;                                                           // one atomic per block, and only when it can matter
@@ -381,32 +398,6 @@ __global__ void k_compact_fast(int A, const int *__restrict__ flag, const int *_
     if ((threadIdx.x & 31) == 0 && s > 0) atomicMax(&s_max, s);
     __syncthreads();
     if (threadIdx.x == 0 && (unsigned long long)s_max > *(volatile unsigned long long *)max_start) atomicMax(max_start, (unsigned long long)s_max);
-}
-// Data order = the stable sort of the fillings by start, so two fillings of a read compare in data order like (start, u):
-// the index fi of a filling among its read's fillings in data order, and the read's filling count L, are known BEFORE the sort
-// from the neighbouring records in bed order (coalesced).  Kept in REC[2u+1].zw = {fi, L} until k_assign_fast overwrites them.
-__global__ void k_fi_fast(int D, int4 *REC, int *err) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= D) return;
-    const int4 r0 = REC[2 * u];
-    int fi = 0, L = 1;
-    bool over = false;
-    for (int k = u - 1; k >= 0; k--) {
-        const int4 o = REC[2 * k];
-        if (o.x != r0.x) break;
-        if (++L > LMAX) { over = true; break; }
-        fi += o.z <= r0.z;                                                          // (start', u') < (start, u) with u' < u
-        if (k == u - 1 && REC[2 * k + 1].y != REC[2 * u + 1].y) atomicOr(err, EF_NALN);   // n_alignments constant over a read's rows
-    }
-    for (int k = u + 1; !over && k < D; k++) {
-        const int4 o = REC[2 * k];
-        if (o.x != r0.x) break;
-        if (++L > LMAX) { over = true; break; }
-        fi += o.z < r0.z;                                                           // u' > u
-    }
-    if (over) { atomicOr(err, EF_TOOMANY); L = LMAX; fi &= 63; }
-    int2 *zw = (int2 *)&REC[2 * u + 1] + 1;
-    *zw = make_int2(fi, L);
 }
 // per data position d (filling u = dfill[d]): the filling's record, gathered as one sector, written out coalesced;
 // flag64[d] = (1 << 32 | L) when the filling is its read's first item in data order (fi == 0), else 0
