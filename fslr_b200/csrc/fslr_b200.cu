@@ -560,9 +560,10 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     { int r = mark(ctx, ST_SAT); if (r) return r; }
     // a saturating read adds at most edge_threshold edges in the scan that reaches the threshold and one per later filling
     const int replay_blocks_max = n_sms(ctx) * 16;
+    const int list_blocks_max = n_sms(ctx) * resident_blocks(k_replay_list, RL_WARPS * 32);
     unsigned long long capp = (unsigned long long)nP * ((unsigned long long)std::max(P->Tedge, 0) + LMAX) + 64;
     unsigned long long alt = 2ull * (unsigned long long)ctx->h_pin[3] + 64;
-    P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * RG_GROUPS * (replay_blocks_max + 1);
+    P->cap_pedges = std::min(capp, alt) + (unsigned long long)RP_CHUNK * std::max(RG_GROUPS * (replay_blocks_max + 1), RL_WARPS * (list_blocks_max + 1));
     DA(P->pedges, P->cap_pedges);
     if (nP > 0) {
         int *sflag, *spos, *sstart, *rflag, *rpos, *rstart;
@@ -586,7 +587,9 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
                     (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16)
         if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (walk) KL((k_replay<false, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
-        else KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
+        else if (getenv("FSLRC_REPLAY_GROUPS")) KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
+        else KL(k_replay_list, std::min(nblk(nRuns, RL_WARPS), list_blocks_max), RL_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo,
+                P->stop, P->stopS, P->ticket, P->pedges, (unsigned long long *)(P->cnt + 7), P->cap_pedges, P->err, (unsigned long long *)(P->cnt + 16));
 #undef REPLAY_ARGS
     }
     { int r = mark(ctx, ST_REPLAY); if (r) return r; }

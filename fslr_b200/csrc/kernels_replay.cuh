@@ -665,3 +665,151 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                                    d_stall += __shfl_down_sync(FULL, d_stall, o); d_sleep += __shfl_down_sync(FULL, d_sleep, o); }
     if (lane == 0 && dbg) { atomicAdd(dbg, d_iter); atomicAdd(dbg + 1, d_steps); atomicAdd(dbg + 2, d_stall); atomicAdd(dbg + 3, d_sleep); }
 }
+
+// ---------------------------------------------------------------- LIST-only replay, one WARP per read
+// Used when every saturating read has partner records (no WALK read in the table, --overlap > 0): the same state machine as
+// k_replay's LIST mode — runs by ticket, one filling's scan per step, non-blocking retry on stops that are not published yet
+// — but a whole warp replays one read with ONE partner per lane (two for reads with 33..64 partners), all in registers.
+// Every branch is warp-uniform: nothing serialises inside a warp (k_replay's four 8-lane groups run their phases one after the
+// other, 15 of 32 lanes active), the break is a handful of warp-wide REDUX rounds, edges leave through one ballot.
+#define RL_WARPS 2
+#define RL_SLOTS ((RP_K + 31) / 32)
+__global__ void __launch_bounds__(RL_WARPS * 32, 16) k_replay_list(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+                                                                  const int *__restrict__ rstart, const int *__restrict__ isP,
+                                                                  const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
+                                                                  int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
+                                                                  unsigned long long cap_pedges, int *err, unsigned long long *dbg) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+    unsigned tk = 0, tk1 = 0;
+    unsigned long long chunk_base = 0, d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
+    int chunk_used = RP_CHUNK;                                                     // nothing reserved yet
+    for (;;) {
+        // ---- next read of the run (or the next run)
+        if (tk == tk1) {
+            unsigned run = 0;
+            if (lane == 0) run = atomicAdd(ticket, 1u);
+            run = __shfl_sync(FULL, run, 0);
+            if (run >= (unsigned)nRuns) break;
+            tk = (unsigned)__ldg(&rstart[run]);
+            tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
+        }
+        const int a = __ldg(&plist[tk]);
+        const int wa = __ldg(&t.RI[a]).w;
+        const PLInfo pi = plinfo[a];
+        const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1;
+        if (pi.n < 0 || pi.n > RP_K || La > 4) { if (lane == 0) atomicOr(err, EF_OVERFLOW); break; }   // (cannot happen: the host picks k_replay then)
+        // lanes 0..La-1 hold a's fillings: chromosome (for the scan's lower end) and {pos, ub}
+        int myc = 0, mypos = 0;
+        if (lane < La) { myc = rm0(t, offa + lane).x; mypos = rm1(t, offa + lane).x; }
+        int posA[4], loA[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) { posA[g] = __shfl_sync(FULL, mypos, g); loA[g] = __shfl_sync(FULL, myc, g); }
+        if (lane < La) myc = __ldg(&t.chrom_lo[myc]);
+#pragma unroll
+        for (int g = 0; g < 4; g++) loA[g] = __shfl_sync(FULL, myc, g);
+        // one partner per lane and slot: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}, {key[0..3]}
+        int4 p0[RL_SLOTS], p1[RL_SLOTS];
+#pragma unroll
+        for (int s = 0; s < RL_SLOTS; s++) {
+            const int j = s * 32 + lane;
+            p0[s] = make_int4(0, 0, 0, 1); p1[s] = make_int4(-1, -1, -1, -1);      // (no partner: "visited", never met)
+            if (j < pi.n) { p0[s] = __ldg(&PL[2 * (pi.off + j)]); p1[s] = __ldg(&PL[2 * (pi.off + j) + 1]); }
+        }
+#pragma unroll
+        for (int s = 0; s < RL_SLOTS; s++) {
+            const int j = s * 32 + lane;
+            if (j < pi.n) { const int b = p0[s].x & QMASK; p0[s].w = (b < a && !__ldg(&isP[b])) ? 1 : 0; }   // b < a and never breaking: it saw the pair
+        }
+        int edges = 0;
+        for (int fi = 0; fi < La;) {                                               // one filling's scan per step (retried while it depends on
+            d_iter += lane == 0;                                                   //  a stop that is not published yet)
+            // where does the scan first meet each partner; did an earlier-ranked partner's own query see a first?
+            int key[RL_SLOTS], ekey[RL_SLOTS];
+            int mxReach = -1, mxUn = -1, nEdge = 0;
+#pragma unroll
+            for (int s = 0; s < RL_SLOTS; s++) {
+                key[s] = -1; ekey[s] = -1;
+                if (!(p0[s].w & 1)) key[s] = fi == 0 ? p1[s].x : fi == 1 ? p1[s].y : fi == 2 ? p1[s].z : p1[s].w;
+                const int b = p0[s].x & QMASK;
+                if (key[s] >= 0 && b < a && !(p0[s].w & 12)) {                      // ask b's stops
+                    const int offb = (int)((unsigned)p0[s].y >> 6), Lb = (p0[s].y & 63) + 1;
+                    int sv[4];
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        sv[g] = (g < Lb && (((unsigned)p0[s].z >> (4 * g)) & 4u)) ? ld_relaxed(&stop[offb + g]) : 0x7fffffff;
+                    bool vis = false, unres = false;
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const unsigned cgg = ((unsigned)p0[s].z >> (4 * g)) & 15u;
+                        if (cgg & 4u) {
+                            const int pa = (cgg & 3u) == 0 ? posA[0] : (cgg & 3u) == 1 ? posA[1] : (cgg & 3u) == 2 ? posA[2] : posA[3];
+                            if (stop_reached(sv[g]) <= pa) vis = true; else if (sv[g] < 0) unres = true;
+                        }
+                    }
+                    if (vis) p0[s].w |= 4; else if (!unres) p0[s].w |= 8;
+                }
+                if (key[s] >= 0) {
+                    if (b > a || (p0[s].w & 8)) {
+                        mxReach = max(mxReach, key[s]);
+                        if (p0[s].x < 0) { nEdge++; ekey[s] = key[s]; }
+                    } else if (!(p0[s].w & 4)) mxUn = max(mxUn, key[s]);
+                }
+            }
+            // the break (cluster.py:223-224): the first reached partner, in scan order, at which `edges` is >= edge_threshold
+            const int need = t.Tedge - edges;
+            int brkkey = -1;
+            if (need <= 0) brkkey = __reduce_max_sync(FULL, mxReach);
+            else if (__reduce_add_sync(FULL, nEdge) >= need) {                     // the need-th highest edge partner
+                int thr = 0x7fffffff;
+                for (int r = 0; r < need; r++) {
+                    int m = -1;
+#pragma unroll
+                    for (int s = 0; s < RL_SLOTS; s++) if (ekey[s] < thr) m = max(m, ekey[s]);
+                    thr = __reduce_max_sync(FULL, m);
+                }
+                brkkey = thr;
+            }
+            const int unkey = __reduce_max_sync(FULL, mxUn);
+            d_steps += lane == 0;
+            if (unkey > brkkey) {                                                  // an undecided partner comes first: retry
+                d_stall += lane == 0; d_sleep += lane == 0;
+                __nanosleep(100);
+                continue;
+            }
+            // commit: everything met at or above the break has now been seen by a's query
+#pragma unroll
+            for (int s = 0; s < RL_SLOTS; s++) {
+                bool emit = false;
+                if (key[s] >= 0 && key[s] >= brkkey) {
+                    emit = p0[s].x < 0 && ((p0[s].x & QMASK) > a || (p0[s].w & 8));
+                    p0[s].w |= 1;
+                }
+                const unsigned em = __ballot_sync(FULL, emit);
+                if (em) {
+                    const int n = __popc(em);
+                    if (chunk_used + n > RP_CHUNK) {                               // reserve a fresh chunk, pad the old one
+                        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
+                        if (lane == 0) chunk_base = atomicAdd(n_slots, (unsigned long long)RP_CHUNK);
+                        chunk_base = __shfl_sync(FULL, chunk_base, 0);
+                        chunk_used = 0;
+                        if (chunk_base + RP_CHUNK > cap_pedges) { if (lane == 0) atomicOr(err, EF_OVERFLOW); chunk_base = 0; }
+                    }
+                    if (emit) pedges[chunk_base + chunk_used + __popc(em & ltmask)] = make_int2(a, p0[s].x & QMASK);
+                    chunk_used += n;
+                    edges += n;
+                }
+            }
+            const int lof = fi == 0 ? loA[0] : fi == 1 ? loA[1] : fi == 2 ? loA[2] : loA[3];
+            const int posf = fi == 0 ? posA[0] : fi == 1 ? posA[1] : fi == 2 ? posA[2] : posA[3];
+            const int stopf = brkkey >= 0 ? brkkey : lof;
+            if (lane == 0) { st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf); }
+            fi++;
+        }
+        tk++;
+    }
+    if (chunk_used < RP_CHUNK)
+        for (int k = chunk_used + lane; k < RP_CHUNK; k += 32) pedges[chunk_base + k] = make_int2(-1, -1);
+    if (lane == 0 && dbg) { atomicAdd(dbg, d_iter); atomicAdd(dbg + 1, d_steps); atomicAdd(dbg + 2, d_stall); atomicAdd(dbg + 3, d_sleep); }
+}
