@@ -731,6 +731,7 @@ __global__ void __launch_bounds__(RL_WARPS * 32, 16) k_replay_list(Tab t, int nP
 #pragma unroll
             for (int s = 0; s < RL_SLOTS; s++) {
                 key[s] = -1; ekey[s] = -1;
+                if (s * 32 >= pi.n) continue;                                       // (warp-uniform: most reads have <= 32 partners)
                 if (!(p0[s].w & 1)) key[s] = fi == 0 ? p1[s].x : fi == 1 ? p1[s].y : fi == 2 ? p1[s].z : p1[s].w;
                 const int b = p0[s].x & QMASK;
                 if (key[s] >= 0 && b < a && !(p0[s].w & 12)) {                      // ask b's stops
@@ -781,6 +782,7 @@ __global__ void __launch_bounds__(RL_WARPS * 32, 16) k_replay_list(Tab t, int nP
             // commit: everything met at or above the break has now been seen by a's query
 #pragma unroll
             for (int s = 0; s < RL_SLOTS; s++) {
+                if (s * 32 >= pi.n) continue;
                 bool emit = false;
                 if (key[s] >= 0 && key[s] >= brkkey) {
                     emit = p0[s].x < 0 && ((p0[s].x & QMASK) > a || (p0[s].w & 8));
