@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int
 
 // One lane per hit.  La <= 4 always (light reads); partners with more than 4 fillings take the loop over global lists.
 #define EV_THREADS 256
-__global__ void __launch_bounds__(EV_THREADS, 4) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
+#ifndef EV_MINB
+#define EV_MINB 4
+#endif
+__global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
                                                      unsigned long long cap, unsigned *cp, unsigned long long *n_tests,
                                                      unsigned long long *n_real) {
     __shared__ int s_umax[LMAX + 1];
@@ -240,7 +243,10 @@ __global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__re
 }
 // One lane per recorded pair: the partner record of saturating read a about partner b (see PLInfo / k_pair for the fields)
 #define PLT_THREADS 256
-__global__ void __launch_bounds__(PLT_THREADS) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
+#ifndef PLT_MINB
+#define PLT_MINB 5
+#endif
+__global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
                                                        unsigned long long n_fixed, unsigned long long cap,
                                                        const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
     unsigned long long n = n_slots ? *n_slots : n_fixed;
