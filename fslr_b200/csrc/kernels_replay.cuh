@@ -674,7 +674,10 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
 // other, 15 of 32 lanes active), the break is a handful of warp-wide REDUX rounds, edges leave through one ballot.
 #define RL_WARPS 2
 #define RL_SLOTS ((RP_K + 31) / 32)
-__global__ void __launch_bounds__(RL_WARPS * 32, 16) k_replay_list(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+#ifndef RL_MINB
+#define RL_MINB 24              // 48 warps per SM at 40 registers (a few spilled words) beat 32 warps at 62: measured 1.21 vs 1.34 ms
+#endif
+__global__ void __launch_bounds__(RL_WARPS * 32, RL_MINB) k_replay_list(Tab t, int nP, const int *__restrict__ plist, int nRuns,
                                                                   const int *__restrict__ rstart, const int *__restrict__ isP,
                                                                   const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                                   int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
@@ -703,12 +706,10 @@ __global__ void __launch_bounds__(RL_WARPS * 32, 16) k_replay_list(Tab t, int nP
         // lanes 0..La-1 hold a's fillings: chromosome (for the scan's lower end) and {pos, ub}
         int myc = 0, mypos = 0;
         if (lane < La) { myc = rm0(t, offa + lane).x; mypos = rm1(t, offa + lane).x; }
+        if (lane < La) myc = __ldg(&t.chrom_lo[myc]);
         int posA[4], loA[4];
 #pragma unroll
         for (int g = 0; g < 4; g++) { posA[g] = __shfl_sync(FULL, mypos, g); loA[g] = __shfl_sync(FULL, myc, g); }
-        if (lane < La) myc = __ldg(&t.chrom_lo[myc]);
-#pragma unroll
-        for (int g = 0; g < 4; g++) loA[g] = __shfl_sync(FULL, myc, g);
         // one partner per lane and slot: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}, {key[0..3]}
         int4 p0[RL_SLOTS], p1[RL_SLOTS];
 #pragma unroll
