@@ -600,7 +600,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, TB * UE_PER), TB, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
+    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, UE_THREADS * UE_PER), UE_THREADS, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
                                                                            (unsigned long long *)(P->cnt + 8));
     // replayed edges are identical on every rank; rank 0 contributes them once
     if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));

@@ -25,23 +25,45 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 // b > a -> a tested it (edge); b < a -> edge only if b is saturating and its scan stopped before reaching a (then a's
 // query tested the pair, direction a -> b)
 #define UE_PER 4
-__global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP, Tab t,
-                                const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
-    const unsigned long long k0 = (unsigned long long)blockIdx.x * (blockDim.x * UE_PER) + threadIdx.x;
+#define UE_THREADS 256
+// Only about a third of the list's slots are edges (the rest: padding, pairs of saturating reads, pairs that do not pass), and
+// union-find is pointer chasing: what counts is how many chases are in flight.  Every block filters its 1024 slots (entry and
+// isP loads batched), compacts the survivors in shared memory and walks them with all lanes busy.
+__global__ void __launch_bounds__(UE_THREADS) k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP,
+                                                              Tab t, const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
+    __shared__ int2 sE[UE_THREADS * UE_PER];
+    __shared__ int s_warp[UE_THREADS / 32];
+    __shared__ int s_ne;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long k0 = (unsigned long long)blockIdx.x * (UE_THREADS * UE_PER) + tid;
+    if (tid == 0) s_ne = 0;
     int2 ab[UE_PER];
     int pa[UE_PER];
-    int ne = 0;
 #pragma unroll
     for (int u = 0; u < UE_PER; u++) {                                              // all entries, then all flags: loads in flight together
-        const unsigned long long k = k0 + (unsigned long long)u * blockDim.x;
+        const unsigned long long k = k0 + (unsigned long long)u * UE_THREADS;
         ab[u] = k < n ? __ldg(&entries[k]) : make_int2(-1, -1);
     }
 #pragma unroll
     for (int u = 0; u < UE_PER; u++) pa[u] = (ab[u].x >= 0 && ab[u].y >= 0) ? __ldg(&isP[ab[u].x]) : 1;   // (y < 0: the pair does not pass)
+    int mine = 0;
 #pragma unroll
-    for (int u = 0; u < UE_PER; u++) {
-        if (pa[u]) continue;
-        const int a = ab[u].x, b = ab[u].y & QMASK;                                 // y: b | EB_NOPASS | EB_HEAVY
+    for (int u = 0; u < UE_PER; u++) mine += !pa[u];
+    int incl = mine;                                                                // block-wide exclusive scan of the survivor counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < UE_THREADS / 32; w++) { const int c = s_warp[w]; if (w < warp) wbase += c; total += c; }
+    int at = wbase + incl - mine;
+#pragma unroll
+    for (int u = 0; u < UE_PER; u++) if (!pa[u]) sE[at++] = make_int2(ab[u].x, ab[u].y & QMASK);   // y: b | EB_NOPASS | EB_HEAVY
+    __syncthreads();
+    int ne = 0;
+    for (int idx = tid; idx < total; idx += UE_THREADS) {
+        const int a = sE[idx].x, b = sE[idx].y;
         bool e = true;
         if (b < a) {
             e = false;
@@ -63,12 +85,9 @@ __global__ void k_union_entries(unsigned long long n, const int2 *__restrict__ e
         if (e) { ing[a] = 1; ing[b] = 1; uf_union(parent, a, b); ne++; }
     }
     for (int o = 16; o; o >>= 1) ne += __shfl_down_sync(0xffffffffu, ne, o);
-    __shared__ int s_ne;
-    if (threadIdx.x == 0) s_ne = 0;
+    if (lane == 0 && ne) atomicAdd(&s_ne, ne);
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && ne) atomicAdd(&s_ne, ne);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_ne) atomicAdd(n_edges, (unsigned long long)s_ne);    // one counter update per block
+    if (tid == 0 && s_ne) atomicAdd(n_edges, (unsigned long long)s_ne);             // one counter update per block
 }
 __global__ void k_union_edges(unsigned long long n, const int2 *__restrict__ edges, int *parent, int *ing, unsigned long long *n_edges) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
