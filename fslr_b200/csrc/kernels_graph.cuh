@@ -30,7 +30,9 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 // union-find is pointer chasing: what counts is how many chases are in flight.  Every block filters its 1024 slots (entry and
 // isP loads batched), compacts the survivors in shared memory and walks them with all lanes busy.
 __global__ void __launch_bounds__(UE_THREADS) k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP,
-                                                              Tab t, const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
+                                                              Tab t, const int *stop, int *parent, int *ing, unsigned long long *n_edges,
+                                                              const unsigned *__restrict__ only_if_zero) {
+    if (only_if_zero && *only_if_zero != 0) return;                                // (the reverse list exists in symmetric mode only)
     __shared__ int2 sE[UE_THREADS * UE_PER];
     __shared__ int s_warp[UE_THREADS / 32];
     __shared__ int s_ne;

@@ -38,8 +38,12 @@ __global__ void k_heavy_list(Tab t, const int *__restrict__ rclass, int *heavy_l
 // groups, round robin over ranks: consecutive ranks = usually one PCR family stay on one rank).
 // The tight bands of a read's (<= 4) fillings are walked as ONE concatenated list of (filling, position) pairs, 8 per step:
 // no per-filling loop, and the lanes of a group stay busy whatever the individual band lengths are.
-__global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass, int2 *hits,
+// Symmetric mode (no heavy read in the table, *n_heavy == 0): a pair {a, b} is listed only from its lower-ranked read; k_eval
+// derives BOTH directed tests from the one match matrix (b -> a is its transpose), so half the hits, half the evaluations.
+__global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int nshard, const int *__restrict__ rclass,
+                                                           const unsigned *__restrict__ n_heavy, int2 *hits,
                                                            unsigned long long *n_slots, unsigned long long cap, int *err) {
+    const bool sym = *n_heavy == 0;
     __shared__ int2 sHash[HK_GROUPS][HK_HASH];                                     // {b, q}: partner b was hit during read q's scan ...
     __shared__ int sHkey[HK_GROUPS][HK_HASH];                                      // ... at filling pair fa << 6 | fb (the lowest listed so far)
     __shared__ int4 sF[HK_GROUPS][4];                                              // the read's fillings {chrom, start, end, T}
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int
             }
             const int4 ff = sF[grp][fi];
             const int b = c0.w & QMASK;
-            bool hit = v && b != q && (min(ff.z, c0.y) - max(ff.y, c0.x)) >= max(ff.w, c0.z);   // cluster.py:157, T >= 1
+            bool hit = v && (sym ? b > q : b != q) && (min(ff.z, c0.y) - max(ff.y, c0.x)) >= max(ff.w, c0.z);   // cluster.py:157, T >= 1
             if (hit) {                                                              // a filter only: k_eval's canonical rule is exact
                 const int slot = b & (HK_HASH - 1), key = (fi << 6) | (int)((unsigned)c0.w >> 26);
                 const int2 h = sHash[grp][slot];
@@ -120,9 +124,10 @@ __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int
 #ifndef EV_MINB
 #define EV_MINB 4
 #endif
-__global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned long long *n_slots,
-                                                     unsigned long long cap, unsigned *cp, unsigned long long *n_tests,
-                                                     unsigned long long *n_real) {
+__global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxTab um, int2 *hits, int2 *rev, const unsigned *__restrict__ n_heavy,
+                                                     const unsigned long long *n_slots, unsigned long long cap, unsigned *cp,
+                                                     unsigned long long *n_tests, unsigned long long *n_real) {
+    const bool sym = *n_heavy == 0;                                                // symmetric mode: slot i also yields rev[i] = (b, a | flags)
     __shared__ int s_umax[LMAX + 1];
     for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
     __syncthreads();
@@ -197,14 +202,28 @@ __global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxT
             }
             if (canon) atomicOr(&cp[q], CP_LONG);                                   // the replay has to WALK this read
         }
-        int2 e = make_int2(-1, -1);
+        int2 e = make_int2(-1, -1), e2 = make_int2(-1, -1);
         if ((small || gen) && canon && nmatch > 0) {
             const bool pass = (La + Lb - nmatch) <= s_umax[nmatch];                 // cluster.py:165-170,218-219
             tests++; real += pass;
             e = make_int2(q, (int)((unsigned)b | (pass ? 0u : EB_NOPASS)));
             atomicAdd(&cp[q], 0x10000u + (pass ? 1u : 0u));
+            if (sym) {                                                              // b -> a: the same matrix read by columns (b's fillings in
+                unsigned usedA = 0;                                                 //  order, each taking the first free matching filling of a)
+                int nba = 0;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const unsigned col = ((m[0] >> g) & 1u) | (((m[1] >> g) & 1u) << 1) | (((m[2] >> g) & 1u) << 2) | (((m[3] >> g) & 1u) << 3);
+                    const unsigned avail = col & ~usedA;
+                    if (avail) { usedA |= avail & (0u - avail); nba++; }
+                }
+                const bool pass2 = (La + Lb - nba) <= s_umax[nba];
+                tests++; real += pass2;
+                e2 = make_int2(b, (int)((unsigned)q | (pass2 ? 0u : EB_NOPASS)));
+                atomicAdd(&cp[b], 0x10000u + (pass2 ? 1u : 0u));
+            }
         }
-        if (i < n) hits[i] = e;
+        if (i < n) { hits[i] = e; if (sym) rev[i] = e2; }
     }
     for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
     if ((threadIdx.x & 31) == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
@@ -248,7 +267,9 @@ __global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__re
 #endif
 __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
                                                        unsigned long long n_fixed, unsigned long long cap,
-                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
+                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err,
+                                                       const unsigned *__restrict__ only_if_zero) {
+    if (only_if_zero && *only_if_zero != 0) return;                                // (the reverse list exists in symmetric mode only)
     unsigned long long n = n_slots ? *n_slots : n_fixed;
     if (n > cap) n = cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * PLT_THREADS;
@@ -292,7 +313,8 @@ __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const in
 }
 // multi-GPU: this rank's recorded pairs of light saturating reads with partner lists, compacted for the all-gather
 __global__ void k_pent_compact(const int2 *__restrict__ ent, unsigned long long n, const PLInfo *__restrict__ plinfo, int2 *out,
-                               unsigned long long *n_out) {
+                               unsigned long long *n_out, const unsigned *__restrict__ only_if_zero) {
+    if (only_if_zero && *only_if_zero != 0) return;
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     bool keep = false;
     int2 e = make_int2(-1, -1);
