@@ -134,7 +134,6 @@ struct Pipe {
     int *rclass, *heavy_list, *plcount, *ploff;
     int hits_blocks;
     int2 *entries, *pedges;
-    int2 *rev;               // symmetric mode: rev[i] = the reverse directed pair of entries[i] (k_eval)
     int4 *PL; PLInfo *plinfo;
     unsigned long long cap_entries, cap_pedges, cap_pl;
     int *parent, *ing;
@@ -488,7 +487,6 @@ static int pipe_bands(fslrc_ctx *ctx, Pipe *P, const int *s_dp, const int *rmidx
     P->cap_entries = std::min<unsigned long long>(lightT + capT, tight) + (unsigned long long)PK_CHUNK * PK_WARPS * P->pair_blocks +
                      (unsigned long long)HK_CHUNK * HK_WARPS * P->hits_blocks + 64;
     DA(P->entries, P->cap_entries);
-    DA(P->rev, pr.overlap > 0.0 ? P->cap_entries : 1);
     DA(P->cp, Q); DA(P->heavy_list, Q); DA(P->plcount, Q); DA(P->ploff, Q);
     // partner records of saturating reads (replay LIST mode): at most RP_K per read and never more than tight-band hits
     P->cap_pl = std::min<unsigned long long>((unsigned long long)Q * RP_K, tight) + (unsigned long long)PL_CHUNK * PK_WARPS * P->pair_blocks * 2 + 64;
@@ -511,7 +509,7 @@ static int pipe_pair(fslrc_ctx *ctx, Pipe *P, int shard, int nshard) {
     }
     { int r = mark(ctx, ST_CAND); if (r) return r; }
     if (dense)
-        KL(k_eval, n_sms(ctx) * resident_blocks(k_eval, EV_THREADS), EV_THREADS, P->tab, P->um, P->entries, P->rev, (const unsigned *)(P->cnt + 46),
+        KL(k_eval, n_sms(ctx) * resident_blocks(k_eval, EV_THREADS), EV_THREADS, P->tab, P->um, P->entries, (const unsigned *)(P->cnt + 46),
            (const unsigned long long *)(P->cnt + 5), P->cap_entries, P->cp,
            (unsigned long long *)(P->cnt + 4), (unsigned long long *)(P->cnt + 13));
     { int r = mark(ctx, ST_PAIR); if (r) return r; }
@@ -546,13 +544,9 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     DA(posQ, Q);
     if (Q > 0 && P->pr.overlap > 0.0) {                                   // partner records of the light saturating reads
         if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS)), PLT_THREADS, P->tab, pairs,
-                                       (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->cp, P->PL, P->err, (const unsigned *)nullptr); }
-        else {
-            KL(k_plist, n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS), PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
-               P->cap_entries, P->plinfo, P->cp, P->PL, P->err, (const unsigned *)nullptr);
-            KL(k_plist, n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS), PLT_THREADS, P->tab, (const int2 *)P->rev, (const unsigned long long *)(P->cnt + 5), 0ull,
-               P->cap_entries, P->plinfo, P->cp, P->PL, P->err, (const unsigned *)(P->cnt + 46));
-        }
+                                       (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->cp, P->PL, P->err); }
+        else KL(k_plist, n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS), PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
+                P->cap_entries, P->plinfo, P->cp, P->PL, P->err);
     }
     if (Q > 0) {
         int r = xscan(ctx, P, P->isP, posQ, Q, P->cnt + 6); if (r) return r;
@@ -607,13 +601,8 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         KL(k_iota, nblk(Q, TB), TB, P->parent, Q);
         CK(cudaMemsetAsync(P->ing, 0, sizeof(int) * Q, st));
     }
-    if (nent > 0) {
-        KL(k_union_entries, nblk((int64_t)nent, UE_THREADS * UE_PER), UE_THREADS, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
-           (unsigned long long *)(P->cnt + 8), (const unsigned *)nullptr);
-        if (P->pr.overlap > 0.0)
-            KL(k_union_entries, nblk((int64_t)nent, UE_THREADS * UE_PER), UE_THREADS, nent, P->rev, P->isP, P->tab, P->stop, P->parent, P->ing,
-               (unsigned long long *)(P->cnt + 8), (const unsigned *)(P->cnt + 46));
-    }
+    if (nent > 0) KL(k_union_entries, nblk((int64_t)nent, UE_THREADS * UE_PER), UE_THREADS, nent, P->entries, P->isP, P->tab, P->stop, P->parent, P->ing,
+                                                                           (unsigned long long *)(P->cnt + 8));
     // replayed edges are identical on every rank; rank 0 contributes them once
     if (nped > 0 && shard == 0) KL(k_union_edges, nblk((int64_t)nped, TB), TB, nped, P->pedges, P->parent, P->ing, (unsigned long long *)(P->cnt + 8));
     (void)nshard;
@@ -863,11 +852,7 @@ int fslrc_mg_partners(fslrc_ctx *ctx, int rank, int world, int32_t **pairs, int6
     r = err_code(ctx); if (r) return r;
     const unsigned long long nent = std::min<unsigned long long>((unsigned long long)ctx->h_pin[5], P->cap_entries);
     int2 *pent; DA(pent, 2 * nent);
-    if (nent > 0) {
-        KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->entries, nent, P->plinfo, pent, (unsigned long long *)(P->cnt + 47), (const unsigned *)nullptr);
-        if (P->pr.overlap > 0.0)
-            KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->rev, nent, P->plinfo, pent, (unsigned long long *)(P->cnt + 47), (const unsigned *)(P->cnt + 46));
-    }
+    if (nent > 0) KL(k_pent_compact, nblk((int64_t)nent, 256), 256, (const int2 *)P->entries, nent, P->plinfo, pent, (unsigned long long *)(P->cnt + 47));
     r = read_counts(ctx, P); if (r) return r;
     *pairs = (int32_t *)pent; *n_pairs = ctx->h_pin[47];
     return 0;

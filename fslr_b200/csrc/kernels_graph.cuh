@@ -30,27 +30,29 @@ __device__ __forceinline__ void uf_union(int *parent, int a, int b) {
 // union-find is pointer chasing: what counts is how many chases are in flight.  Every block filters its 1024 slots (entry and
 // isP loads batched), compacts the survivors in shared memory and walks them with all lanes busy.
 __global__ void __launch_bounds__(UE_THREADS) k_union_entries(unsigned long long n, const int2 *__restrict__ entries, const int *__restrict__ isP,
-                                                              Tab t, const int *stop, int *parent, int *ing, unsigned long long *n_edges,
-                                                              const unsigned *__restrict__ only_if_zero) {
-    if (only_if_zero && *only_if_zero != 0) return;                                // (the reverse list exists in symmetric mode only)
-    __shared__ int2 sE[UE_THREADS * UE_PER];
+                                                              Tab t, const int *stop, int *parent, int *ing, unsigned long long *n_edges) {
+    __shared__ int2 sE[UE_THREADS * UE_PER * 2];                                    // (a symmetric slot stands for two directed pairs)
     __shared__ int s_warp[UE_THREADS / 32];
     __shared__ int s_ne;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long k0 = (unsigned long long)blockIdx.x * (UE_THREADS * UE_PER) + tid;
     if (tid == 0) s_ne = 0;
     int2 ab[UE_PER];
-    int pa[UE_PER];
+    int pa[UE_PER], pb[UE_PER];
 #pragma unroll
     for (int u = 0; u < UE_PER; u++) {                                              // all entries, then all flags: loads in flight together
         const unsigned long long k = k0 + (unsigned long long)u * UE_THREADS;
         ab[u] = k < n ? __ldg(&entries[k]) : make_int2(-1, -1);
     }
 #pragma unroll
-    for (int u = 0; u < UE_PER; u++) pa[u] = (ab[u].x >= 0 && ab[u].y >= 0) ? __ldg(&isP[ab[u].x]) : 1;   // (y < 0: the pair does not pass)
+    for (int u = 0; u < UE_PER; u++) {                                              // 1: nothing to do for that direction
+        const unsigned y = (unsigned)ab[u].y;
+        pa[u] = (ab[u].x >= 0 && !(y & EB_NOPASS)) ? __ldg(&isP[ab[u].x]) : 1;
+        pb[u] = (ab[u].x >= 0 && (y & EB_SYM) && !(y & EB_NOPASS2)) ? __ldg(&isP[y & QMASK]) : 1;
+    }
     int mine = 0;
 #pragma unroll
-    for (int u = 0; u < UE_PER; u++) mine += !pa[u];
+    for (int u = 0; u < UE_PER; u++) mine += !pa[u] + !pb[u];
     int incl = mine;                                                                // block-wide exclusive scan of the survivor counts
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
@@ -61,7 +63,10 @@ __global__ void __launch_bounds__(UE_THREADS) k_union_entries(unsigned long long
     for (int w = 0; w < UE_THREADS / 32; w++) { const int c = s_warp[w]; if (w < warp) wbase += c; total += c; }
     int at = wbase + incl - mine;
 #pragma unroll
-    for (int u = 0; u < UE_PER; u++) if (!pa[u]) sE[at++] = make_int2(ab[u].x, ab[u].y & QMASK);   // y: b | EB_NOPASS | EB_HEAVY
+    for (int u = 0; u < UE_PER; u++) {                                              // y: b | EB_NOPASS | EB_HEAVY | EB_SYM | EB_NOPASS2
+        if (!pa[u]) sE[at++] = make_int2(ab[u].x, ab[u].y & QMASK);
+        if (!pb[u]) sE[at++] = make_int2(ab[u].y & QMASK, ab[u].x);
+    }
     __syncthreads();
     int ne = 0;
     for (int idx = tid; idx < total; idx += UE_THREADS) {

@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(HK_WARPS * 32, 8) k_hits(Tab t, int shard, int
 #ifndef EV_MINB
 #define EV_MINB 4
 #endif
-__global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxTab um, int2 *hits, int2 *rev, const unsigned *__restrict__ n_heavy,
+__global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxTab um, int2 *hits, const unsigned *__restrict__ n_heavy,
                                                      const unsigned long long *n_slots, unsigned long long cap, unsigned *cp,
                                                      unsigned long long *n_tests, unsigned long long *n_real) {
-    const bool sym = *n_heavy == 0;                                                // symmetric mode: slot i also yields rev[i] = (b, a | flags)
+    const bool sym = *n_heavy == 0;                                                // symmetric mode: slot i also stands for (b, a): EB_SYM
     __shared__ int s_umax[LMAX + 1];
     for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
     __syncthreads();
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxT
             }
             if (canon) atomicOr(&cp[q], CP_LONG);                                   // the replay has to WALK this read
         }
-        int2 e = make_int2(-1, -1), e2 = make_int2(-1, -1);
+        int2 e = make_int2(-1, -1);
         if ((small || gen) && canon && nmatch > 0) {
             const bool pass = (La + Lb - nmatch) <= s_umax[nmatch];                 // cluster.py:165-170,218-219
             tests++; real += pass;
@@ -219,11 +219,11 @@ __global__ void __launch_bounds__(EV_THREADS, EV_MINB) k_eval(Tab t, const UmaxT
                 }
                 const bool pass2 = (La + Lb - nba) <= s_umax[nba];
                 tests++; real += pass2;
-                e2 = make_int2(b, (int)((unsigned)q | (pass2 ? 0u : EB_NOPASS)));
+                e.y |= (int)(EB_SYM | (pass2 ? 0u : EB_NOPASS2));
                 atomicAdd(&cp[b], 0x10000u + (pass2 ? 1u : 0u));
             }
         }
-        if (i < n) { hits[i] = e; if (sym) rev[i] = e2; }
+        if (i < n) hits[i] = e;
     }
     for (int o = 16; o; o >>= 1) { tests += __shfl_down_sync(FULL, tests, o); real += __shfl_down_sync(FULL, real, o); }
     if ((threadIdx.x & 31) == 0) { if (tests) atomicAdd(n_tests, tests); if (real) atomicAdd(n_real, real); }
@@ -267,64 +267,78 @@ __global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__re
 #endif
 __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
                                                        unsigned long long n_fixed, unsigned long long cap,
-                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err,
-                                                       const unsigned *__restrict__ only_if_zero) {
-    if (only_if_zero && *only_if_zero != 0) return;                                // (the reverse list exists in symmetric mode only)
+                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
     unsigned long long n = n_slots ? *n_slots : n_fixed;
     if (n > cap) n = cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * PLT_THREADS;
     for (unsigned long long i = (unsigned long long)blockIdx.x * PLT_THREADS + threadIdx.x; i < n; i += stride) {
         const int2 e = __ldg(&ent[i]);
-        const int a = e.x;
-        if (a < 0 || ((unsigned)e.y & EB_HEAVY)) continue;
-        const int b = e.y & QMASK;
-        const PLInfo pi = plinfo[a];                                                // n > 0: saturating, and the replay takes its list
-        const int wb = __ldg(&t.RI[b]).w;                                           // (both gathers in flight together)
-        if (pi.n <= 0) continue;
-        const int wa = pi.pad;
-        const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
-        const unsigned slot = atomicAdd(&cp[a], 1u);
-        if ((int)slot >= pi.n || La > 4 || Lb > 4) { atomicOr(err, EF_OVERFLOW); continue; }   // (cannot happen: counted by k_eval)
-        int4 A[4]; int pa[4];
+        if (e.x < 0 || ((unsigned)e.y & EB_HEAVY)) continue;
+        const int e1 = e.y & QMASK;
+        const PLInfo pi0 = plinfo[e.x];                                             // n > 0: saturating, and the replay takes its list
+        const int w1 = __ldg(&t.RI[e1]).w;                                          // (both gathers in flight together)
+        const bool sym = ((unsigned)e.y & EB_SYM) != 0;                             // the slot also stands for (e1, e.x)
+        PLInfo pi1; pi1.off = 0; pi1.n = 0; pi1.pad = 0;
+        if (sym) pi1 = plinfo[e1];
+        for (int dir = 0; dir < 2; dir++) {
+            const PLInfo pi = dir ? pi1 : pi0;
+            if (pi.n <= 0) continue;
+            const int a = dir ? e1 : e.x, b = dir ? e.x : e1;
+            const int wa = pi.pad, wb = dir ? pi0.pad : w1;                         // (pad = RI[.].w for every light read)
+            const bool nopass = ((unsigned)e.y & (dir ? EB_NOPASS2 : EB_NOPASS)) != 0;
+            const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
+            const unsigned slot = atomicAdd(&cp[a], 1u);
+            if ((int)slot >= pi.n || La > 4 || Lb > 4) { atomicOr(err, EF_OVERFLOW); continue; }   // (cannot happen: counted by k_eval)
+            int4 A[4]; int pa[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            A[k] = make_int4(-1, 0, 0, 0); pa[k] = -1;
-            if (k < La) { A[k] = rm0(t, offa + k); pa[k] = rm1(t, offa + k).x; }
-        }
-        int key[4] = {-1, -1, -1, -1};
-        unsigned cg = 0;
-        for (int gb = 0; gb < Lb; gb++) {
-            const int4 i0 = rm0(t, offb + gb);
-            const int pg = rm1(t, offb + gb).x;
-            int best = -1, bestfa = 0;
-#pragma unroll
-            for (int fa = 0; fa < 4; fa++) {
-                if (fa < La && A[fa].x == i0.x && A[fa].y <= i0.z && A[fa].z >= i0.y) {   // closed overlap: a scan of one visits the other
-                    key[fa] = max(key[fa], pg);
-                    if (pa[fa] > best) { best = pa[fa]; bestfa = fa; }
-                }
+            for (int k = 0; k < 4; k++) {
+                A[k] = make_int4(-1, 0, 0, 0); pa[k] = -1;
+                if (k < La) { A[k] = rm0(t, offa + k); pa[k] = rm1(t, offa + k).x; }
             }
-            if (best >= 0) cg |= (4u | (unsigned)bestfa) << (4 * gb);
+            int key[4] = {-1, -1, -1, -1};
+            unsigned cg = 0;
+            for (int gb = 0; gb < Lb; gb++) {
+                const int4 i0 = rm0(t, offb + gb);
+                const int pg = rm1(t, offb + gb).x;
+                int best = -1, bestfa = 0;
+#pragma unroll
+                for (int fa = 0; fa < 4; fa++) {
+                    if (fa < La && A[fa].x == i0.x && A[fa].y <= i0.z && A[fa].z >= i0.y) {   // closed overlap: a scan of one visits the other
+                        key[fa] = max(key[fa], pg);
+                        if (pa[fa] > best) { best = pa[fa]; bestfa = fa; }
+                    }
+                }
+                if (best >= 0) cg |= (4u | (unsigned)bestfa) << (4 * gb);
+            }
+            const unsigned long long at = pi.off + slot;
+            PL[2 * at] = make_int4((int)((unsigned)b | (nopass ? 0u : 0x80000000u)), wb, (int)cg, 0);
+            PL[2 * at + 1] = make_int4(key[0], key[1], key[2], key[3]);
         }
-        const unsigned long long at = pi.off + slot;
-        PL[2 * at] = make_int4((int)((unsigned)b | (((unsigned)e.y & EB_NOPASS) ? 0u : 0x80000000u)), wb, (int)cg, 0);
-        PL[2 * at + 1] = make_int4(key[0], key[1], key[2], key[3]);
     }
 }
 // multi-GPU: this rank's recorded pairs of light saturating reads with partner lists, compacted for the all-gather
 __global__ void k_pent_compact(const int2 *__restrict__ ent, unsigned long long n, const PLInfo *__restrict__ plinfo, int2 *out,
-                               unsigned long long *n_out, const unsigned *__restrict__ only_if_zero) {
-    if (only_if_zero && *only_if_zero != 0) return;
+                               unsigned long long *n_out) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    bool keep = false;
-    int2 e = make_int2(-1, -1);
+    bool keep = false, keep2 = false;                                               // (a symmetric slot stands for two directed pairs)
+    int2 e = make_int2(-1, -1), e2 = make_int2(-1, -1);
     if (i < n) {
         e = ent[i];
-        keep = e.x >= 0 && !((unsigned)e.y & EB_HEAVY) && plinfo[e.x].n > 0;
+        if (e.x >= 0 && !((unsigned)e.y & EB_HEAVY)) {
+            const int b = e.y & QMASK;
+            keep = plinfo[e.x].n > 0;
+            if ((unsigned)e.y & EB_SYM) {
+                keep2 = plinfo[b].n > 0;
+                e2 = make_int2(b, (int)((unsigned)e.x | (((unsigned)e.y & EB_NOPASS2) ? EB_NOPASS : 0u)));
+            }
+            e.y = (int)((unsigned)b | ((unsigned)e.y & EB_NOPASS));
+        }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    const unsigned m = __ballot_sync(0xffffffffu, keep), m2 = __ballot_sync(0xffffffffu, keep2);
     unsigned long long at = 0;
-    if ((threadIdx.x & 31) == 0 && m) at = atomicAdd(n_out, (unsigned long long)__popc(m));
+    if ((threadIdx.x & 31) == 0 && (m | m2)) at = atomicAdd(n_out, (unsigned long long)(__popc(m) + __popc(m2)));
     at = __shfl_sync(0xffffffffu, at, 0);
-    if (keep) out[at + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = e;
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+    if (keep) out[at + __popc(m & lt)] = e;
+    if (keep2) out[at + __popc(m) + __popc(m2 & lt)] = e2;
 }

@@ -232,6 +232,8 @@ __global__ void k_apply_delta(int D, const unsigned *__restrict__ val, int *s_dp
 #define PCAP 128                // a sorted position whose tight band is longer makes its read "heavy" (kernels_hits.cuh)
 #define EB_NOPASS 0x80000000u   // entry.y bit 31: b is a partner of a (n > 0) but a -> b fails the Jaccard cutoff
 #define EB_HEAVY 0x40000000u    // entry.y bit 30: recorded by k_pair for a heavy read (its partner records exist already)
+#define EB_SYM 0x20000000u      // entry.y bit 29: symmetric mode, the slot also stands for the reverse directed pair (b, a) ...
+#define EB_NOPASS2 0x10000000u  // entry.y bit 28: ... which fails the Jaccard cutoff (the greedy count is not symmetric)
 // per-read word `cp` (light reads): bits 0-15 passing partners, bits 16-30 partners, bit 31 a partner has > 4 fillings
 #define CP_LONG 0x80000000u
 __global__ void k_records(int D, const int *__restrict__ s_dp, const int *__restrict__ rmidx, const int *__restrict__ it_q,
