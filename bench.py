@@ -348,6 +348,8 @@ def main():
         ok = all(int(c[2]) == 1 and torch.equal(c[:2], allc[0][:2]) for c in allc)
         assert ok, "sharded result differs from the single-GPU result of the same table (rank %d: %s)" % (rank, [c.tolist() for c in allc])
         sharded_check = {"equal_to_single_gpu_run_on_every_rank": True, "checksum": [int(x) for x in allc[0][:2].tolist()]}
+        for _ in range(2):                                    # the single-GPU run above resized the scratch pools: settle them again
+            step_resident()
 
     t_first = time.time()
     ms, sts, launches = timed(step_resident, args.steps)

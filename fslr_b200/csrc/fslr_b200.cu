@@ -544,9 +544,9 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     DA(posQ, Q);
     if (Q > 0 && P->pr.overlap > 0.0) {                                   // partner records of the light saturating reads
         if (pairs) { if (n_pairs > 0) KL(k_plist, std::min(nblk((int64_t)n_pairs, PLT_THREADS), n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS)), PLT_THREADS, P->tab, pairs,
-                                       (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->cp, P->PL, P->err); }
+                                       (const unsigned long long *)nullptr, n_pairs, n_pairs, P->plinfo, P->isP, P->cp, P->PL, P->err); }
         else KL(k_plist, n_sms(ctx) * resident_blocks(k_plist, PLT_THREADS), PLT_THREADS, P->tab, (const int2 *)P->entries, (const unsigned long long *)(P->cnt + 5), 0ull,
-                P->cap_entries, P->plinfo, P->cp, P->PL, P->err);
+                P->cap_entries, P->plinfo, P->isP, P->cp, P->PL, P->err);
     }
     if (Q > 0) {
         int r = xscan(ctx, P, P->isP, posQ, Q, P->cnt + 6); if (r) return r;
@@ -569,7 +569,10 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
     if (nP > 0) {
         int *sflag, *spos, *sstart, *rflag, *rpos, *rstart;
         DA(sflag, nP); DA(spos, nP); DA(sstart, nP); DA(rflag, nP); DA(rpos, nP); DA(rstart, nP);
-        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, sflag, P->stop, P->stopS);
+        const bool walk = !(P->pr.overlap > 0.0) || ctx->h_pin[43] != 0;   // some read without partner records?
+        int4 *RH = nullptr;
+        if (!walk) DA(RH, 3 * (int64_t)nP);
+        KL(k_run_flags, nblk(nP, TB), TB, nP, P->plist, P->RI, P->RM, sflag, P->stop, P->stopS, P->plinfo, P->tab.chrom_lo, RH);
         int r = xscan(ctx, P, sflag, spos, nP, P->cnt + 15); if (r) return r;
         KL(k_compact_flagged, nblk(nP, TB), TB, nP, sflag, spos, sstart);
         KL(k_run_cut, nblk(nP, TB), TB, nP, sflag, spos, sstart, P->cnt + 15, rflag);
@@ -578,7 +581,6 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
-        const bool walk = !(P->pr.overlap > 0.0) || ctx->h_pin[43] != 0;   // some read without partner records?
         if (walk && D > 0) {
             int *sib; DA(sib, D);
             KL(k_sib, nblk(D, TB), TB, D, P->SR0, P->SR1, P->RM, sib);
@@ -589,7 +591,7 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (walk) KL((k_replay<false, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (getenv("FSLRC_REPLAY_GROUPS")) KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
-        else KL(k_replay_list, std::min(nblk(nRuns, RL_WARPS), list_blocks_max), RL_WARPS * 32, P->tab, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo,
+        else KL(k_replay_list, std::min(nblk(nRuns, RL_WARPS), list_blocks_max), RL_WARPS * 32, P->tab, nP, RH, nRuns, rstart, P->isP, P->PL,
                 P->stop, P->stopS, P->ticket, P->pedges, (unsigned long long *)(P->cnt + 7), P->cap_pedges, P->err, (unsigned long long *)(P->cnt + 16));
 #undef REPLAY_ARGS
     }
@@ -639,6 +641,12 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->no_clusters = h[9] == 0;
     if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld, walk-mode reads %lld\n",
                                        (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12], (long long)h[43]);
+#ifdef FSLRC_WALKPROF
+    if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] walkprof: %.3f ms; warp-wide steps %lld (%.0f cycles each), other iterations %lld (%.0f cycles each), group-wide steps %lld; inside a warp-wide step: %.0f cycles to the first-round results, %.0f to the sibling results\n",
+                                       1e-6 * (double)h[29], (long long)h[30], (double)h[31] / (double)std::max<long long>(h[30], 1), (long long)h[32],
+                                       (double)h[33] / (double)std::max<long long>(h[32], 1), (long long)h[34], (double)h[35] / (double)std::max<long long>(h[30], 1), (double)h[36] / (double)std::max<long long>(h[30], 1));
+    else
+#endif
     if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] long stall: a %lld waits b %lld stops %d %d base %lld top %lld posf %lld bpos %lld %lld apos2 %lld fi %lld (n=%lld)\n",
                                        (long long)h[29], (long long)h[30], (int)h[31], (int)h[32], (long long)h[33], (long long)h[34], (long long)h[35], (long long)h[36], (long long)h[37], (long long)h[38], (long long)h[39], (long long)h[28]);
     if (getenv("FSLRC_DEBUG") && h[20]) fprintf(stderr, "[fslrc] longest walk: %lld steps (stalled %lld) read %lld filling %lld/%lld band %lld walked %lld edges %lld\n",

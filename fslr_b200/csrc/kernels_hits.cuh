@@ -263,11 +263,11 @@ __global__ void k_plinfo(int Q, const int *__restrict__ plcount, const int *__re
 // One lane per recorded pair: the partner record of saturating read a about partner b (see PLInfo / k_pair for the fields)
 #define PLT_THREADS 256
 #ifndef PLT_MINB
-#define PLT_MINB 5
+#define PLT_MINB 4               // 64 registers, no spills (5 blocks: 48 registers + spilled words, measured 1.12 vs 1.05 ms for the stage)
 #endif
 __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const int2 *__restrict__ ent, const unsigned long long *n_slots,
                                                        unsigned long long n_fixed, unsigned long long cap,
-                                                       const PLInfo *__restrict__ plinfo, unsigned *cp, int4 *PL, int *err) {
+                                                       const PLInfo *__restrict__ plinfo, const int *__restrict__ isP, unsigned *cp, int4 *PL, int *err) {
     unsigned long long n = n_slots ? *n_slots : n_fixed;
     if (n > cap) n = cap;
     const unsigned long long stride = (unsigned long long)gridDim.x * PLT_THREADS;
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const in
             const bool nopass = ((unsigned)e.y & (dir ? EB_NOPASS2 : EB_NOPASS)) != 0;
             const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1, offb = (int)((unsigned)wb >> 6), Lb = (wb & 63) + 1;
             const unsigned slot = atomicAdd(&cp[a], 1u);
+            const int seen = (b < a && !__ldg(&isP[b])) ? 1 : 0;                    // b < a and never breaking: its query saw the pair
             if ((int)slot >= pi.n || La > 4 || Lb > 4) { atomicOr(err, EF_OVERFLOW); continue; }   // (cannot happen: counted by k_eval)
             int4 A[4]; int pa[4];
 #pragma unroll
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(PLT_THREADS, PLT_MINB) k_plist(Tab t, const in
                 if (best >= 0) cg |= (4u | (unsigned)bestfa) << (4 * gb);
             }
             const unsigned long long at = pi.off + slot;
-            PL[2 * at] = make_int4((int)((unsigned)b | (nopass ? 0u : 0x80000000u)), wb, (int)cg, 0);
+            PL[2 * at] = make_int4((int)((unsigned)b | (nopass ? 0u : 0x80000000u)), wb, (int)cg, PLF_KNOWN | seen);
             PL[2 * at + 1] = make_int4(key[0], key[1], key[2], key[3]);
         }
     }

@@ -135,6 +135,7 @@ __device__ __noinline__ int eval_general(const int4 *__restrict__ A, int La, con
 //   key[fa] the highest sorted position of an interval of b inside the closed band of a's filling fa (-1: none): where
 //           a's scan of fa first meets b.
 struct PLInfo { unsigned long long off; int n; int pad; };
+#define PLF_KNOWN 16            // partner record .w: bit 0 ("b < a and b never breaks: b's query saw the pair") was resolved by k_plist
 
 // heavy_list != NULL: the kernel runs over the reads k_hits listed as heavy (more than 4 fillings, or a hotspot band), every
 // rank over all of them (their partner records and isP are needed everywhere; they are few); NULL: over all query reads

@@ -40,13 +40,28 @@ __device__ __forceinline__ void st_relaxed(int *p, int v) {
 __device__ __forceinline__ int stop_reached(int v) { return v >= 0 ? v : -2 - v; }   // lowest position known to be visited
 // streak starts: ticket k continues the previous saturating read's streak iff their first fillings reciprocally overlap
 // (same PCR family: they depend on each other).  Also marks the stops of every saturating read as unknown.
+// RH (k_replay_list): per ticket one 48-byte header {a, RI[a].w, PL offset (40 bits), n}, {pos of fillings 0..3}, {chromosome
+// start of fillings 0..3}: everything the replay of read a needs before its partner records, in ONE coalesced round trip
+// (instead of the chain plist -> RI / plinfo -> RM -> chrom_lo on the latency-bound path)
 __global__ void k_run_flags(int nP, const int *__restrict__ plist, const int4 *__restrict__ RI, const int4 *__restrict__ RM, int *flag,
-                            int *stop, int *stopS) {
+                            int *stop, int *stopS, const PLInfo *__restrict__ plinfo, const int *__restrict__ chrom_lo, int4 *RH) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nP) return;
-    const int w = RI[plist[k]].w;
+    const int a = plist[k];
+    const int w = RI[a].w;
     const int off = (int)((unsigned)w >> 6), L = (w & 63) + 1;
-    for (int j = 0; j < L; j++) { stop[off + j] = STOP_UNSTARTED; stopS[RM[2 * (off + j) + 1].x] = STOP_UNSTARTED; }
+    int pos4[4] = {0, 0, 0, 0}, lo4[4] = {0, 0, 0, 0};
+    for (int j = 0; j < L; j++) {
+        const int pj = RM[2 * (off + j) + 1].x;
+        stop[off + j] = STOP_UNSTARTED; stopS[pj] = STOP_UNSTARTED;
+        if (j < 4) { pos4[j] = pj; lo4[j] = chrom_lo[RM[2 * (off + j)].x]; }
+    }
+    if (RH) {
+        const PLInfo pi = plinfo[a];
+        RH[3 * k] = make_int4(a, w, (int)(unsigned)(pi.off & 0xffffffffull), (int)((unsigned)((pi.off >> 32) & 0xffull) | ((unsigned)pi.n << 8)));
+        RH[3 * k + 1] = make_int4(pos4[0], pos4[1], pos4[2], pos4[3]);
+        RH[3 * k + 2] = make_int4(lo4[0], lo4[1], lo4[2], lo4[3]);
+    }
     int f = 1;
     if (k > 0) {
         const int4 x = RM[2 * ((unsigned)RI[plist[k - 1]].w >> 6)], y = RM[2 * off];
@@ -146,6 +161,14 @@ __device__ __forceinline__ int gmax8(unsigned gmask, int v) { return __reduce_ma
 #ifndef RG_MINB_WALK
 #define RG_MINB_WALK 6          // ... and the instantiation with the band-walking code (wide skip steps: 32 loads per lane in flight)
 #endif
+#ifdef FSLRC_WALKPROF
+#define FSLRC_WALKPROF_ON 1
+#else
+#define FSLRC_WALKPROF_ON 0
+#endif
+#ifndef RG_PARK
+#define RG_PARK 16              // wide skip steps after which a walk counts as long (its warp stops taking new runs)
+#endif
 #ifndef RG_REC
 #define RG_REC 16               // reads a group remembers the final stops of (direct mapped by rank)
 #endif
@@ -174,11 +197,14 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
     unsigned tk = 0, tk1 = 0;
     int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0, posf = 0;
     int nPart = 0;
-    bool wide = false;
+    bool wide = false, parked = false;
     int4 ria = make_int4(0, 0, 0, 0), f = make_int4(0, 0, 0, 0);
     unsigned long long tests = 0, chunk_base = 0;
     unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
     int d_fsteps = 0, d_fstall = 0;
+#ifdef FSLRC_WALKPROF
+    long long wp_t0 = 0, wp_cw = 0, wp_cn = 0, wp_it0 = 0, wp_c1 = 0, wp_c2 = 0; int wp_nw = 0, wp_nn = 0, wp_n64 = 0;
+#endif
     int chunk_used = RP_CHUNK;
     for (int k = threadIdx.x; k <= LMAX; k += blockDim.x) s_umax[k] = um.v[k];
     __syncthreads();
@@ -188,10 +214,17 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
         __syncwarp();
         d_iter += lane == 0;
         wit++;
+#ifdef FSLRC_WALKPROF
+        { const long long now = clock64(); if (wp_it0 && phase == 2) { wp_cn += now - wp_it0; wp_nn++; } wp_it0 = now; }
+#endif
         if (WALK) {
             // ---- every group of this warp that still has work is skipping through a long band (the tail of a giant clique):
             // serve one of them with all 32 lanes, 256 positions per step (a lone 8-lane walker is instruction-latency bound)
-            const unsigned actm = __ballot_sync(FULL, phase != 3), widem = __ballot_sync(FULL, phase == 2 && wide);
+            // A group between two runs takes no new ticket while another group of its warp is deep in such a walk (other warps
+            // take the tickets): the walker then owns all 32 lanes instead of sharing every loop iteration with three groups
+            // that evaluate candidates (measured at C5: 8 us per 64-position step shared, ~2 us per 256-position step alone).
+            parked = __ballot_sync(FULL, phase == 2 && wide && d_fsteps > RG_PARK) != 0 && phase == 0 && tk == tk1;
+            const unsigned actm = __ballot_sync(FULL, phase != 3 && !parked), widem = __ballot_sync(FULL, phase == 2 && wide);
             if (actm != 0 && widem == actm) {
                 const unsigned gm = ((actm >> 0) & 1u) | (((actm >> 8) & 1u) << 1) | (((actm >> 16) & 1u) << 2) | (((actm >> 24) & 1u) << 3);
                 const int sel = __fns(gm, 0, (wit % __popc(gm)) + 1);              // round robin over the walking groups
@@ -203,21 +236,28 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     // filling sits — and the prefix max that tells whether anything at or below wbase still overlaps the filling
                     const int pmx = __ldg(&t.pmaxS[wbase]);
                     const bool sibs = t.sib && wLa <= 4;
+                    // (every load is issued on a clamped index before any result is touched: a conditional block per position makes
+                    //  the compiler consume each record right behind its load — eight serial round trips instead of one)
                     int wq[8], we[8], ws[8], wv[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
-                        const int p = wbase - 32 * k - lane;
-                        wq[k] = -1; we[k] = 0; ws[k] = 0; wv[k] = 0;
-                        if (p >= wlo) {
-                            const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]);
-                            if (sibs) wv[k] = __ldg(&t.sib[p]);
-                        }
+                        const int pc = max(wbase - 32 * k - lane, wlo);
+                        const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
+                        wv[k] = sibs ? __ldg(&t.sib[pc]) : 0;
                     }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) wq[k] = (wbase - 32 * k - lane >= wlo) ? (wq[k] & QMASK) : -1;
                     if (pmx < wfy) { if ((lane >> 3) == sel) wide = false; continue; }     // the walk is over: the normal path closes it
                     bool needs[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++)
                         needs[k] = wq[k] >= 0 && wq[k] != wa && we[k] >= wfy && !(wq[k] < wa && stop_reached(ws[k]) <= wposf);
+#ifdef FSLRC_WALKPROF
+                    { bool any = false;
+#pragma unroll
+                      for (int k = 0; k < 8; k++) any |= needs[k];
+                      const long long now = clock64(); if (__any_sync(FULL, any) || true) { if ((lane >> 3) == sel) wp_c1 += now - wp_it0; } }
+#endif
                     if (sibs) {
                         int sp[8];
 #pragma unroll
@@ -226,19 +266,28 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                             if (needs[k] && wq[k] < wa && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
                         }
                         int cs[8], ce[8], cv[8];
+                        bool anysp = false;
 #pragma unroll
-                        for (int k = 0; k < 8; k++)
-                            if (sp[k] >= 0) { const int4 c = __ldg(&t.SR0[sp[k]]); cs[k] = c.x; ce[k] = c.y; cv[k] = stop_reached(ld_relaxed(&stopS[sp[k]])); }
+                        for (int k = 0; k < 8; k++) anysp |= sp[k] >= 0;
+                        if (__any_sync(FULL, anysp)) {
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            if (sp[k] >= 0) {
+                            for (int k = 0; k < 8; k++) {                          // (same rule: all loads first)
+                                const int sc = max(sp[k], 0);
+                                const int4 c = __ldg(&t.SR0[sc]); cs[k] = c.x; ce[k] = c.y; cv[k] = ld_relaxed(&stopS[sc]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; k++) {
+                                const int reach = stop_reached(cv[k]);
 #pragma unroll
                                 for (int fa = 0; fa < 4; fa++)
-                                    if (fa < wLa && sp[k] >= sAchr[wgrp][fa].x && sp[k] < sAchr[wgrp][fa].y && sA0[wgrp][fa].y <= ce[k] &&
-                                        sA0[wgrp][fa].z >= cs[k] && cv[k] <= sA1[wgrp][fa].x) needs[k] = false;
+                                    if (sp[k] >= 0 && fa < wLa && sp[k] >= sAchr[wgrp][fa].x && sp[k] < sAchr[wgrp][fa].y && sA0[wgrp][fa].y <= ce[k] &&
+                                        sA0[wgrp][fa].z >= cs[k] && reach <= sA1[wgrp][fa].x) needs[k] = false;
                             }
                         }
                     }
+#ifdef FSLRC_WALKPROF
+                    { const long long now = clock64(); if ((lane >> 3) == sel) wp_c2 += now - wp_it0; }
+#endif
                     int adv = 256;
 #pragma unroll
                     for (int k = 7; k >= 0; k--) {
@@ -251,11 +300,14 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                         if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
                         d_fsteps++;
                     }
+#ifdef FSLRC_WALKPROF
+                    { const long long now = clock64(); if ((lane >> 3) == sel) { wp_cw += now - wp_it0; wp_nw++; } wp_it0 = 0; }
+#endif
                     continue;
                 }
             }
         }
-        if (phase == 0) {
+        if (phase == 0 && !(WALK && parked)) {
             if (tk == tk1) {                                                       // run finished: take the next ticket
                 unsigned run = 0;
                 if (gl == 0) run = atomicAdd(ticket, 1u);
@@ -467,6 +519,9 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
             base = top;
             wide = false;
             phase = 2;
+#ifdef FSLRC_WALKPROF
+            { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); wp_t0 = (long long)g; wp_cw = wp_cn = wp_c1 = wp_c2 = 0; wp_nw = wp_nn = wp_n64 = 0; }
+#endif
         }
         if (phase == 2) {
             int stopf = -1;                                                        // >= 0: this filling's scan ended there
@@ -478,38 +533,42 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 // provably saw a first (its scan of this very interval already passed a's filling), 64 positions per step
                 int adv = 64;
                 const bool sibs = t.sib && La <= 4;
-                int wq[8], we[8], ws[8], wv[8];                                    // all 24 loads of the step are issued before any use
+                int wq[8], we[8], ws[8], wv[8];                                    // all 24 loads of the step are issued (on clamped indices)
 #pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int p = base - 8 * k - gl;
-                    wq[k] = -1; we[k] = 0; ws[k] = 0; wv[k] = 0;
-                    if (p >= lo) {
-                        const int4 c0 = __ldg(&t.SR0[p]); wq[k] = c0.w & QMASK; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[p]);
-                        if (sibs) wv[k] = __ldg(&t.sib[p]);
-                    }
+                for (int k = 0; k < 8; k++) {                                      //  before any result is touched
+                    const int pc = max(base - 8 * k - gl, lo);
+                    const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
+                    wv[k] = sibs ? __ldg(&t.sib[pc]) : 0;
                 }
+#pragma unroll
+                for (int k = 0; k < 8; k++) wq[k] = (base - 8 * k - gl >= lo) ? (wq[k] & QMASK) : -1;
                 bool needs[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++)
                     needs[k] = wq[k] >= 0 && wq[k] != a && we[k] >= f.y && !(wq[k] < a && stop_reached(ws[k]) <= posf);
                 if (sibs) {                                                        // ... or through its other filling (reads of 2 fillings:
                     int sp[8];                                                     //     the loads of all 8 positions are batched)
+                    bool anysp = false;
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         sp[k] = -1;
                         if (needs[k] && wq[k] < a && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
+                        anysp |= sp[k] >= 0;
                     }
-                    int cs[8], ce[8], cv[8];
+                    if ((__ballot_sync(gmask, anysp) >> gsh) & 0xffu) {
+                        int cs[8], ce[8], cv[8];
 #pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        if (sp[k] >= 0) { const int4 c = __ldg(&t.SR0[sp[k]]); cs[k] = c.x; ce[k] = c.y; cv[k] = stop_reached(ld_relaxed(&stopS[sp[k]])); }
+                        for (int k = 0; k < 8; k++) {
+                            const int sc = max(sp[k], 0);
+                            const int4 c = __ldg(&t.SR0[sc]); cs[k] = c.x; ce[k] = c.y; cv[k] = ld_relaxed(&stopS[sc]);
+                        }
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        if (sp[k] >= 0) {
+                        for (int k = 0; k < 8; k++) {
+                            const int reach = stop_reached(cv[k]);
 #pragma unroll
                             for (int fa = 0; fa < 4; fa++)
-                                if (fa < La && sp[k] >= sAchr[grp][fa].x && sp[k] < sAchr[grp][fa].y && sA0[grp][fa].y <= ce[k] &&
-                                    sA0[grp][fa].z >= cs[k] && cv[k] <= sA1[grp][fa].x) needs[k] = false;
+                                if (sp[k] >= 0 && fa < La && sp[k] >= sAchr[grp][fa].x && sp[k] < sAchr[grp][fa].y && sA0[grp][fa].y <= ce[k] &&
+                                    sA0[grp][fa].z >= cs[k] && reach <= sA1[grp][fa].x) needs[k] = false;
                         }
                     }
                 }
@@ -519,6 +578,9 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     if (nm) adv = 8 * k + __ffs(nm) - 1;
                 }
                 base -= adv;
+#ifdef FSLRC_WALKPROF
+                wp_n64++;
+#endif
                 if (adv < 64) wide = false;
                 if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
                 d_fsteps++;
@@ -619,7 +681,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 }
                 if (gl == 0) { d_steps++; d_stall += stalled; }
                 d_fsteps++; d_fstall += stalled;
-                if (dbg && stalled && d_fstall == 5000 && (U & 1u) && gl == 0) {   // lane 0 is the undecided candidate
+                if (dbg && !FSLRC_WALKPROF_ON && stalled && d_fstall == 5000 && (U & 1u) && gl == 0) {   // lane 0 is the undecided candidate
                     if (atomicAdd(dbg + 12, 1ull) == 0) {
                         const int wb2 = __ldg(&t.SR1[base]).w; const int ob = (int)((unsigned)wb2 >> 6);
                         dbg[13] = a; dbg[14] = b; dbg[15] = (unsigned)ld_relaxed(&stop[ob]); dbg[16] = (unsigned)ld_relaxed(&stop[ob + 1]);
@@ -644,9 +706,18 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     sStop[grp][fi] = stopf; st_relaxed(&stop[offa + fi], stopf); st_relaxed(&stopS[posf], stopf);
                     if (La <= 4) ((int *)&sRecStop[grp][a & (RG_REC - 1)])[fi] = stopf;
                 }
+#ifdef FSLRC_WALKPROF
+                if (dbg && gl == 0 && top - stopf > 100000) {                      // (profiling build: the longest walk by distance)
+                    if (atomicMax(dbg + 4, (unsigned long long)(top - stopf)) < (unsigned long long)(top - stopf)) {
+#else
                 if (dbg && gl == 0 && d_fsteps > 2000) {
                     if (atomicMax(dbg + 4, (unsigned long long)d_fsteps) < (unsigned long long)d_fsteps) {
+#endif
                         dbg[5] = a; dbg[6] = fi; dbg[7] = top - lo; dbg[8] = d_fstall; dbg[9] = top - stopf; dbg[10] = edges; dbg[11] = La;
+#ifdef FSLRC_WALKPROF
+                        { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                          dbg[12] = 1; dbg[13] = g - (unsigned long long)wp_t0; dbg[14] = wp_nw; dbg[15] = wp_cw; dbg[16] = wp_nn; dbg[17] = wp_cn; dbg[18] = wp_n64; dbg[19] = wp_c1; dbg[20] = wp_c2; }
+#endif
                     }
                 }
                 d_fsteps = 0; d_fstall = 0;
@@ -677,9 +748,9 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
 #ifndef RL_MINB
 #define RL_MINB 24              // 48 warps per SM at 40 registers (a few spilled words) beat 32 warps at 62: measured 1.21 vs 1.34 ms
 #endif
-__global__ void __launch_bounds__(RL_WARPS * 32, RL_MINB) k_replay_list(Tab t, int nP, const int *__restrict__ plist, int nRuns,
+__global__ void __launch_bounds__(RL_WARPS * 32, RL_MINB) k_replay_list(Tab t, int nP, const int4 *__restrict__ RH, int nRuns,
                                                                   const int *__restrict__ rstart, const int *__restrict__ isP,
-                                                                  const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
+                                                                  const int4 *__restrict__ PL, int *stop,
                                                                   int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
                                                                   unsigned long long cap_pedges, int *err, unsigned long long *dbg) {
     const unsigned FULL = 0xffffffffu;
@@ -698,18 +769,17 @@ __global__ void __launch_bounds__(RL_WARPS * 32, RL_MINB) k_replay_list(Tab t, i
             tk = (unsigned)__ldg(&rstart[run]);
             tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
         }
-        const int a = __ldg(&plist[tk]);
-        const int wa = __ldg(&t.RI[a]).w;
-        const PLInfo pi = plinfo[a];
+        int4 hd = make_int4(0, 0, 0, 0);                                            // the read's header: lanes 0..2 load 16 bytes each
+        if (lane < 3) hd = __ldg(&RH[3 * (size_t)tk + lane]);
+        const int a = __shfl_sync(FULL, hd.x, 0), wa = __shfl_sync(FULL, hd.y, 0);
+        const unsigned hlo = (unsigned)__shfl_sync(FULL, hd.z, 0), hhi = (unsigned)__shfl_sync(FULL, hd.w, 0);
+        struct { unsigned long long off; int n; } pi;
+        pi.off = ((unsigned long long)(hhi & 0xffu) << 32) | hlo; pi.n = (int)hhi >> 8;
         const int offa = (int)((unsigned)wa >> 6), La = (wa & 63) + 1;
         if (pi.n < 0 || pi.n > RP_K || La > 4) { if (lane == 0) atomicOr(err, EF_OVERFLOW); break; }   // (cannot happen: the host picks k_replay then)
-        // lanes 0..La-1 hold a's fillings: chromosome (for the scan's lower end) and {pos, ub}
-        int myc = 0, mypos = 0;
-        if (lane < La) { myc = rm0(t, offa + lane).x; mypos = rm1(t, offa + lane).x; }
-        if (lane < La) myc = __ldg(&t.chrom_lo[myc]);
         int posA[4], loA[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) { posA[g] = __shfl_sync(FULL, mypos, g); loA[g] = __shfl_sync(FULL, myc, g); }
+        posA[0] = __shfl_sync(FULL, hd.x, 1); posA[1] = __shfl_sync(FULL, hd.y, 1); posA[2] = __shfl_sync(FULL, hd.z, 1); posA[3] = __shfl_sync(FULL, hd.w, 1);
+        loA[0] = __shfl_sync(FULL, hd.x, 2); loA[1] = __shfl_sync(FULL, hd.y, 2); loA[2] = __shfl_sync(FULL, hd.z, 2); loA[3] = __shfl_sync(FULL, hd.w, 2);
         // one partner per lane and slot: {b | edge << 31, off_b << 6 | L_b - 1, cg, flags}, {key[0..3]}
         int4 p0[RL_SLOTS], p1[RL_SLOTS];
 #pragma unroll
@@ -719,9 +789,12 @@ __global__ void __launch_bounds__(RL_WARPS * 32, RL_MINB) k_replay_list(Tab t, i
             if (j < pi.n) { p0[s] = __ldg(&PL[2 * (pi.off + j)]); p1[s] = __ldg(&PL[2 * (pi.off + j) + 1]); }
         }
 #pragma unroll
-        for (int s = 0; s < RL_SLOTS; s++) {
-            const int j = s * 32 + lane;
-            if (j < pi.n) { const int b = p0[s].x & QMASK; p0[s].w = (b < a && !__ldg(&isP[b])) ? 1 : 0; }   // b < a and never breaking: it saw the pair
+        for (int s = 0; s < RL_SLOTS; s++) {                                        // b < a and never breaking: it saw the pair (k_plist
+            const int j = s * 32 + lane;                                            //  resolved it: PLF_KNOWN; k_pair's records are looked up)
+            if (j < pi.n) {
+                const int b = p0[s].x & QMASK;
+                p0[s].w = (p0[s].w & PLF_KNOWN) ? (p0[s].w & 1) : ((b < a && !__ldg(&isP[b])) ? 1 : 0);
+            }
         }
         int edges = 0;
         for (int fi = 0; fi < La;) {                                               // one filling's scan per step (retried while it depends on

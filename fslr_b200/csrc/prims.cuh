@@ -195,8 +195,17 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan_segmax(const int *__restric
 }
 
 // ---------------------------------------------------------------- one-sweep LSD radix sort of (u32 key, i32 value) pairs
-constexpr int RS_THREADS = 512;
-constexpr int RS_ITEMS = 16;
+#ifndef RS_THREADS_
+#define RS_THREADS_ 512
+#endif
+#ifndef RS_ITEMS_
+#define RS_ITEMS_ 12
+#endif
+#ifndef RS_MINB
+#define RS_MINB 2
+#endif
+constexpr int RS_THREADS = RS_THREADS_;     // (>= 256: thread t < 256 owns digit t)
+constexpr int RS_ITEMS = RS_ITEMS_;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 8192 pairs per tile
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr unsigned RS_AGG = 1u << 30, RS_INC = 2u << 30, RS_MASK = (1u << 30) - 1u;
@@ -238,7 +247,7 @@ struct RsSmem {
     unsigned keys[RS_TILE];
     int vals[RS_TILE];
 };
-__global__ void __launch_bounds__(RS_THREADS, 2) k_rs_onesweep(const unsigned *__restrict__ kin, unsigned *__restrict__ kout,
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) k_rs_onesweep(const unsigned *__restrict__ kin, unsigned *__restrict__ kout,
                                                             const int *__restrict__ vin, int *__restrict__ vout, int n, int shift,
                                                             int mask, const unsigned *__restrict__ gbase, unsigned *status, unsigned *ticket) {
     extern __shared__ __align__(16) unsigned char rs_raw[];
