@@ -238,15 +238,16 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     const bool sibs = t.sib && wLa <= 4;
                     // (every load is issued on a clamped index before any result is touched: a conditional block per position makes
                     //  the compiler consume each record right behind its load — eight serial round trips instead of one)
-                    int wq[8], we[8], ws[8], wv[8];
+                    int wq[8], we[8], ws[8], wv[8], wx[8];
 #pragma unroll
                     for (int k = 0; k < 8; k++) {
                         const int pc = max(wbase - 32 * k - lane, wlo);
                         const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
+                        wx[k] = c0.x | c0.z;                                       // (start, T >= 0: keeps the record ONE 16-byte load)
                         wv[k] = sibs ? __ldg(&t.sib[pc]) : 0;
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; k++) wq[k] = (wbase - 32 * k - lane >= wlo) ? (wq[k] & QMASK) : -1;
+                    for (int k = 0; k < 8; k++) wq[k] = (wbase - 32 * k - lane >= wlo && wx[k] >= 0) ? (wq[k] & QMASK) : -1;
                     if (pmx < wfy) { if ((lane >> 3) == sel) wide = false; continue; }     // the walk is over: the normal path closes it
                     bool needs[8];
 #pragma unroll
@@ -533,15 +534,16 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 // provably saw a first (its scan of this very interval already passed a's filling), 64 positions per step
                 int adv = 64;
                 const bool sibs = t.sib && La <= 4;
-                int wq[8], we[8], ws[8], wv[8];                                    // all 24 loads of the step are issued (on clamped indices)
+                int wq[8], we[8], ws[8], wv[8], wx[8];                             // all 24 loads of the step are issued (on clamped indices)
 #pragma unroll
                 for (int k = 0; k < 8; k++) {                                      //  before any result is touched
                     const int pc = max(base - 8 * k - gl, lo);
                     const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
+                    wx[k] = c0.x | c0.z;                                           // (start, T >= 0: keeps the record ONE 16-byte load)
                     wv[k] = sibs ? __ldg(&t.sib[pc]) : 0;
                 }
 #pragma unroll
-                for (int k = 0; k < 8; k++) wq[k] = (base - 8 * k - gl >= lo) ? (wq[k] & QMASK) : -1;
+                for (int k = 0; k < 8; k++) wq[k] = (base - 8 * k - gl >= lo && wx[k] >= 0) ? (wq[k] & QMASK) : -1;
                 bool needs[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++)
