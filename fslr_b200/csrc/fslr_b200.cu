@@ -581,13 +581,16 @@ static int pipe_replay_union(fslrc_ctx *ctx, Pipe *P, int shard, int nshard, con
         r = read_counts(ctx, P); if (r) return r;
         const int nRuns = (int)ctx->h_pin[12];
         int blocks = std::min(nblk(nRuns, RG_GROUPS), replay_blocks_max);
+        int *wboard = nullptr;                                               // job board of the long skip walks (kernels_replay.cuh)
+        if (walk) { DA(wboard, WB_SLOTS * WB_STRIDE); CK(cudaMemsetAsync(wboard, 0, sizeof(int) * WB_SLOTS * WB_STRIDE, st)); }
         if (walk && D > 0) {
             int *sib; DA(sib, D);
             KL(k_sib, nblk(D, TB), TB, D, P->SR0, P->SR1, P->RM, sib);
             P->tab.sib = sib;
         }
 #define REPLAY_ARGS P->tab, P->um, nP, P->plist, nRuns, rstart, P->isP, P->PL, P->plinfo, P->stop, P->stopS, P->ticket, P->pedges, \
-                    (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16)
+                    (unsigned long long *)(P->cnt + 7), P->cap_pedges, (unsigned long long *)(P->cnt + 4), P->err, (unsigned long long *)(P->cnt + 16), \
+                    wboard, (unsigned *)(P->cnt + 51), (unsigned *)(P->cnt + 49), (unsigned long long *)(P->cnt + 50)
         if (!(P->pr.overlap > 0.0)) KL((k_replay<true, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (walk) KL((k_replay<false, true>), blocks, RG_WARPS * 32, REPLAY_ARGS);
         else if (getenv("FSLRC_REPLAY_GROUPS")) KL((k_replay<false, false>), std::min(nblk(nRuns, RG_GROUPS), n_sms(ctx) * 16), RG_WARPS * 32, REPLAY_ARGS);
@@ -639,8 +642,8 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     s->edges = h[8]; s->components = h[9]; s->clustered_reads = (int64_t)P->R - h[11];
     s->partner_records = h[42];
     s->no_clusters = h[9] == 0;
-    if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld, walk-mode reads %lld\n",
-                                       (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12], (long long)h[43]);
+    if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld, walk-mode reads %lld, skip chunks done by helper warps %lld\n",
+                                       (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12], (long long)h[43], (long long)h[50]);
 #ifdef FSLRC_WALKPROF
     if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] walkprof: %.3f ms; warp-wide steps %lld (%.0f cycles each), other iterations %lld (%.0f cycles each), group-wide steps %lld; inside a warp-wide step: %.0f cycles to the first-round results, %.0f to the sibling results\n",
                                        1e-6 * (double)h[29], (long long)h[30], (double)h[31] / (double)std::max<long long>(h[30], 1), (long long)h[32],

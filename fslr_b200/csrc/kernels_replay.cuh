@@ -140,6 +140,225 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *umax, c
     }
     return RF_TESTED | RF_REACH | ((La + Lb - n) <= umax[n] ? RF_EDGE : 0);
 }
+// ---------------------------------------------------------------- job board of the long skip walks (WALK replay)
+// The tail of a giant clique is a few reads whose scans skip through the whole island (every earlier read saw them first):
+// sequential in the reference, and one warp covers only 256 positions per ~3.5 us round trip.  The chunks of such a walk are
+// independent of each other ("does any position of this chunk need an evaluation?"), so the walker posts the next WB_CHUNKS
+// chunks on a board in global memory and every warp of the grid that ran out of tickets works them off (wide_help).
+// Slot words: [0] lock, [1] seq (published job id), [2] (seq & 0xffff) << 16 | next chunk, [3] chunks of the job,
+// [4] chunks done by others, [5] base, [6..11] a, lo, posf, La, start of the filling, sibling flag, [16..43] a's fillings,
+// [64..] result per chunk (first position of the chunk that needs an evaluation, 256 = none).
+#define WB_SLOTS 64
+#define WB_STRIDE 192
+#ifndef WB_CHUNKS
+#define WB_CHUNKS 64
+#endif
+struct WJob { int wa, wlo, wposf, wLa, wfy, sibs; int4 A0[4]; int A1x[4]; int2 Achr[4]; };
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 ld_relaxed_v4(const int *p) {
+    int4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// one chunk = the 256 positions cb, cb - 1, ..: where (counted from cb) is the first one whose candidate a's scan has to
+// evaluate — anything that is no candidate at all, or whose read provably saw a first (its scan of this very interval, or of
+// its other filling, already passed a's filling), is skipped.  All loads are issued on clamped indices before any result is
+// touched (a conditional block per position makes the compiler consume each record right behind its load: eight serial
+// round trips instead of one); the record stays ONE 16-byte load because all four words are used.
+__device__ __forceinline__ int wide_chunk(const Tab &t, const int *stopS, const WJob &J, int cb, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    int wq[8], we[8], ws[8], wv[8], wx[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int pc = max(cb - 32 * k - lane, J.wlo);
+        const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
+        wx[k] = c0.x | c0.z;                                                       // (start, T >= 0)
+        wv[k] = J.sibs ? __ldg(&t.sib[pc]) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) wq[k] = (cb - 32 * k - lane >= J.wlo && wx[k] >= 0) ? (wq[k] & QMASK) : -1;
+    bool needs[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        needs[k] = wq[k] >= 0 && wq[k] != J.wa && we[k] >= J.wfy && !(wq[k] < J.wa && stop_reached(ws[k]) <= J.wposf);
+    if (J.sibs) {                                                                  // ... or through its other filling (reads of 2 fillings)
+        int sp[8];
+        bool anysp = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            sp[k] = -1;
+            if (needs[k] && wq[k] < J.wa && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
+            anysp |= sp[k] >= 0;
+        }
+        if (__any_sync(FULL, anysp)) {
+            int cs[8], ce[8], cv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int sc = max(sp[k], 0);
+                const int4 c = __ldg(&t.SR0[sc]); cs[k] = c.x; ce[k] = c.y; cv[k] = ld_relaxed(&stopS[sc]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int reach = stop_reached(cv[k]);
+#pragma unroll
+                for (int fa = 0; fa < 4; fa++)
+                    if (sp[k] >= 0 && fa < J.wLa && sp[k] >= J.Achr[fa].x && sp[k] < J.Achr[fa].y && J.A0[fa].y <= ce[k] &&
+                        J.A0[fa].z >= cs[k] && reach <= J.A1x[fa]) needs[k] = false;
+            }
+        }
+    }
+    int adv = 256;
+#pragma unroll
+    for (int k = 7; k >= 0; k--) {
+        const unsigned nm = __ballot_sync(FULL, needs[k]);
+        if (nm) adv = 32 * k + __ffs(nm) - 1;
+    }
+    return adv;
+}
+// a free slot for this warp's walk (-1: none right now)
+__device__ __forceinline__ int wide_job_claim(int *wboard, int id, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    int got = -1;
+    for (int r = 0; r < WB_SLOTS / 32 && got < 0; r++) {
+        const int sidx = (id + r * 32 + lane) % WB_SLOTS;
+        const unsigned fm = __ballot_sync(FULL, ld_relaxed(wboard + (size_t)sidx * WB_STRIDE) == 0);
+        if (fm) {
+            const int l = __ffs(fm) - 1;
+            const int cand = __shfl_sync(FULL, sidx, l);
+            int ok = 0;
+            if (lane == 0) ok = atomicCAS(wboard + (size_t)cand * WB_STRIDE, 0, id + 1) == 0;
+            if (__shfl_sync(FULL, ok, 0)) got = cand;
+        }
+    }
+    return got;
+}
+__device__ __forceinline__ void wide_job_release(int *slot, int lane) {
+    if (lane == 0) st_release(slot, 0);
+}
+// publish a job: chunks 1 .. nch - 1 of the walk at wbase are up for grabs (chunk 0 is the owner's); returns the job's tag
+__device__ __forceinline__ int wide_job_post(int *slot, const WJob &J, int wbase, int nch, int lane, unsigned *open_jobs) {
+    int seq = 0;
+    if (lane == 0) {
+        seq = ld_relaxed(slot + 1) + 1;
+        st_relaxed(slot + 4, 0); st_relaxed(slot + 3, nch); st_relaxed(slot + 5, wbase);
+        st_relaxed(slot + 6, J.wa); st_relaxed(slot + 7, J.wlo); st_relaxed(slot + 8, J.wposf); st_relaxed(slot + 9, J.wLa);
+        st_relaxed(slot + 10, J.wfy); st_relaxed(slot + 11, J.sibs);
+#pragma unroll
+        for (int fa = 0; fa < 4; fa++) {
+            st_relaxed(slot + 16 + 4 * fa, J.A0[fa].x); st_relaxed(slot + 17 + 4 * fa, J.A0[fa].y);
+            st_relaxed(slot + 18 + 4 * fa, J.A0[fa].z); st_relaxed(slot + 19 + 4 * fa, J.A0[fa].w);
+            st_relaxed(slot + 32 + fa, J.A1x[fa]);
+            st_relaxed(slot + 36 + 2 * fa, J.Achr[fa].x); st_relaxed(slot + 37 + 2 * fa, J.Achr[fa].y);
+        }
+        st_relaxed(slot + 2, (int)((((unsigned)seq & 0xffffu) << 16) | 1u));        // next chunk to hand out: 1
+        __threadfence();
+        st_release(slot + 1, seq);
+        atomicAdd(open_jobs, 1u);
+    }
+    return __shfl_sync(0xffffffffu, seq, 0);
+}
+// The owner after its own chunk 0 (adv0): works chunks off like everybody else until all are handed out — or closes the job
+// as soon as a chunk found a position that needs an evaluation (or the walk is over: cancel) —, waits for the chunks others
+// took and folds the results in scan order.  Returns the positions skipped.
+__device__ __forceinline__ int wide_job_finish(const Tab &t, const int *stopS, int *slot, const WJob &J, int wbase, int nch, int seq, int adv0,
+                                               bool cancel, int lane, unsigned *open_jobs) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned tag = ((unsigned)seq & 0xffffu) << 16;
+    int mine = 0, limit = nch;
+    bool closing = cancel || adv0 < 256;
+    for (;;) {
+        int v = 0;
+        if (closing) {
+            if (lane == 0) v = atomicExch(slot + 2, (int)(tag | 0x8000u));          // nothing is handed out any more (grabs see c >= nch)
+            limit = min(__shfl_sync(FULL, v, 0) & 0xffff, nch);                     // chunks [1, limit) were
+            break;
+        }
+        if (lane == 0) v = atomicAdd(slot + 2, 1);
+        const int c = __shfl_sync(FULL, v, 0) & 0xffff;
+        if (c >= nch) break;                                                        // all handed out
+        const int r = wide_chunk(t, stopS, J, wbase - 256 * c, lane);
+        if (lane == 0) st_relaxed(slot + 64 + c, r);
+        mine++;
+        if (r < 256) closing = true;
+    }
+    if (lane == 0) { while (ld_acquire(slot + 4) < limit - 1 - mine) __nanosleep(32); }
+    __syncwarp();
+    int total = adv0;
+    if (!cancel && adv0 == 256) {
+        for (int h = 1; h < limit; h++) {
+            const int r = ld_relaxed(slot + 64 + h);
+            total += r;
+            if (r < 256) break;
+        }
+    }
+    if (lane == 0) atomicSub(open_jobs, 1u);
+    return total;
+}
+// a warp without tickets: work chunks off the board until every run of the replay is finished
+__device__ __noinline__ void wide_help(const Tab &t, const int *stopS, int *wboard, unsigned *open_jobs, const unsigned *runs_done, unsigned nRuns,
+                                       int lane, unsigned long long *n_helped) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned rot = (blockIdx.x * 7 + (threadIdx.x >> 5)) % WB_SLOTS;
+    unsigned long long helped = 0;
+    for (;;) {
+        int fin = 0, op = 0;
+        if (lane == 0) { fin = ld_acquire((const int *)runs_done) >= (int)nRuns; op = ld_relaxed((const int *)open_jobs); }
+        fin = __shfl_sync(FULL, fin, 0); op = __shfl_sync(FULL, op, 0);
+        if (fin) break;
+        if (op <= 0) { __nanosleep(4000); continue; }
+        // a slot with chunks left (two slots per lane, rotated so that the helpers spread over the walks)
+        int pick = -1;
+        for (int r = 0; r < WB_SLOTS / 32 && pick < 0; r++) {
+            const int sidx = (rot + r * 32 + lane) % WB_SLOTS;
+            const int4 hd = ld_relaxed_v4(wboard + (size_t)sidx * WB_STRIDE);   // {lock, seq, counter, chunks}
+            const bool avail = hd.x != 0 && (hd.z & 0xffff) < hd.w;
+            const unsigned am = __ballot_sync(FULL, avail);
+            if (am) pick = __shfl_sync(FULL, sidx, __ffs(am) - 1);
+        }
+        if (pick < 0) { __nanosleep(1500); continue; }
+        rot = (unsigned)pick;
+        int *slot = wboard + (size_t)pick * WB_STRIDE;
+        for (;;) {                                                                  // chunks of this walk while there are any
+            int v = 0;
+            if (lane == 0) v = atomicAdd(slot + 2, 1);
+            v = __shfl_sync(FULL, v, 0);
+            const int c = v & 0xffff;
+            const unsigned tag = (unsigned)v >> 16;
+            int seq = 0, nch = 0;
+            if (lane == 0) {                                                        // the job this chunk belongs to: published yet? gone already?
+                for (;;) {
+                    seq = ld_acquire(slot + 1);
+                    if (((unsigned)seq & 0xffffu) == tag) { nch = ld_relaxed(slot + 3); break; }
+                    if ((((unsigned)seq + 1u) & 0xffffu) == tag) { __nanosleep(20); continue; }   // (counter written, seq not yet)
+                    nch = 0; break;                                                 // a job of the past
+                }
+            }
+            nch = __shfl_sync(FULL, nch, 0);
+            if (c >= nch) break;
+            WJob J;
+            const int wbase = ld_relaxed(slot + 5);
+            J.wa = ld_relaxed(slot + 6); J.wlo = ld_relaxed(slot + 7); J.wposf = ld_relaxed(slot + 8); J.wLa = ld_relaxed(slot + 9);
+            J.wfy = ld_relaxed(slot + 10); J.sibs = ld_relaxed(slot + 11);
+#pragma unroll
+            for (int fa = 0; fa < 4; fa++) {
+                J.A0[fa] = make_int4(ld_relaxed(slot + 16 + 4 * fa), ld_relaxed(slot + 17 + 4 * fa), ld_relaxed(slot + 18 + 4 * fa), ld_relaxed(slot + 19 + 4 * fa));
+                J.A1x[fa] = ld_relaxed(slot + 32 + fa);
+                J.Achr[fa] = make_int2(ld_relaxed(slot + 36 + 2 * fa), ld_relaxed(slot + 37 + 2 * fa));
+            }
+            const int r = wide_chunk(t, stopS, J, wbase - 256 * c, lane);
+            if (lane == 0) { st_relaxed(slot + 64 + c, r); __threadfence(); atomicAdd(slot + 4, 1); }
+            helped++;
+        }
+    }
+    if (lane == 0 && helped && n_helped) atomicAdd(n_helped, helped);
+}
 // Two ways to re-run one read's query:
 //   LIST mode (the normal case): the only candidates that can ever matter to a's query are intervals of reads b that share
 //     a reciprocally overlapping filling pair with a (n_i > 0, cluster.py:216) — everything else is skipped by the reference
@@ -178,7 +397,8 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                                                            const int4 *__restrict__ PL, const PLInfo *__restrict__ plinfo, int *stop,
                                                            int *stopS, unsigned *ticket, int2 *pedges, unsigned long long *n_slots,
                                                            unsigned long long cap_pedges, unsigned long long *n_tests, int *err,
-                                                           unsigned long long *dbg) {
+                                                           unsigned long long *dbg, int *wboard, unsigned *open_jobs, unsigned *runs_done,
+                                                           unsigned long long *n_helped) {
     __shared__ int4 sA0[RG_GROUPS][4];
     __shared__ int2 sA1[RG_GROUPS][4];
     __shared__ int sStop[RG_GROUPS][WALK ? LMAX : 1];                              // (WALK mode only)
@@ -197,7 +417,9 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
     unsigned tk = 0, tk1 = 0;
     int a = 0, offa = 0, La = 0, fi = 0, edges = 0, top = 0, lo = 0, base = 0, posf = 0;
     int nPart = 0;
-    bool wide = false, parked = false;
+    bool wide = false, parked = false, hasrun = false;
+    int wnch = 1;                       // chunks the group's skip walk asks for per step (doubles while it keeps skipping)
+    int wslot = -1;                     // the warp's slot on the job board (-1: none)
     int4 ria = make_int4(0, 0, 0, 0), f = make_int4(0, 0, 0, 0);
     unsigned long long tests = 0, chunk_base = 0;
     unsigned long long d_iter = 0, d_steps = 0, d_stall = 0, d_sleep = 0;
@@ -219,85 +441,44 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
 #endif
         if (WALK) {
             // ---- every group of this warp that still has work is skipping through a long band (the tail of a giant clique):
-            // serve one of them with all 32 lanes, 256 positions per step (a lone 8-lane walker is instruction-latency bound)
+            // serve one of them with all 32 lanes, 256 positions per chunk (a lone 8-lane walker is instruction-latency bound).
             // A group between two runs takes no new ticket while another group of its warp is deep in such a walk (other warps
-            // take the tickets): the walker then owns all 32 lanes instead of sharing every loop iteration with three groups
-            // that evaluate candidates (measured at C5: 8 us per 64-position step shared, ~2 us per 256-position step alone).
+            // take the tickets): the walker owns the warp.  A walk that keeps skipping posts its next chunks on the job board
+            // (wide_job_*): warps that ran out of tickets anywhere on the GPU work them off, so the sequential tail of a 500k-read
+            // clique advances up to WB_CHUNKS * 256 positions per step instead of 256.
             parked = __ballot_sync(FULL, phase == 2 && wide && d_fsteps > RG_PARK) != 0 && phase == 0 && tk == tk1;
             const unsigned actm = __ballot_sync(FULL, phase != 3 && !parked), widem = __ballot_sync(FULL, phase == 2 && wide);
             if (actm != 0 && widem == actm) {
                 const unsigned gm = ((actm >> 0) & 1u) | (((actm >> 8) & 1u) << 1) | (((actm >> 16) & 1u) << 2) | (((actm >> 24) & 1u) << 3);
                 const int sel = __fns(gm, 0, (wit % __popc(gm)) + 1);              // round robin over the walking groups
                 const int src = sel * 8, wgrp = w * 4 + sel;
-                const int wa = __shfl_sync(FULL, a, src), wlo = __shfl_sync(FULL, lo, src), wbase = __shfl_sync(FULL, base, src);
-                const int wposf = __shfl_sync(FULL, posf, src), wLa = __shfl_sync(FULL, La, src), wfy = __shfl_sync(FULL, f.y, src);
-                if (wbase >= wlo) {
-                    // one round trip for everything a position can say by itself: its record, its own stop, where its read's other
-                    // filling sits — and the prefix max that tells whether anything at or below wbase still overlaps the filling
+                WJob J;
+                J.wa = __shfl_sync(FULL, a, src); J.wlo = __shfl_sync(FULL, lo, src);
+                J.wposf = __shfl_sync(FULL, posf, src); J.wLa = __shfl_sync(FULL, La, src); J.wfy = __shfl_sync(FULL, f.y, src);
+                const int wbase = __shfl_sync(FULL, base, src);
+                int nch = __shfl_sync(FULL, wnch, src);
+                if (wbase >= J.wlo) {
                     const int pmx = __ldg(&t.pmaxS[wbase]);
-                    const bool sibs = t.sib && wLa <= 4;
-                    // (every load is issued on a clamped index before any result is touched: a conditional block per position makes
-                    //  the compiler consume each record right behind its load — eight serial round trips instead of one)
-                    int wq[8], we[8], ws[8], wv[8], wx[8];
+                    J.sibs = (t.sib && J.wLa <= 4) ? 1 : 0;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const int pc = max(wbase - 32 * k - lane, wlo);
-                        const int4 c0 = __ldg(&t.SR0[pc]); wq[k] = c0.w; we[k] = c0.y; ws[k] = ld_relaxed(&stopS[pc]);
-                        wx[k] = c0.x | c0.z;                                       // (start, T >= 0: keeps the record ONE 16-byte load)
-                        wv[k] = sibs ? __ldg(&t.sib[pc]) : 0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; k++) wq[k] = (wbase - 32 * k - lane >= wlo && wx[k] >= 0) ? (wq[k] & QMASK) : -1;
-                    if (pmx < wfy) { if ((lane >> 3) == sel) wide = false; continue; }     // the walk is over: the normal path closes it
-                    bool needs[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++)
-                        needs[k] = wq[k] >= 0 && wq[k] != wa && we[k] >= wfy && !(wq[k] < wa && stop_reached(ws[k]) <= wposf);
-#ifdef FSLRC_WALKPROF
-                    { bool any = false;
-#pragma unroll
-                      for (int k = 0; k < 8; k++) any |= needs[k];
-                      const long long now = clock64(); if (__any_sync(FULL, any) || true) { if ((lane >> 3) == sel) wp_c1 += now - wp_it0; } }
-#endif
-                    if (sibs) {
-                        int sp[8];
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            sp[k] = -1;
-                            if (needs[k] && wq[k] < wa && ((unsigned)wv[k] >> 26) == 1u) sp[k] = wv[k] & QMASK;
-                        }
-                        int cs[8], ce[8], cv[8];
-                        bool anysp = false;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) anysp |= sp[k] >= 0;
-                        if (__any_sync(FULL, anysp)) {
-#pragma unroll
-                            for (int k = 0; k < 8; k++) {                          // (same rule: all loads first)
-                                const int sc = max(sp[k], 0);
-                                const int4 c = __ldg(&t.SR0[sc]); cs[k] = c.x; ce[k] = c.y; cv[k] = ld_relaxed(&stopS[sc]);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 8; k++) {
-                                const int reach = stop_reached(cv[k]);
-#pragma unroll
-                                for (int fa = 0; fa < 4; fa++)
-                                    if (sp[k] >= 0 && fa < wLa && sp[k] >= sAchr[wgrp][fa].x && sp[k] < sAchr[wgrp][fa].y && sA0[wgrp][fa].y <= ce[k] &&
-                                        sA0[wgrp][fa].z >= cs[k] && reach <= sA1[wgrp][fa].x) needs[k] = false;
-                            }
-                        }
-                    }
-#ifdef FSLRC_WALKPROF
-                    { const long long now = clock64(); if ((lane >> 3) == sel) wp_c2 += now - wp_it0; }
-#endif
-                    int adv = 256;
-#pragma unroll
-                    for (int k = 7; k >= 0; k--) {
-                        const unsigned nm = __ballot_sync(FULL, needs[k]);
-                        if (nm) adv = 32 * k + __ffs(nm) - 1;
+                    for (int fa = 0; fa < 4; fa++) { J.A0[fa] = sA0[wgrp][fa]; J.A1x[fa] = sA1[wgrp][fa].x; J.Achr[fa] = sAchr[wgrp][fa]; }
+                    nch = min(nch, (wbase - J.wlo) / 256 + 1);
+                    if (nch > 1 && wslot < 0) wslot = wide_job_claim(wboard, blockIdx.x * RG_WARPS + w, lane);
+                    if (wslot < 0) nch = 1;
+                    int jseq = 0;
+                    if (nch > 1) jseq = wide_job_post(wboard + (size_t)wslot * WB_STRIDE, J, wbase, nch, lane, open_jobs);
+                    const int adv = wide_chunk(t, stopS, J, wbase, lane);           // chunk 0 is always the owner's
+                    const bool over = pmx < J.wfy;                                 // the walk is over: the normal path closes it
+                    int total = adv;
+                    if (nch > 1) total = wide_job_finish(t, stopS, wboard + (size_t)wslot * WB_STRIDE, J, wbase, nch, jseq, adv, over, lane, open_jobs);
+                    if (over) {
+                        if ((lane >> 3) == sel) { wide = false; wnch = 1; }
+                        continue;
                     }
                     if ((lane >> 3) == sel) {
-                        base -= adv;
-                        if (adv < 256) wide = false;
+                        base -= total;
+                        if (total < 256 * nch) { wide = false; wnch = 1; }
+                        else wnch = min(2 * nch, WB_CHUNKS);
                         if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
                         d_fsteps++;
                     }
@@ -307,16 +488,20 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     continue;
                 }
             }
+            else if (wslot >= 0 && widem == 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane); wslot = -1; }
         }
         if (phase == 0 && !(WALK && parked)) {
             if (tk == tk1) {                                                       // run finished: take the next ticket
                 unsigned run = 0;
+                if (WALK && hasrun && gl == 0) { __threadfence(); atomicAdd(runs_done, 1u); }   // (helpers leave when every run is done)
+                hasrun = false;
                 if (gl == 0) run = atomicAdd(ticket, 1u);
                 run = __shfl_sync(gmask, run, gsh);
                 if (run >= (unsigned)nRuns) phase = 3;
                 else {
                     tk = (unsigned)__ldg(&rstart[run]);
                     tk1 = (run + 1 < (unsigned)nRuns) ? (unsigned)__ldg(&rstart[run + 1]) : (unsigned)nP;
+                    hasrun = true;
                 }
             }
             if (phase == 0) {
@@ -357,7 +542,13 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 }
             }
         }
-        if (__all_sync(FULL, phase == 3)) break;
+        if (__all_sync(FULL, phase == 3)) {
+            if (WALK) {
+                if (wslot >= 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane); wslot = -1; }
+                wide_help(t, stopS, wboard, open_jobs, runs_done, (unsigned)nRuns, lane, n_helped);
+            }
+            break;
+        }
         __syncwarp();
         bool stalled = false;
         // ------------------------------------------------------------ LIST mode: one filling's scan over the partners
@@ -518,7 +709,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
             else { f = rm0(t, offa + fi); const int2 pu = rm1(t, offa + fi); posf = pu.x; top = pu.y; }
             lo = __ldg(&t.chrom_lo[f.x]);
             base = top;
-            wide = false;
+            wide = false; wnch = 1;
             phase = 2;
 #ifdef FSLRC_WALKPROF
             { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); wp_t0 = (long long)g; wp_cw = wp_cn = wp_c1 = wp_c2 = 0; wp_nw = wp_nn = wp_n64 = 0; }
