@@ -645,6 +645,9 @@ static void fill_stats(fslrc_ctx *ctx, Pipe *P, fslrc_stats *s) {
     if (getenv("FSLRC_DEBUG")) fprintf(stderr, "[fslrc] replay: warp-iterations %lld, group-steps %lld, stalled %lld, sleeps %lld, runs %lld, walk-mode reads %lld, skip chunks done by helper warps %lld\n",
                                        (long long)h[16], (long long)h[17], (long long)h[18], (long long)h[19], (long long)h[12], (long long)h[43], (long long)h[50]);
 #ifdef FSLRC_WALKPROF
+    if (getenv("FSLRC_DEBUG") && h[43]) fprintf(stderr, "[fslrc] walkprof: runs finished after ms (since the first): 50%% %.3f  90%% %.3f  99%% %.3f  99.9%% %.3f  99.99%% %.3f  all %.3f\n",
+                                       1e-6 * (double)(h[53] - h[52]), 1e-6 * (double)(h[39] - h[52]), 1e-6 * (double)(h[54] - h[52]), 1e-6 * (double)(h[37] - h[52]),
+                                       1e-6 * (double)(h[38] - h[52]), 1e-6 * (double)(h[55] - h[52]));
     if (getenv("FSLRC_DEBUG") && h[28]) fprintf(stderr, "[fslrc] walkprof: %.3f ms; warp-wide steps %lld (%.0f cycles each), other iterations %lld (%.0f cycles each), group-wide steps %lld; inside a warp-wide step: %.0f cycles to the first-round results, %.0f to the sibling results\n",
                                        1e-6 * (double)h[29], (long long)h[30], (double)h[31] / (double)std::max<long long>(h[30], 1), (long long)h[32],
                                        (double)h[33] / (double)std::max<long long>(h[32], 1), (long long)h[34], (double)h[35] / (double)std::max<long long>(h[30], 1), (double)h[36] / (double)std::max<long long>(h[30], 1));

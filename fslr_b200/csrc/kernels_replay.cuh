@@ -149,10 +149,10 @@ __device__ __noinline__ int replay_eval_general(const Tab &t, const int *umax, c
 // [4] chunks done by others, [5] base, [6..11] a, lo, posf, La, start of the filling, sibling flag, [16..43] a's fillings,
 // [64..] result per chunk (first position of the chunk that needs an evaluation, 256 = none).
 #define WB_SLOTS 64
-#define WB_STRIDE 192
 #ifndef WB_CHUNKS
-#define WB_CHUNKS 64
+#define WB_CHUNKS 256
 #endif
+#define WB_STRIDE (64 + WB_CHUNKS)
 struct WJob { int wa, wlo, wposf, wLa, wfy, sibs; int4 A0[4]; int A1x[4]; int2 Achr[4]; };
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
@@ -223,7 +223,7 @@ __device__ __forceinline__ int wide_chunk(const Tab &t, const int *stopS, const 
     return adv;
 }
 // a free slot for this warp's walk (-1: none right now)
-__device__ __forceinline__ int wide_job_claim(int *wboard, int id, int lane) {
+__device__ __forceinline__ int wide_job_claim(int *wboard, int id, int lane, unsigned *open_jobs) {
     const unsigned FULL = 0xffffffffu;
     int got = -1;
     for (int r = 0; r < WB_SLOTS / 32 && got < 0; r++) {
@@ -237,10 +237,11 @@ __device__ __forceinline__ int wide_job_claim(int *wboard, int id, int lane) {
             if (__shfl_sync(FULL, ok, 0)) got = cand;
         }
     }
+    if (got >= 0 && lane == 0) atomicAdd(open_jobs, 1u);                            // (helpers poll the board while any slot is taken)
     return got;
 }
-__device__ __forceinline__ void wide_job_release(int *slot, int lane) {
-    if (lane == 0) st_release(slot, 0);
+__device__ __forceinline__ void wide_job_release(int *slot, int lane, unsigned *open_jobs) {
+    if (lane == 0) { st_release(slot, 0); atomicSub(open_jobs, 1u); }
 }
 // publish a job: chunks 1 .. nch - 1 of the walk at wbase are up for grabs (chunk 0 is the owner's); returns the job's tag
 __device__ __forceinline__ int wide_job_post(int *slot, const WJob &J, int wbase, int nch, int lane, unsigned *open_jobs) {
@@ -260,7 +261,6 @@ __device__ __forceinline__ int wide_job_post(int *slot, const WJob &J, int wbase
         st_relaxed(slot + 2, (int)((((unsigned)seq & 0xffffu) << 16) | 1u));        // next chunk to hand out: 1
         __threadfence();
         st_release(slot + 1, seq);
-        atomicAdd(open_jobs, 1u);
     }
     return __shfl_sync(0xffffffffu, seq, 0);
 }
@@ -291,14 +291,19 @@ __device__ __forceinline__ int wide_job_finish(const Tab &t, const int *stopS, i
     if (lane == 0) { while (ld_acquire(slot + 4) < limit - 1 - mine) __nanosleep(32); }
     __syncwarp();
     int total = adv0;
-    if (!cancel && adv0 == 256) {
-        for (int h = 1; h < limit; h++) {
-            const int r = ld_relaxed(slot + 64 + h);
-            total += r;
-            if (r < 256) break;
+    if (!cancel && adv0 == 256) {                                                  // fold in scan order: 32 results per round trip
+        for (int h0 = 1; h0 < limit; h0 += 32) {
+            const int h = h0 + lane;
+            const int r = h < limit ? ld_relaxed(slot + 64 + h) : 0;
+            const unsigned stopm = __ballot_sync(FULL, r < 256);                    // (lanes past the limit stop the fold too)
+            if (stopm) {
+                const int l = __ffs(stopm) - 1;
+                total += 256 * l + (h0 + l < limit ? __shfl_sync(FULL, r, l) : 0);
+                break;
+            }
+            total += 256 * 32;
         }
     }
-    if (lane == 0) atomicSub(open_jobs, 1u);
     return total;
 }
 // a warp without tickets: work chunks off the board until every run of the replay is finished
@@ -322,7 +327,7 @@ __device__ __noinline__ void wide_help(const Tab &t, const int *stopS, int *wboa
             const unsigned am = __ballot_sync(FULL, avail);
             if (am) pick = __shfl_sync(FULL, sidx, __ffs(am) - 1);
         }
-        if (pick < 0) { __nanosleep(1500); continue; }
+        if (pick < 0) { __nanosleep(400); continue; }
         rot = (unsigned)pick;
         int *slot = wboard + (size_t)pick * WB_STRIDE;
         for (;;) {                                                                  // chunks of this walk while there are any
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
 #pragma unroll
                     for (int fa = 0; fa < 4; fa++) { J.A0[fa] = sA0[wgrp][fa]; J.A1x[fa] = sA1[wgrp][fa].x; J.Achr[fa] = sAchr[wgrp][fa]; }
                     nch = min(nch, (wbase - J.wlo) / 256 + 1);
-                    if (nch > 1 && wslot < 0) wslot = wide_job_claim(wboard, blockIdx.x * RG_WARPS + w, lane);
+                    if (nch > 1 && wslot < 0) wslot = wide_job_claim(wboard, blockIdx.x * RG_WARPS + w, lane, open_jobs);
                     if (wslot < 0) nch = 1;
                     int jseq = 0;
                     if (nch > 1) jseq = wide_job_post(wboard + (size_t)wslot * WB_STRIDE, J, wbase, nch, lane, open_jobs);
@@ -478,7 +483,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     if ((lane >> 3) == sel) {
                         base -= total;
                         if (total < 256 * nch) { wide = false; wnch = 1; }
-                        else wnch = min(2 * nch, WB_CHUNKS);
+                        else wnch = min(4 * nch, WB_CHUNKS);
                         if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
                         d_fsteps++;
                     }
@@ -488,12 +493,30 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                     continue;
                 }
             }
-            else if (wslot >= 0 && widem == 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane); wslot = -1; }
+            else if (wslot >= 0 && widem == 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane, open_jobs); wslot = -1; }
         }
         if (phase == 0 && !(WALK && parked)) {
             if (tk == tk1) {                                                       // run finished: take the next ticket
                 unsigned run = 0;
-                if (WALK && hasrun && gl == 0) { __threadfence(); atomicAdd(runs_done, 1u); }   // (helpers leave when every run is done)
+                if (WALK && hasrun && gl == 0) {                                   // (helpers leave when every run is done)
+                    __threadfence();
+                    const unsigned dn = atomicAdd(runs_done, 1u) + 1u;
+#ifdef FSLRC_WALKPROF
+                    if (dbg) {                                                     // when were 50 / 90 / 99 / 99.9 / 99.99 / 100 % of the runs finished
+                        unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+                        const unsigned n = (unsigned)nRuns;
+                        if (dn == 1u) dbg[36] = g;                                 // (dbg = cnt + 16: cnt[52..55] and dbg[21..23] are free here)
+                        if (dn == n / 2) dbg[37] = g;
+                        if (dn == n - n / 10) dbg[23] = g;
+                        if (dn == n - n / 100) dbg[38] = g;
+                        if (dn == n - n / 1000) dbg[21] = g;
+                        if (dn == n - n / 10000) dbg[22] = g;
+                        if (dn == n) dbg[39] = g;
+                    }
+#else
+                    (void)dn;
+#endif
+                }
                 hasrun = false;
                 if (gl == 0) run = atomicAdd(ticket, 1u);
                 run = __shfl_sync(gmask, run, gsh);
@@ -544,7 +567,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
         }
         if (__all_sync(FULL, phase == 3)) {
             if (WALK) {
-                if (wslot >= 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane); wslot = -1; }
+                if (wslot >= 0) { wide_job_release(wboard + (size_t)wslot * WB_STRIDE, lane, open_jobs); wslot = -1; }
                 wide_help(t, stopS, wboard, open_jobs, runs_done, (unsigned)nRuns, lane, n_helped);
             }
             break;
