@@ -64,3 +64,23 @@ def test_c3_fullsize_cutoff_sweep(c3_table, cut):
     assert np.array_equal(res.cluster, ocl)
     assert np.array_equal(res.n_reads, onr)
     assert res.stats["components"] == ost["components"]
+
+
+def test_c5_job_board_is_repeatable():
+    """C5's giant clique drives the WALK replay's job board (kernels_replay.cuh: wide_job_* / wide_help): warps without tickets
+    work off chunks of the tail walks, with hand-overs through global memory whose timing differs from run to run.  The result
+    must not: eight more runs of the same table give the ids of the first one (which test_fullsize_vs_oracle pins to the oracle)."""
+    from fslr_b200 import synth
+    from fslr_b200.engine import get_engine
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C5"))
+    p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK["C5"])
+    eng = get_engine(0)
+    first = eng.cluster(t, p)
+    _props(first, t.n_reads)
+    assert first.stats["saturating_reads"] > 500000                # the hotspot is there
+    for _ in range(8):
+        res = eng.cluster(t, p)
+        assert np.array_equal(res.cluster, first.cluster)
+        assert np.array_equal(res.n_reads, first.n_reads)
+        assert res.stats["edges"] == first.stats["edges"]
