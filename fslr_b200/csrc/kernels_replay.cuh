@@ -38,6 +38,10 @@ __device__ __forceinline__ void st_relaxed(int *p, int v) {
 // position >= x has been visited already" (progress of a long walk), STOP_UNSTARTED = nothing known yet.
 #define STOP_UNSTARTED ((int)0x80000000)
 __device__ __forceinline__ int stop_reached(int v) { return v >= 0 ? v : -2 - v; }   // lowest position known to be visited
+// progress of a walk whose next position is `base`: "everything >= base + 1 is visited".  A step can carry base below the
+// chromosome's first position lo (by up to one step); the word must stay a PROGRESS word (<= -2) there — on the first
+// chromosome (lo = 0) -2 - (base + 1) would turn non-negative and read as a final stop.
+__device__ __forceinline__ int progress_word(int base, int lo) { return -2 - max(base + 1, lo); }
 // streak starts: ticket k continues the previous saturating read's streak iff their first fillings reciprocally overlap
 // (same PCR family: they depend on each other).  Also marks the stops of every saturating read as unknown.
 // RH (k_replay_list): per ticket one 48-byte header {a, RI[a].w, PL offset (40 bits), n}, {pos of fillings 0..3}, {chromosome
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                         base -= total;
                         if (total < 256 * nch) { wide = false; wnch = 1; }
                         else wnch = min(4 * nch, WB_CHUNKS);
-                        if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                        if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], progress_word(base, lo)); st_relaxed(&stopS[posf], progress_word(base, lo)); }
                         d_fsteps++;
                     }
 #ifdef FSLRC_WALKPROF
@@ -798,7 +802,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 wp_n64++;
 #endif
                 if (adv < 64) wide = false;
-                if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                if (gl == 0) { d_steps++; st_relaxed(&stop[offa + fi], progress_word(base, lo)); st_relaxed(&stopS[posf], progress_word(base, lo)); }
                 d_fsteps++;
             }
             else {
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32, WALK ? RG_MINB_WALK : RG_MINB) 
                 if (brk >= 0) stopf = base - brk;
                 else {
                     base -= nres; stalled = nres == 0;
-                    if (gl == 0 && nres) { st_relaxed(&stop[offa + fi], -2 - (base + 1)); st_relaxed(&stopS[posf], -2 - (base + 1)); }
+                    if (gl == 0 && nres) { st_relaxed(&stop[offa + fi], progress_word(base, lo)); st_relaxed(&stopS[posf], progress_word(base, lo)); }
                 }
                 if (gl == 0) { d_steps++; d_stall += stalled; }
                 d_fsteps++; d_fstall += stalled;
