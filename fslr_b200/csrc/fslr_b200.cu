@@ -55,6 +55,11 @@ struct fslrc_ctx {
     int blocking;
     struct BamState *bam;    // table produced from a BAM file, kept on the device between fslrc_bam_open and fslrc_bam_close
     long long launches;      // kernels of this library launched since fslrc_create
+    // host calls: the column the first kernels do not read (n_alignments) is uploaded on a second stream BEHIND the others, so the
+    // tail of the upload overlaps keep_fillings (ev_c1: the other copies are done; ev_c2: this one is)
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_c1, ev_c2;
+    bool late_pending;
 };
 
 static void tsv_free(fslrc_ctx *ctx);
@@ -89,6 +94,7 @@ static int dalloc(fslrc_ctx *ctx, T **p, int64_t n) {
     return 0;
 }
 static void free_all(fslrc_ctx *ctx) {
+    if (ctx->late_pending) { cudaStreamWaitEvent(ctx->stream, ctx->ev_c2, 0); ctx->late_pending = false; }   // (an error path got here first)
     for (void *p : ctx->allocs) cudaFreeAsync(p, ctx->stream);
     ctx->allocs.clear();
 }
@@ -120,6 +126,8 @@ struct Pipe {
     // inputs (device)
     fslrc_table tb;
     fslrc_params pr;
+    Widen w_late;            // host calls: the n_alignments column still on its way (ctx->copy_stream); widened by late_columns()
+    bool late;
     int A, R, F, D, Q, nP, Tedge, pair_blocks;
     int *err;
     int64_t *cnt;            // device counters: 0 F,1 D,2 Q,3 band,4 tests,5 entry slots,6 nP,7 pedge slots,8 edges,9 ncl,10 forest,
@@ -278,6 +286,16 @@ static int pipe_chrom_order(fslrc_ctx *ctx, Pipe *P, const int4 *IT0, unsigned *
 
 // ---- stages 1-4, fast form (kernels_ingest.cuh: contiguous reads, no caller `order`).  Returns 1 when the table does not
 // meet the precondition (nothing useful was computed: the caller runs the general path), 0 on success, < 0 on error.
+// the column that was uploaded behind the others (resolve_columns): wait for it and widen it, right before its first reader
+static int late_columns(fslrc_ctx *ctx, Pipe *P) {
+    if (!P->late) return 0;
+    cudaStream_t st = ctx->stream;
+    CK(cudaStreamWaitEvent(st, ctx->ev_c2, 0));
+    ctx->late_pending = false;
+    P->late = false;
+    if (P->A > 0) KL(k_widen, nblk(P->A, 256), 256, (int64_t)P->A, P->w_late);
+    return 0;
+}
 static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, const unsigned char *d_cmask) {
     const fslrc_table &tb = P->tb; const fslrc_params &pr = P->pr;
     cudaStream_t st = ctx->stream;
@@ -307,6 +325,7 @@ static int pipe_ingest_fast(fslrc_ctx *ctx, Pipe *P, const long long *d_clen, co
     int kbits = 32;
     if (D > 0) {
         if (D >= (1 << 26)) return fail(ctx, FSLRC_ERR_RANGE, "more than 2^26 intervals");
+        { int r = late_columns(ctx, P); if (r) return r; }
         KL(k_compact_fast, nblk(A, TB), TB, A, flagA, posA, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size, tb.n_alignments,
            REC, key, val, (unsigned long long *)(P->cnt + 48), P->err);
         // the genome bounds the sort key: 4 passes of 8 bits cover any int32 start, fewer when the chromosome lengths say so
@@ -386,6 +405,7 @@ static int pipe_prepare(fslrc_ctx *ctx, Pipe *P) {
     if (tb.order && tb.n_order != F) return fail(ctx, FSLRC_ERR_ARG, "order has the wrong length (must equal the number of fillings)");
     int4 *FR0; int2 *FR1;
     DA(FR0, F); DA(FR1, F);
+    { int r = late_columns(ctx, P); if (r) return r; }
     if (A > 0) KL(k_fill_records, nblk(A, TB), TB, A, flagA, posA, tb.read_id, tb.chrom, tb.rstart, tb.rend, tb.aln_size, tb.n_alignments,
                   pr.n_chrom, FR0, FR1, P->err);
     { int r = mark(ctx, ST_KEEP); if (r) return r; }
@@ -719,6 +739,17 @@ static int resolve_columns(fslrc_ctx *ctx, Pipe *P, const fslrc_table *in, bool 
     if (in->qend || A == 0) BRING(in->qend, a4, out->qend);
     else { BRING(in->qend_u16, 2 * (size_t)A, w.qe16); DA(w.qend, A); out->qend = w.qend; any = true; }
     if (in->n_alignments || A == 0) BRING(in->n_alignments, a4, out->n_alignments);
+    else if (host && ctx->copy_stream && A >= (1 << 20)) {
+        // the first kernels (keep_fillings) do not read this column: its upload goes LAST, on a second stream, and overlaps them
+        unsigned char *d16; DA(d16, 2 * (size_t)A); DA(w.naln, A); out->n_alignments = w.naln;
+        CK(cudaEventRecord(ctx->ev_c1, st));                                       // (every other column is on its way)
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_c1, 0));
+        CK(cudaMemcpyAsync(d16, in->n_alignments_u16, 2 * (size_t)A, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_c2, ctx->copy_stream));
+        memset(&P->w_late, 0, sizeof(P->w_late));
+        P->w_late.n16 = (const unsigned short *)d16; P->w_late.naln = w.naln;
+        P->late = true; ctx->late_pending = true;
+    }
     else { BRING(in->n_alignments_u16, 2 * (size_t)A, w.n16); DA(w.naln, A); out->n_alignments = w.naln; any = true; }
     if (in->aln_size || A == 0) BRING(in->aln_size, a4, out->aln_size);
     else {                                                                         // aln_size = qend - qstart (check_args saw the flag)
@@ -759,6 +790,10 @@ int fslrc_create(int device, fslrc_ctx **out) {
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     ctx->blocking = 0;
+    ctx->copy_stream = nullptr; ctx->late_pending = false;
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->copy_stream = nullptr; cudaGetLastError(); }
+    cudaEventCreateWithFlags(&ctx->ev_c1, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_c2, cudaEventDisableTiming);
     cudaFuncSetAttribute(prims::k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(prims::RsSmem));
     cudaMemPool_t pool;                                   // keep freed scratch cached between calls
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -778,6 +813,8 @@ void fslrc_destroy(fslrc_ctx *ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i <= FSLRC_N_STAGES; i++) cudaEventDestroy(ctx->ev[i]);
     cudaEventDestroy(ctx->ev_block);
+    cudaEventDestroy(ctx->ev_c1); cudaEventDestroy(ctx->ev_c2);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     delete ctx->pipe;
     delete ctx;

@@ -156,3 +156,31 @@ def test_narrow_wire_columns_match():
     eng.run_resident(dw, t, p)
     assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), dw.out_cluster[:t.n_reads].cpu().numpy())
     assert np.array_equal(wide.out_n_reads[:t.n_reads].numpy(), dw.out_n_reads[:t.n_reads].cpu().numpy())
+
+
+def test_late_column_upload_and_its_error_path():
+    """Host calls with the wire format upload n_alignments behind the other columns on a second stream (tables of >= 2^20 rows;
+    resolve_columns / late_columns): same result as the int32 columns, and a call that fails before the column's first reader
+    (here: a negative coordinate found by keep_fillings) neither hangs nor disturbs the next call."""
+    import pytest
+    from fslr_b200 import synth
+    from fslr_b200._native import FslrError
+    from fslr_b200.engine import PinnedTable, get_engine
+    from fslr_b200.table import ClusterParams, ColumnarTable
+    t = ColumnarTable.from_synth(synth.make_config("C3", 0.3))
+    assert t.n_rows >= (1 << 20)
+    p = ClusterParams.from_options(t, cluster_mask=synth.CONFIG_MASK["C3"])
+    eng = get_engine(0)
+    wide, narrow = PinnedTable(t), PinnedTable(t, compact=True)
+    eng.run_host(wide, t, p)
+    eng.run_host(narrow, t, p)
+    assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), narrow.out_cluster[:t.n_reads].numpy())
+    assert np.array_equal(wide.out_n_reads[:t.n_reads].numpy(), narrow.out_n_reads[:t.n_reads].numpy())
+    keep = narrow.cols["rstart"][:40].clone()
+    narrow.cols["rstart"][:40] = -100000                                        # (40 rows: some of them are fillings)
+    with pytest.raises(FslrError):
+        eng.run_host(narrow, t, p)
+    narrow.cols["rstart"][:40] = keep
+    narrow.out_cluster.zero_()
+    eng.run_host(narrow, t, p)
+    assert np.array_equal(wide.out_cluster[:t.n_reads].numpy(), narrow.out_cluster[:t.n_reads].numpy())
