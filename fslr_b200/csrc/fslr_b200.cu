@@ -739,8 +739,10 @@ static int resolve_columns(fslrc_ctx *ctx, Pipe *P, const fslrc_table *in, bool 
     if (in->qend || A == 0) BRING(in->qend, a4, out->qend);
     else { BRING(in->qend_u16, 2 * (size_t)A, w.qe16); DA(w.qend, A); out->qend = w.qend; any = true; }
     if (in->n_alignments || A == 0) BRING(in->n_alignments, a4, out->n_alignments);
-    else if (host && ctx->copy_stream && A >= (1 << 20)) {
+    else if (host && ctx->copy_stream && !ctx->blocking && A >= (1 << 20)) {
         // the first kernels (keep_fillings) do not read this column: its upload goes LAST, on a second stream, and overlaps them
+        // (not for the contexts of a HostPipeline — blocking-sync waits —: there the whole upload already overlaps the kernels of
+        // the table before; a second copy stream per context would only reorder the DMA queue)
         unsigned char *d16; DA(d16, 2 * (size_t)A); DA(w.naln, A); out->n_alignments = w.naln;
         CK(cudaEventRecord(ctx->ev_c1, st));                                       // (every other column is on its way)
         CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_c1, 0));
